@@ -1,0 +1,157 @@
+/* hvx_oracle.h -- CPU ORACLE for the Transvoxel chunk-extraction hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, bench.py's
+ * cpu_baseline / --impl reference legs and __graft_entry__.smoke() may load it.
+ * The shipped library (libhelio_voxel_cuda.so) never links, loads or calls it.
+ *
+ * It is a plain-C restatement of the reference's CPU extractor.  The reference
+ * is Rust and no Rust toolchain exists in this image, so the reference itself
+ * cannot be executed here; the oracle is pinned instead against every known
+ * answer the reference's own tests and docs hold for this path (table audit
+ * fingerprint, per-fixture vertex/triangle counts, CellWord packing, the
+ * secondary-position case, overflow contract, transition winding ...), see
+ * tests/test_oracle_golden.py and SURVEY.md section 8(c).
+ *
+ * Parity status: integer outputs (case words, ranges, indices, materials,
+ * flags, counters) are PINNED at edge 32.  Float outputs are pinned by the
+ * reference only to its own tolerances (position 1e-5, normal 2e-4); the exact
+ * bit patterns follow the reference's CPU formulae operation by operation.
+ * Edge 64, the fBm density quantisation and the dense-random field have no
+ * counterpart in the reference: "parity unpinned" for those, they are pinned
+ * only by this oracle's generalisation over the edge length.
+ *
+ * All citations are relative to /root/reference/ ; PV =
+ * crates/passes/3d/helio-pass-planetary-voxel.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC (see oracle/Makefile).
+ * -ffp-contract=off matters: Rust never fuses a*b+c, gcc would under -march=native.
+ */
+#ifndef HVX_ORACLE_H
+#define HVX_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* PV/src/extraction.rs:72-79 GpuTerrainVertex, repr(C, align(16)), 32 bytes. */
+typedef struct {
+    float position[3];
+    uint32_t material;
+    float normal[3];
+    uint32_t flags;
+} hvxo_vertex;
+
+/* PV/src/fixture.rs:9-16 ExtractionFixtureKind (same order). */
+enum {
+    HVXO_FIELD_PLANE = 0,
+    HVXO_FIELD_SPHERE = 1,
+    HVXO_FIELD_CAVE = 2,
+    HVXO_FIELD_SHARP_CORNER = 3,
+    HVXO_FIELD_THIN_SLAB = 4,
+    HVXO_FIELD_MATERIAL_SEAM = 5,
+    /* ours: no reference counterpart, parity unpinned */
+    HVXO_FIELD_TERRAIN_FBM = 16,
+    HVXO_FIELD_DENSE_RANDOM = 17
+};
+
+/* PV/src/transvoxel.rs:248-261 TransvoxelTableAudit. */
+typedef struct {
+    uint32_t regular_cases, transition_cases;
+    uint32_t regular_vertices, regular_triangles;
+    uint32_t transition_vertices, transition_triangles;
+    uint32_t max_regular_vertices, max_regular_triangles;
+    uint32_t max_transition_vertices, max_transition_triangles;
+    uint64_t fingerprint;
+} hvxo_table_audit;
+
+/* PV/src/fixture.rs:74-81 ExtractionFixtureMetrics. */
+typedef struct {
+    uint32_t solid_samples, air_samples, active_cells, _pad;
+    uint64_t active_microbrick_mask;
+    uint64_t fingerprint;
+} hvxo_fixture_metrics;
+
+/* helio-planet-voxel-core/src/types.rs:335-337 CellWord::new. */
+uint32_t hvxo_cellword(int16_t density, uint8_t material, uint8_t flags);
+
+/* PV/src/transvoxel.rs:263-379 validate_transvoxel_tables; returns 0 when every
+ * case is index safe, else a negative code. */
+int hvxo_validate_tables(hvxo_table_audit* out);
+const char* hvxo_table_revision(void);
+/* PV/src/transvoxel.rs:201-238: raw per-case topology, for table tests.
+ * kind 0 regular / 1 transition; triangles already have the inverse flip applied. */
+int hvxo_case_topology(int kind, uint32_t case_index, uint32_t* class_index, uint32_t* reverse,
+                       uint32_t* vertex_count, uint32_t* triangle_count, uint16_t codes[12],
+                       uint8_t triangles[36]);
+
+/* PV/src/fixture.rs:43-71 sample_canonical (+ our two extra fields). */
+uint32_t hvxo_sample_canonical(int kind, const int64_t position[3], uint32_t lod);
+/* PV/src/fixture.rs:95-124 ExtractionFixture::new, generalised over edge.
+ * samples: (edge+2)^3 words, x fastest then y then z. */
+int hvxo_fixture_fill(int kind, int edge, uint32_t lod, const int64_t page_xyz[3], uint32_t* samples);
+/* PV/src/fixture.rs:169-197 measure. */
+int hvxo_fixture_metrics_of(int edge, const uint32_t* samples, hvxo_fixture_metrics* out);
+/* PV/src/transvoxel_transition.rs:335-349 slab_samples for all six faces
+ * (PV/tests/gpu_transvoxel_transitions.rs:389-403 layout): 6*(2*edge+3)^2*3 words. */
+int hvxo_slab_fill(int kind, int edge, uint32_t lod, const int64_t page_xyz[3], uint32_t* slabs);
+
+/* crates/passes/3d/helio-pass-sdf/src/noise.rs:139-208 terrain_sdf, Rolling style,
+ * TerrainConfig::rolling() (terrain.rs:40-51). */
+float hvxo_terrain_sdf_rolling(float x, float y, float z);
+
+/* Counter layouts:
+ *   classify[4]  PV/src/transvoxel_gpu.rs:134-141  visited, active, vertices, triangles
+ *   emission[8]  PV/src/transvoxel_emit.rs:38-48   required_v, required_i, emitted_v, emitted_i,
+ *                                                   vertex_overflow, index_overflow, completed, pad
+ *   transition[12] PV/src/transvoxel_transition_gpu.rs:133-146 active_cells, active_faces,
+ *                  required_v, required_i, emitted_v, emitted_i, v_overflow, i_overflow, completed, pad*3
+ */
+
+/* PV/tests/gpu_transvoxel_emission.rs:272-344 expected_mesh +
+ * PV/tests/gpu_transvoxel.rs:150-186 expected_classification, generalised over edge.
+ *   cell_words  : edge^3 * 4 u32  (GpuTransvoxelCell; untouched for non-dirty cells)  or NULL
+ *   cell_ranges : edge^3 * 2 u32  (first_vertex, first_index; untouched for non-dirty) or NULL
+ * vertices/indices receive min(required, cap) entries; the counters carry the
+ * all-or-nothing overflow contract against max_vertices / max_indices. */
+int hvxo_extract_regular(int edge, const uint32_t* samples, uint64_t generation,
+                         uint64_t dirty_microbricks, uint32_t transition_mask,
+                         uint32_t max_vertices, uint32_t max_indices,
+                         hvxo_vertex* vertices, uint32_t vertex_cap,
+                         uint32_t* indices, uint32_t index_cap,
+                         uint32_t* cell_words, uint32_t* cell_ranges,
+                         uint32_t classify[4], uint32_t emission[8]);
+
+/* PV/src/transvoxel_transition.rs:189-270,366-397 +
+ * PV/tests/gpu_transvoxel_transitions.rs:351-387, consuming the six-face slab
+ * block exactly as the GPU extractor does (gradients from the slab halo).
+ *   cell_words  : 6*edge^2 * 4 u32 (GpuTransvoxelTransitionCell; zeroed for inactive faces) or NULL
+ *   cell_ranges : 6*edge^2 * 2 u32 or NULL */
+int hvxo_extract_transition(int edge, const uint32_t* slabs, uint32_t transition_mask,
+                            uint64_t generation, uint32_t max_vertices, uint32_t max_indices,
+                            hvxo_vertex* vertices, uint32_t vertex_cap,
+                            uint32_t* indices, uint32_t index_cap,
+                            uint32_t* cell_words, uint32_t* cell_ranges, uint32_t counters[12]);
+
+/* The reference's own route: evaluate the analytic field around every face
+ * sample (PV/src/transvoxel_transition.rs:313-329,399-424) instead of reading a
+ * slab.  Used to prove the slab-halo gradient derivation is exact.  One face. */
+int hvxo_extract_transition_face_analytic(int kind, int edge, uint32_t lod,
+                                          const int64_t page_xyz[3], int face,
+                                          hvxo_vertex* vertices, uint32_t vertex_cap,
+                                          uint32_t* indices, uint32_t index_cap,
+                                          uint32_t* vertex_count, uint32_t* index_count);
+
+/* Batch driver for the CPU baseline: fill (optional) + regular extraction of n
+ * chunks with OpenMP `schedule(dynamic)` over chunks.  Returns total cells.
+ * totals[0..3] = sum required vertices, sum required indices, active cells, chunks with output. */
+int64_t hvxo_batch_regular(int kind, int edge, uint32_t lod, const int64_t* page_xyz /* n*3 */,
+                           uint32_t n, int do_fill, const uint32_t* samples_or_null,
+                           int threads, uint64_t totals[4]);
+int hvxo_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
