@@ -1,0 +1,23 @@
+"""helio_b200 -- B200-native Transvoxel chunk extraction behind Helio's extractor API.
+
+Only the planetary-voxel mesh-extraction hot path lives here: the C-ABI
+CUDA library (csrc/, libhelio_voxel_cuda.so) and the host-side mirror of the reference's
+extractor objects.  Importing the package does not load the library; creating any extractor
+does, and fails loudly if it is missing -- there is no CPU fallback.
+"""
+from . import _ffi
+from .context import (CELL_OFFSET_DTYPE, CELL_RECORD_DTYPE, CLASSIFY_COUNTERS_DTYPE, EMISSION_COUNTERS_DTYPE,
+                      RANGE_DTYPE, SCAN_BLOCK_DTYPE, TRANSITION_COUNTERS_DTYPE, VERTEX_DTYPE, Context, make_descs)
+from .errors import (AddressError, BatchCapacity, CudaError, DeviceLimit, FinestLodHasNoFinerNeighbor, HvxError,
+                     InvalidExtractionCapacity, SampleCount, TerrainLodTopologyError, TransitionDeviceLimit,
+                     TransitionInvalidExtractionCapacity, TransitionMask, TransitionSampleCount,
+                     TransvoxelGpuError, TransvoxelTransitionGpuError)
+from .extractor import (EXTRACTION_SAMPLE_COUNT, TRANSITION_ALL_FACE_SLAB_SAMPLE_COUNT,
+                        TRANSVOXEL_SCAN_WORKGROUP_SIZE, ChunkBatchExtractor, ResourceStats, TransvoxelGpuClassifier,
+                        TransvoxelGpuExtractor, TransvoxelGpuExtractorConfig, TransvoxelGpuTransitionExtractor,
+                        TransvoxelGpuTransitionExtractorConfig)
+from .lod import HorizonLodFixturePlan, TerrainLodTopology, TerrainLodTopologyStats, chunk_cost, partition_chunks
+from .types import (MAX_ADDRESSABLE_LOD, PAGE_EDGE, TRANSITION_FACE_MASK, CellWord, ExtractionFixtureKind,
+                    GpuTransvoxelCell, GpuTransvoxelTransitionCell, PageKey, TransitionFace)
+
+__version__ = "0.1.0"

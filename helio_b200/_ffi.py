@@ -1,0 +1,131 @@
+"""ctypes binding of libhelio_voxel_cuda.so (include/hvx.h).
+
+There is no fallback of any kind: if the shared library is missing or the machine has no
+CUDA device, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libhelio_voxel_cuda.so"
+
+HVX_OK = 0
+HVX_E_SAMPLE_COUNT = -1
+HVX_E_INVALID_CAPACITY = -2
+HVX_E_DEVICE_LIMIT = -3
+HVX_E_TRANSITION_MASK = -4
+HVX_E_INVALID_ARGUMENT = -5
+HVX_E_CUDA = -6
+HVX_E_BATCH_CAPACITY = -7
+HVX_E_FINEST_LOD = -8
+HVX_E_ADDRESS = -9
+HVX_E_TOPOLOGY_EMPTY = -20
+HVX_E_TOPOLOGY_DUPLICATE = -21
+HVX_E_TOPOLOGY_OVERLAP = -22
+HVX_E_TOPOLOGY_UNBALANCED = -23
+HVX_E_TOPOLOGY_ROOT_LOD = -24
+HVX_E_TOPOLOGY_MINIMUM_LOD = -25
+HVX_E_TOPOLOGY_PAGE_BUDGET = -26
+HVX_E_TOPOLOGY_MISSING_PARENT = -27
+HVX_E_TOPOLOGY_COVERAGE = -28
+
+HVX_CFG_DEBUG_RECORDS = 1
+
+(BUF_SAMPLES, BUF_SLABS, BUF_REGULAR_VERTICES, BUF_REGULAR_INDICES, BUF_REGULAR_COUNTERS, BUF_REGULAR_CLASSIFY,
+ BUF_REGULAR_RANGES, BUF_REGULAR_CELLS, BUF_REGULAR_OFFSETS, BUF_REGULAR_BLOCKS, BUF_TRANSITION_VERTICES,
+ BUF_TRANSITION_INDICES, BUF_TRANSITION_COUNTERS, BUF_TRANSITION_RANGES, BUF_TRANSITION_CELLS,
+ BUF_TRANSITION_OFFSETS, BUF_TRANSITION_BLOCKS) = range(17)
+
+
+class Config(C.Structure):
+    _fields_ = [("edge", C.c_uint32), ("max_chunks", C.c_uint32), ("max_vertices", C.c_uint32),
+                ("max_indices", C.c_uint32), ("max_transition_vertices", C.c_uint32),
+                ("max_transition_indices", C.c_uint32), ("flags", C.c_uint32), ("_reserved", C.c_uint32)]
+
+
+class ChunkDesc(C.Structure):
+    _fields_ = [("generation", C.c_uint64), ("dirty_microbricks", C.c_uint64), ("transition_mask", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class Range(C.Structure):
+    _fields_ = [("first_vertex", C.c_uint32), ("vertex_count", C.c_uint32), ("first_index", C.c_uint32),
+                ("index_count", C.c_uint32)]
+
+
+class Page(C.Structure):
+    _fields_ = [("page_xyz", C.c_int64 * 3), ("lod", C.c_uint8), ("transition_mask", C.c_uint8),
+                ("_pad", C.c_uint8 * 6)]
+
+
+class LodStats(C.Structure):
+    _fields_ = [("pages", C.c_uint32), ("minimum_lod", C.c_uint32), ("maximum_lod", C.c_uint32),
+                ("transition_faces", C.c_uint32)]
+
+
+# every symbol include/hvx.h declares; tests assert the library exports all of them
+EXPORTS = [
+    "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
+    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count",
+    "hvx_fill_density", "hvx_fill_slabs", "hvx_extract_regular", "hvx_classify_regular", "hvx_extract_transition",
+    "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
+    "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA extension; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("HVX_LIBRARY", LIB_PATH))
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). helio_b200 has no CPU or PyTorch fallback.")
+    L = C.CDLL(str(path))
+    vp, u32p, u64p, i64p, u8p = C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int64), \
+        C.POINTER(C.c_uint8)
+    L.hvx_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Config)]
+    L.hvx_destroy.argtypes = [vp]
+    L.hvx_destroy.restype = None
+    L.hvx_last_error.argtypes = [vp]
+    L.hvx_last_error.restype = C.c_char_p
+    L.hvx_status_name.argtypes = [C.c_int]
+    L.hvx_status_name.restype = C.c_char_p
+    L.hvx_abi_version.restype = C.c_uint32
+    L.hvx_get_config.argtypes = [vp, C.POINTER(Config)]
+    L.hvx_allocated_bytes.argtypes = [vp]
+    L.hvx_allocated_bytes.restype = C.c_uint64
+    L.hvx_set_stream.argtypes = [vp, vp]
+    L.hvx_get_stream.argtypes = [vp]
+    L.hvx_get_stream.restype = vp
+    L.hvx_synchronize.argtypes = [vp]
+    L.hvx_launch_count.argtypes = [vp]
+    L.hvx_launch_count.restype = C.c_uint64
+    L.hvx_fill_density.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
+    L.hvx_fill_slabs.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
+    L.hvx_extract_regular.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
+    L.hvx_classify_regular.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
+    L.hvx_extract_transition.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
+    L.hvx_buffer.argtypes = [vp, C.c_int]
+    L.hvx_buffer.restype = vp
+    L.hvx_buffer_bytes.argtypes = [vp, C.c_int]
+    L.hvx_buffer_bytes.restype = C.c_uint64
+    L.hvx_read.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
+    L.hvx_write.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
+    L.hvx_read_meshes.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, vp, C.c_uint64, vp, C.c_uint64,
+                                  C.POINTER(Range), u64p, u64p]
+    L.hvx_lod_topology.argtypes = [C.POINTER(Page), C.c_uint32, C.c_uint32, C.POINTER(LodStats)]
+    L.hvx_horizon_plan.argtypes = [i64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Page), u32p,
+                                   C.POINTER(Page), C.POINTER(LodStats)]
+    L.hvx_partition_chunks.argtypes = [u64p, C.c_uint32, C.c_uint32, u32p]
+    L.hvx_chunk_cost.argtypes = [C.c_uint32, C.c_uint32]
+    L.hvx_chunk_cost.restype = C.c_uint64
+    _lib = L
+    return L

@@ -1,0 +1,226 @@
+"""Thin object wrapper over one ``hvx_ctx`` (device + stream + output arenas)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from .errors import raise_for_status
+
+VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("material", "<u4"), ("normal", "<f4", 3), ("flags", "<u4")])
+EMISSION_COUNTERS_DTYPE = np.dtype([(n, "<u4") for n in (
+    "required_vertices", "required_indices", "emitted_vertices", "emitted_indices", "vertex_overflow",
+    "index_overflow", "completed", "_pad")])
+CLASSIFY_COUNTERS_DTYPE = np.dtype([(n, "<u4") for n in ("visited_cells", "active_cells", "vertices", "triangles")])
+TRANSITION_COUNTERS_DTYPE = np.dtype([(n, "<u4") for n in (
+    "active_cells", "active_faces", "required_vertices", "required_indices", "emitted_vertices", "emitted_indices",
+    "vertex_overflow", "index_overflow", "completed", "_pad0", "_pad1", "_pad2")])
+CELL_RECORD_DTYPE = np.dtype([("packed_case_class_counts", "<u4"), ("generation_low", "<u4"),
+                              ("generation_high", "<u4"), ("_pad", "<u4")])
+CELL_OFFSET_DTYPE = np.dtype([("first_vertex", "<u4"), ("first_index", "<u4"), ("generation_low", "<u4"),
+                              ("generation_high", "<u4")])
+SCAN_BLOCK_DTYPE = np.dtype([("vertex_count", "<u4"), ("index_count", "<u4"), ("first_vertex", "<u4"),
+                             ("first_index", "<u4")])
+RANGE_DTYPE = np.dtype([("first_vertex", "<u4"), ("vertex_count", "<u4"), ("first_index", "<u4"),
+                        ("index_count", "<u4")])
+assert VERTEX_DTYPE.itemsize == 32 and EMISSION_COUNTERS_DTYPE.itemsize == 32
+assert TRANSITION_COUNTERS_DTYPE.itemsize == 48 and CLASSIFY_COUNTERS_DTYPE.itemsize == 16
+
+_BUF_DTYPES = {
+    _ffi.BUF_SAMPLES: np.dtype("<u4"), _ffi.BUF_SLABS: np.dtype("<u4"),
+    _ffi.BUF_REGULAR_VERTICES: VERTEX_DTYPE, _ffi.BUF_REGULAR_INDICES: np.dtype("<u4"),
+    _ffi.BUF_REGULAR_COUNTERS: EMISSION_COUNTERS_DTYPE, _ffi.BUF_REGULAR_CLASSIFY: CLASSIFY_COUNTERS_DTYPE,
+    _ffi.BUF_REGULAR_RANGES: RANGE_DTYPE, _ffi.BUF_REGULAR_CELLS: CELL_RECORD_DTYPE,
+    _ffi.BUF_REGULAR_OFFSETS: CELL_OFFSET_DTYPE, _ffi.BUF_REGULAR_BLOCKS: SCAN_BLOCK_DTYPE,
+    _ffi.BUF_TRANSITION_VERTICES: VERTEX_DTYPE, _ffi.BUF_TRANSITION_INDICES: np.dtype("<u4"),
+    _ffi.BUF_TRANSITION_COUNTERS: TRANSITION_COUNTERS_DTYPE, _ffi.BUF_TRANSITION_RANGES: RANGE_DTYPE,
+    _ffi.BUF_TRANSITION_CELLS: CELL_RECORD_DTYPE, _ffi.BUF_TRANSITION_OFFSETS: CELL_OFFSET_DTYPE,
+    _ffi.BUF_TRANSITION_BLOCKS: SCAN_BLOCK_DTYPE,
+}
+
+
+def _input_pointer(array, expected_dtype=np.uint32):
+    """(pointer, element_count, keepalive) for a numpy array, a torch tensor or None."""
+    if array is None:
+        return None, None, None
+    if hasattr(array, "data_ptr"):  # torch tensor (host or device) -- no torch import needed
+        if not array.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        if array.element_size() != 4:
+            raise ValueError("tensor must hold 32-bit CellWords")
+        return C.c_void_p(array.data_ptr()), array.numel(), array
+    arr = np.ascontiguousarray(array, dtype=expected_dtype)
+    return C.c_void_p(arr.ctypes.data), arr.size, arr
+
+
+def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask=0):
+    """ctypes array of ``hvx_chunk_desc``; scalar arguments broadcast, sequences are per chunk."""
+    descs = (_ffi.ChunkDesc * max(n, 1))()
+
+    def at(value, i):
+        return int(value[i]) if hasattr(value, "__len__") else int(value)
+
+    for i in range(n):
+        descs[i].generation = at(generation, i) & ((1 << 64) - 1)
+        descs[i].dirty_microbricks = at(dirty_microbricks, i) & ((1 << 64) - 1)
+        descs[i].transition_mask = at(transition_mask, i) & 0xFFFFFFFF
+    return descs
+
+
+class Context:
+    """One device, one stream, one set of fixed-stride output arenas (``hvx_ctx``)."""
+
+    def __init__(self, device=0, *, edge=32, max_chunks=1, max_vertices=393_216, max_indices=491_520,
+                 max_transition_vertices=0, max_transition_indices=0, debug_records=False, error_kind="regular"):
+        self._lib = _ffi.load()
+        self._handle = C.c_void_p()
+        self._error_kind = error_kind
+        cfg = _ffi.Config(edge, max_chunks, max_vertices, max_indices, max_transition_vertices,
+                          max_transition_indices, _ffi.HVX_CFG_DEBUG_RECORDS if debug_records else 0, 0)
+        status = self._lib.hvx_create(C.byref(self._handle), int(device), C.byref(cfg))
+        if status != _ffi.HVX_OK:
+            message = self._lib.hvx_last_error(None).decode()
+            self._handle = C.c_void_p()
+            raise_for_status(status, message, error_kind, max_vertices=max_vertices, max_indices=max_indices)
+        self.device = int(device)
+        self.edge = edge
+        self.max_chunks = max_chunks
+        self.max_vertices = max_vertices
+        self.max_indices = max_indices
+        self.max_transition_vertices = max_transition_vertices
+        self.max_transition_indices = max_transition_indices
+        self.debug_records = debug_records
+        self.sample_words = (edge + 2) ** 3
+        self.slab_words = 18 * (2 * edge + 3) ** 2
+        self.cells = edge ** 3
+        self.transition_cells = 6 * edge * edge
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self._lib.hvx_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, status, kind=None, **extra):
+        if status != _ffi.HVX_OK:
+            raise_for_status(status, self._lib.hvx_last_error(self._handle).decode(), kind or self._error_kind, **extra)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned cudaStream_t (integer handle, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._lib.hvx_set_stream(self._handle, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._check(self._lib.hvx_synchronize(self._handle))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.hvx_launch_count(self._handle))
+
+    @property
+    def allocated_bytes(self):
+        return int(self._lib.hvx_allocated_bytes(self._handle))
+
+    def buffer_ptr(self, buffer_id):
+        ptr = self._lib.hvx_buffer(self._handle, buffer_id)
+        if not ptr:
+            raise ValueError(f"buffer {buffer_id} is not available in this configuration")
+        return int(ptr)
+
+    def buffer_bytes(self, buffer_id):
+        return int(self._lib.hvx_buffer_bytes(self._handle, buffer_id))
+
+    def read(self, buffer_id, first=0, count=None):
+        """Synchronising readback of ``count`` elements starting at element ``first``."""
+        dtype = _BUF_DTYPES[buffer_id]
+        total = self.buffer_bytes(buffer_id) // dtype.itemsize
+        if count is None:
+            count = total - first
+        out = np.empty(count, dtype=dtype)
+        self._check(self._lib.hvx_read(self._handle, buffer_id, first * dtype.itemsize, count * dtype.itemsize,
+                                       C.c_void_p(out.ctypes.data)))
+        return out
+
+    def write(self, buffer_id, array, first=0):
+        dtype = _BUF_DTYPES[buffer_id]
+        arr = np.ascontiguousarray(array, dtype=dtype)
+        self._check(self._lib.hvx_write(self._handle, buffer_id, first * dtype.itemsize, arr.nbytes,
+                                        C.c_void_p(arr.ctypes.data)))
+
+    # -- K1 -----------------------------------------------------------------------------------
+    def _pages(self, page_xyz, lod):
+        pages = np.ascontiguousarray(page_xyz, dtype=np.int64).reshape(-1, 3)
+        n = pages.shape[0]
+        lods = None
+        if lod is not None:
+            lods = np.ascontiguousarray(np.broadcast_to(np.asarray(lod, dtype=np.uint8), (n,)))
+        return pages, lods, n
+
+    def fill_density(self, kind, page_xyz, lod=None, out_ptr=None):
+        pages, lods, n = self._pages(page_xyz, lod)
+        self._check(self._lib.hvx_fill_density(
+            self._handle, int(kind), pages.ctypes.data_as(C.POINTER(C.c_int64)),
+            None if lods is None else lods.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.c_void_p(out_ptr or 0)))
+        return n
+
+    def fill_slabs(self, kind, page_xyz, lod, out_ptr=None):
+        pages, lods, n = self._pages(page_xyz, lod)
+        self._check(self._lib.hvx_fill_slabs(
+            self._handle, int(kind), pages.ctypes.data_as(C.POINTER(C.c_int64)),
+            None if lods is None else lods.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.c_void_p(out_ptr or 0)),
+            kind="transition")
+        return n
+
+    # -- K2-K4 --------------------------------------------------------------------------------
+    def extract_regular(self, samples, descs, n, sample_words=None, classify_only=False):
+        ptr, count, keep = _input_pointer(samples)
+        if sample_words is None:
+            sample_words = n * self.sample_words if count is None else count
+        fn = self._lib.hvx_classify_regular if classify_only else self._lib.hvx_extract_regular
+        self._check(fn(self._handle, ptr, int(sample_words), descs, n), kind="regular")
+        del keep
+
+    def extract_transition(self, slabs, descs, n, slab_words=None):
+        ptr, count, keep = _input_pointer(slabs)
+        if slab_words is None:
+            slab_words = n * self.slab_words if count is None else count
+        self._check(self._lib.hvx_extract_transition(self._handle, ptr, int(slab_words), descs, n), kind="transition")
+        del keep
+
+    def read_meshes(self, kind=0, first=0, n=None, vertices_out=None, indices_out=None):
+        """Packed host copy of chunks [first, first+n): (vertices, indices, ranges)."""
+        if n is None:
+            n = self.max_chunks - first
+        ranges = np.zeros(n, dtype=RANGE_DTYPE)
+        tv, ti = C.c_uint64(), C.c_uint64()
+        rp = ranges.ctypes.data_as(C.POINTER(_ffi.Range))
+        if vertices_out is None or indices_out is None:
+            status = self._lib.hvx_read_meshes(self._handle, kind, first, n, None, 0, None, 0, rp, C.byref(tv), C.byref(ti))
+            if status not in (_ffi.HVX_OK, _ffi.HVX_E_INVALID_CAPACITY):
+                self._check(status)
+            vertices_out = np.empty(tv.value, dtype=VERTEX_DTYPE)
+            indices_out = np.empty(ti.value, dtype=np.uint32)
+            if tv.value == 0 and ti.value == 0:
+                return vertices_out, indices_out, ranges
+        vptr = vertices_out.data_ptr() if hasattr(vertices_out, "data_ptr") else vertices_out.ctypes.data
+        iptr = indices_out.data_ptr() if hasattr(indices_out, "data_ptr") else indices_out.ctypes.data
+        vcap = vertices_out.numel() * vertices_out.element_size() // 32 if hasattr(vertices_out, "data_ptr") else vertices_out.size
+        icap = indices_out.numel() if hasattr(indices_out, "data_ptr") else indices_out.size
+        self._check(self._lib.hvx_read_meshes(self._handle, kind, first, n, C.c_void_p(vptr), vcap, C.c_void_p(iptr), icap,
+                                              rp, C.byref(tv), C.byref(ti)))
+        if hasattr(vertices_out, "data_ptr"):
+            return tv.value, ti.value, ranges
+        return vertices_out[:tv.value], indices_out[:ti.value], ranges

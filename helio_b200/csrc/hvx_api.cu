@@ -1,0 +1,566 @@
+// hvx_api.cu -- the extern "C" boundary (include/hvx.h): context, arenas, validation, launches.
+//
+// Mirrors the reference's extractor objects:
+//   TransvoxelGpuExtractor            PV/src/transvoxel_emit.rs:92-396
+//   TransvoxelGpuClassifier           PV/src/transvoxel_gpu.rs:148-356
+//   TransvoxelGpuTransitionExtractor  PV/src/transvoxel_transition_gpu.rs:190-520
+// Ownership follows the reference: the ctx owns every device buffer, the caller borrows inputs
+// for the duration of the call, outputs are overwritten by the next dispatch.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hvx_kernels.h"
+
+using namespace hvx;
+
+struct hvx_ctx {
+    hvx_config cfg{};
+    int device = 0;
+    DeviceInfo dev{};
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    void* buf[HVX_BUF_COUNT] = {};
+    uint64_t buf_bytes[HVX_BUF_COUNT] = {};
+    ChunkDesc* d_descs = nullptr;
+    int64_t* d_pages = nullptr;
+    uint8_t* d_lod = nullptr;
+    uint32_t* d_work = nullptr;       // [2] work counters (regular, transition)
+    hvx_range* d_packed = nullptr;    // [max_chunks] packed placement for hvx_read_meshes
+    void* pack_v = nullptr;           // staging for hvx_read_meshes
+    void* pack_i = nullptr;
+    uint64_t pack_v_bytes = 0, pack_i_bytes = 0;
+    uint64_t allocated = 0;
+    uint64_t launches = 0;
+    std::string error;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int fail(hvx_ctx* ctx, int status, const char* fmt, ...) {
+    char msg[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(msg, sizeof msg, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->error = msg; else g_create_error = msg;
+    return status;
+}
+
+int cuda_fail(hvx_ctx* ctx, cudaError_t e, const char* what) {
+    return fail(ctx, HVX_E_CUDA, "CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+#define HVX_CUDA(ctx, call)                                   \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call); \
+    } while (0)
+
+uint64_t sample_words(uint32_t edge) { return static_cast<uint64_t>(edge + 2) * (edge + 2) * (edge + 2); }
+uint64_t slab_words(uint32_t edge) { return 18ull * (2 * edge + 3) * (2 * edge + 3); }
+uint64_t cells(uint32_t edge) { return static_cast<uint64_t>(edge) * edge * edge; }
+uint64_t tcells(uint32_t edge) { return 6ull * edge * edge; }
+
+uint64_t arena_bytes(const hvx_config& c, int id) {
+    const uint64_t n = c.max_chunks;
+    const bool dbg = (c.flags & HVX_CFG_DEBUG_RECORDS) != 0;
+    const bool tr = c.max_transition_vertices != 0;
+    switch (id) {
+        case HVX_BUF_SAMPLES: return n * sample_words(c.edge) * 4;
+        case HVX_BUF_SLABS: return n * slab_words(c.edge) * 4;
+        case HVX_BUF_REGULAR_VERTICES: return n * c.max_vertices * sizeof(hvx_vertex);
+        case HVX_BUF_REGULAR_INDICES: return n * c.max_indices * 4ull;
+        case HVX_BUF_REGULAR_COUNTERS: return n * sizeof(hvx_emission_counters);
+        case HVX_BUF_REGULAR_CLASSIFY: return n * sizeof(hvx_classify_counters);
+        case HVX_BUF_REGULAR_RANGES: return n * sizeof(hvx_range);
+        case HVX_BUF_REGULAR_CELLS: return dbg ? n * cells(c.edge) * sizeof(hvx_cell_record) : 0;
+        case HVX_BUF_REGULAR_OFFSETS: return dbg ? n * cells(c.edge) * sizeof(hvx_cell_offset) : 0;
+        case HVX_BUF_REGULAR_BLOCKS: return dbg ? n * (cells(c.edge) / 256) * sizeof(hvx_scan_block) : 0;
+        case HVX_BUF_TRANSITION_VERTICES: return tr ? n * c.max_transition_vertices * sizeof(hvx_vertex) : 0;
+        case HVX_BUF_TRANSITION_INDICES: return tr ? n * c.max_transition_indices * 4ull : 0;
+        case HVX_BUF_TRANSITION_COUNTERS: return tr ? n * sizeof(hvx_transition_counters) : 0;
+        case HVX_BUF_TRANSITION_RANGES: return tr ? n * sizeof(hvx_range) : 0;
+        case HVX_BUF_TRANSITION_CELLS: return tr && dbg ? n * tcells(c.edge) * sizeof(hvx_cell_record) : 0;
+        case HVX_BUF_TRANSITION_OFFSETS: return tr && dbg ? n * tcells(c.edge) * sizeof(hvx_cell_offset) : 0;
+        case HVX_BUF_TRANSITION_BLOCKS: return tr && dbg ? n * (tcells(c.edge) / 256) * sizeof(hvx_scan_block) : 0;
+        default: return 0;
+    }
+}
+
+int ensure_buffer(hvx_ctx* ctx, int id) {
+    if (id < 0 || id >= HVX_BUF_COUNT) return fail(ctx, HVX_E_INVALID_ARGUMENT, "unknown buffer id %d", id);
+    if (ctx->buf[id]) return HVX_OK;
+    const uint64_t bytes = arena_bytes(ctx->cfg, id);
+    if (bytes == 0) return fail(ctx, HVX_E_INVALID_ARGUMENT, "buffer %d is not enabled by this configuration", id);
+    void* ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: buffer %d requires %llu bytes: %s", id,
+                    static_cast<unsigned long long>(bytes), cudaGetErrorString(e));
+    }
+    // debug records start "stale" (generation 0, valid bit clear) like a freshly created wgpu buffer
+    if (id >= HVX_BUF_REGULAR_COUNTERS && id != HVX_BUF_TRANSITION_VERTICES && id != HVX_BUF_TRANSITION_INDICES) {
+        e = cudaMemsetAsync(ptr, 0, bytes, ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(ptr);
+            return cuda_fail(ctx, e, "cudaMemsetAsync");
+        }
+    }
+    ctx->buf[id] = ptr;
+    ctx->buf_bytes[id] = bytes;
+    ctx->allocated += bytes;
+    return HVX_OK;
+}
+
+template <typename T>
+int small_alloc(hvx_ctx* ctx, T** out, uint64_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(out), count * sizeof(T));
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    ctx->allocated += count * sizeof(T);
+    return HVX_OK;
+}
+
+// Resolve an input pointer: NULL -> ctx arena; device pointer -> as is; host pointer -> staged
+// into the ctx arena with an async H2D copy on the ctx stream.
+int resolve_input(hvx_ctx* ctx, const uint32_t* ptr, uint64_t words, int arena_id, const uint32_t** out) {
+    if (ptr == nullptr) {
+        int rc = ensure_buffer(ctx, arena_id);
+        if (rc) return rc;
+        *out = static_cast<const uint32_t*>(ctx->buf[arena_id]);
+        return HVX_OK;
+    }
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        attr.type = cudaMemoryTypeUnregistered;
+    }
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+        if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0)
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "device sample pointer must be 16-byte aligned");
+        if (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device)
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "sample pointer lives on device %d, ctx is on device %d",
+                        attr.device, ctx->device);
+        *out = ptr;
+        return HVX_OK;
+    }
+    int rc = ensure_buffer(ctx, arena_id);
+    if (rc) return rc;
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->buf[arena_id], ptr, words * 4, cudaMemcpyHostToDevice, ctx->stream));
+    *out = static_cast<const uint32_t*>(ctx->buf[arena_id]);
+    return HVX_OK;
+}
+
+int upload_descs(hvx_ctx* ctx, const hvx_chunk_desc* descs, uint32_t n) {
+    static_assert(sizeof(hvx_chunk_desc) == sizeof(ChunkDesc), "desc layout");
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_descs, descs, static_cast<size_t>(n) * sizeof(ChunkDesc),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    return HVX_OK;
+}
+
+int check_batch(hvx_ctx* ctx, const void* descs, uint32_t n) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (n > ctx->cfg.max_chunks)
+        return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
+    if (n != 0 && descs == nullptr) return fail(ctx, HVX_E_INVALID_ARGUMENT, "descs is NULL");
+    return HVX_OK;
+}
+
+int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n,
+                uint32_t mode) {
+    int rc = check_batch(ctx, descs, n);
+    if (rc) return rc;
+    const uint64_t expected = static_cast<uint64_t>(n) * sample_words(ctx->cfg.edge);
+    if (words != expected)
+        return fail(ctx, HVX_E_SAMPLE_COUNT, "Transvoxel classification received %llu samples; expected %llu",
+                    static_cast<unsigned long long>(words), static_cast<unsigned long long>(expected));
+    if (n == 0) return HVX_OK;
+    DeviceGuard guard(ctx->device);
+    const uint32_t* d_samples = nullptr;
+    if ((rc = resolve_input(ctx, samples, words, HVX_BUF_SAMPLES, &d_samples))) return rc;
+    if ((rc = upload_descs(ctx, descs, n))) return rc;
+    RegularParams p{};
+    p.samples = d_samples;
+    p.descs = ctx->d_descs;
+    p.n_chunks = n;
+    p.mode = mode;
+    p.max_vertices = ctx->cfg.max_vertices;
+    p.max_indices = ctx->cfg.max_indices;
+    p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);
+    p.indices = static_cast<uint32_t*>(ctx->buf[HVX_BUF_REGULAR_INDICES]);
+    p.counters = static_cast<hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
+    p.classify = static_cast<hvx_classify_counters*>(ctx->buf[HVX_BUF_REGULAR_CLASSIFY]);
+    p.ranges = static_cast<hvx_range*>(ctx->buf[HVX_BUF_REGULAR_RANGES]);
+    p.cells = static_cast<hvx_cell_record*>(ctx->buf[HVX_BUF_REGULAR_CELLS]);
+    p.offsets = static_cast<hvx_cell_offset*>(ctx->buf[HVX_BUF_REGULAR_OFFSETS]);
+    p.blocks = static_cast<hvx_scan_block*>(ctx->buf[HVX_BUF_REGULAR_BLOCKS]);
+    p.work_counter = ctx->d_work;
+    cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+int validate_pages(hvx_ctx* ctx, const int64_t* page_xyz, const uint8_t* lod, uint32_t n, bool slabs) {
+    const int64_t edge = ctx->cfg.edge;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t l = lod ? lod[i] : 0;
+        if (l > 57) return fail(ctx, HVX_E_ADDRESS, "planetary page LOD %u exceeds the addressable maximum", l);
+        if (slabs && l == 0)
+            return fail(ctx, HVX_E_FINEST_LOD, "LOD0 has no finer neighbor and cannot own a transition mesh");
+        const int64_t span = edge << l, scale = 1ll << l;
+        for (int a = 0; a < 3; ++a) {
+            int64_t lo, hi, tmp;
+            if (__builtin_mul_overflow(page_xyz[3 * i + a], span, &lo) ||
+                __builtin_add_overflow(lo, span, &hi) || __builtin_add_overflow(hi, 2 * scale, &tmp) ||
+                __builtin_sub_overflow(lo, 2 * scale, &tmp))
+                return fail(ctx, HVX_E_ADDRESS, "planetary page coordinate arithmetic overflowed");
+        }
+    }
+    return HVX_OK;
+}
+
+int run_fill(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n, uint32_t* out,
+             bool slabs) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (n > ctx->cfg.max_chunks)
+        return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
+    if (!(kind <= 5 || kind == 16 || kind == 17)) return fail(ctx, HVX_E_INVALID_ARGUMENT, "unknown field kind %u", kind);
+    if (n == 0) return HVX_OK;
+    if (!page_xyz) return fail(ctx, HVX_E_INVALID_ARGUMENT, "page_xyz is NULL");
+    int rc = validate_pages(ctx, page_xyz, lod, n, slabs);
+    if (rc) return rc;
+    DeviceGuard guard(ctx->device);
+    const int arena = slabs ? HVX_BUF_SLABS : HVX_BUF_SAMPLES;
+    if (!out) {
+        if ((rc = ensure_buffer(ctx, arena))) return rc;
+        out = static_cast<uint32_t*>(ctx->buf[arena]);
+    }
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pages, page_xyz, static_cast<size_t>(n) * 3 * sizeof(int64_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (lod) HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_lod, lod, n, cudaMemcpyHostToDevice, ctx->stream));
+    else HVX_CUDA(ctx, cudaMemsetAsync(ctx->d_lod, 0, n, ctx->stream));
+    FillParams p{kind, n, ctx->d_pages, ctx->d_lod, out};
+    cudaError_t e = slabs ? launch_fill_slabs(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream)
+                          : launch_fill_samples(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_fill");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t hvx_abi_version(void) { return HVX_ABI_VERSION; }
+
+const char* hvx_status_name(int status) {
+    switch (status) {
+        case HVX_OK: return "HVX_OK";
+        case HVX_E_SAMPLE_COUNT: return "HVX_E_SAMPLE_COUNT";
+        case HVX_E_INVALID_CAPACITY: return "HVX_E_INVALID_CAPACITY";
+        case HVX_E_DEVICE_LIMIT: return "HVX_E_DEVICE_LIMIT";
+        case HVX_E_TRANSITION_MASK: return "HVX_E_TRANSITION_MASK";
+        case HVX_E_INVALID_ARGUMENT: return "HVX_E_INVALID_ARGUMENT";
+        case HVX_E_CUDA: return "HVX_E_CUDA";
+        case HVX_E_BATCH_CAPACITY: return "HVX_E_BATCH_CAPACITY";
+        case HVX_E_FINEST_LOD: return "HVX_E_FINEST_LOD";
+        case HVX_E_ADDRESS: return "HVX_E_ADDRESS";
+        case HVX_E_TOPOLOGY_EMPTY: return "HVX_E_TOPOLOGY_EMPTY";
+        case HVX_E_TOPOLOGY_DUPLICATE: return "HVX_E_TOPOLOGY_DUPLICATE";
+        case HVX_E_TOPOLOGY_OVERLAP: return "HVX_E_TOPOLOGY_OVERLAP";
+        case HVX_E_TOPOLOGY_UNBALANCED: return "HVX_E_TOPOLOGY_UNBALANCED";
+        case HVX_E_TOPOLOGY_ROOT_LOD: return "HVX_E_TOPOLOGY_ROOT_LOD";
+        case HVX_E_TOPOLOGY_MINIMUM_LOD: return "HVX_E_TOPOLOGY_MINIMUM_LOD";
+        case HVX_E_TOPOLOGY_PAGE_BUDGET: return "HVX_E_TOPOLOGY_PAGE_BUDGET";
+        case HVX_E_TOPOLOGY_MISSING_PARENT: return "HVX_E_TOPOLOGY_MISSING_PARENT";
+        case HVX_E_TOPOLOGY_COVERAGE: return "HVX_E_TOPOLOGY_COVERAGE";
+        default: return "HVX_E_UNKNOWN";
+    }
+}
+
+const char* hvx_last_error(const hvx_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
+    if (!out || !config) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "hvx_create: NULL argument");
+    *out = nullptr;
+    const hvx_config c = *config;
+    if (c.edge != 32 && c.edge != 64) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "edge must be 32 or 64, got %u", c.edge);
+    if (c.max_chunks == 0) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "max_chunks must be nonzero");
+    // TransvoxelGpuExtractorConfig::new, PV/src/transvoxel_emit.rs:63-75
+    if (c.max_vertices == 0 || c.max_indices == 0)
+        return fail(nullptr, HVX_E_INVALID_CAPACITY,
+                    "Transvoxel extraction capacities must be nonzero (vertices=%u, indices=%u)", c.max_vertices,
+                    c.max_indices);
+    // TransvoxelGpuTransitionExtractorConfig::new, PV/src/transvoxel_transition_gpu.rs:160-171
+    if ((c.max_transition_vertices == 0) != (c.max_transition_indices == 0))
+        return fail(nullptr, HVX_E_INVALID_CAPACITY,
+                    "Transvoxel transition capacities must be nonzero (vertices=%u, indices=%u)",
+                    c.max_transition_vertices, c.max_transition_indices);
+    if (static_cast<uint64_t>(c.max_chunks) * c.max_vertices > 0xffffffffull ||
+        static_cast<uint64_t>(c.max_chunks) * c.max_indices > 0xffffffffull ||
+        static_cast<uint64_t>(c.max_chunks) * c.max_transition_vertices > 0xffffffffull ||
+        static_cast<uint64_t>(c.max_chunks) * c.max_transition_indices > 0xffffffffull)
+        return fail(nullptr, HVX_E_DEVICE_LIMIT, "DeviceLimit: max_chunks * per-chunk capacity must fit 32-bit ranges");
+
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, HVX_E_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "device %d out of range (%d devices)", device, count);
+    hvx_ctx* ctx = new (std::nothrow) hvx_ctx();
+    if (!ctx) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "out of host memory");
+    ctx->cfg = c;
+    ctx->device = device;
+    DeviceGuard guard(device);
+    auto bail = [&](int rc) {
+        g_create_error = ctx->error;
+        hvx_destroy(ctx);
+        return rc;
+    };
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaGetDeviceProperties"));
+    if (prop.major < 10)
+        return bail(fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: requires compute capability 10.0 (sm_100a), device is %d.%d",
+                         prop.major, prop.minor));
+    ctx->dev.sm_count = prop.multiProcessorCount;
+    ctx->dev.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
+    if (regular_smem_bytes(static_cast<int>(c.edge)) > prop.sharedMemPerBlockOptin)
+        return bail(fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: shared memory per block: required %zu, available %zu",
+                         regular_smem_bytes(static_cast<int>(c.edge)), prop.sharedMemPerBlockOptin));
+    if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaStreamCreate"));
+    ctx->stream = ctx->own_stream;
+    int rc;
+    if ((rc = small_alloc(ctx, &ctx->d_descs, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_work, 4))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_packed, c.max_chunks))) return bail(rc);
+    for (int id = HVX_BUF_REGULAR_VERTICES; id < HVX_BUF_COUNT; ++id)
+        if (arena_bytes(c, id) != 0 && (rc = ensure_buffer(ctx, id))) return bail(rc);
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaStreamSynchronize"));
+    *out = ctx;
+    return HVX_OK;
+}
+
+void hvx_destroy(hvx_ctx* ctx) {
+    if (!ctx) return;
+    DeviceGuard guard(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (void*& b : ctx->buf)
+        if (b) cudaFree(b);
+    cudaFree(ctx->d_descs);
+    cudaFree(ctx->d_pages);
+    cudaFree(ctx->d_lod);
+    cudaFree(ctx->d_work);
+    cudaFree(ctx->d_packed);
+    cudaFree(ctx->pack_v);
+    cudaFree(ctx->pack_i);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int hvx_get_config(const hvx_ctx* ctx, hvx_config* out) {
+    if (!ctx || !out) return HVX_E_INVALID_ARGUMENT;
+    *out = ctx->cfg;
+    return HVX_OK;
+}
+
+uint64_t hvx_allocated_bytes(const hvx_ctx* ctx) { return ctx ? ctx->allocated : 0; }
+uint64_t hvx_launch_count(const hvx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return HVX_OK;
+}
+
+void* hvx_get_stream(const hvx_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+
+int hvx_synchronize(hvx_ctx* ctx) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+int hvx_fill_density(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
+                     uint32_t* d_samples) {
+    return run_fill(ctx, kind, page_xyz, lod, n, d_samples, false);
+}
+
+int hvx_fill_slabs(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
+                   uint32_t* d_slabs) {
+    return run_fill(ctx, kind, page_xyz, lod, n, d_slabs, true);
+}
+
+int hvx_extract_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n) {
+    return run_regular(ctx, samples, words, descs, n, MODE_EXTRACT);
+}
+
+int hvx_classify_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n) {
+    return run_regular(ctx, samples, words, descs, n, MODE_CLASSIFY);
+}
+
+int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t words, const hvx_chunk_desc* descs, uint32_t n) {
+    int rc = check_batch(ctx, descs, n);
+    if (rc) return rc;
+    if (ctx->cfg.max_transition_vertices == 0)
+        return fail(ctx, HVX_E_INVALID_CAPACITY, "Transvoxel transition capacities must be nonzero (vertices=0, indices=0)");
+    const uint64_t expected = static_cast<uint64_t>(n) * slab_words(ctx->cfg.edge);
+    if (words != expected)
+        return fail(ctx, HVX_E_SAMPLE_COUNT, "Transvoxel transition extraction received %llu scalar samples; expected %llu",
+                    static_cast<unsigned long long>(words), static_cast<unsigned long long>(expected));
+    for (uint32_t i = 0; i < n; ++i)
+        if (descs[i].transition_mask & ~0x3fu)
+            return fail(ctx, HVX_E_TRANSITION_MASK, "transition mask %#x uses bits outside the six page faces",
+                        descs[i].transition_mask);
+    if (n == 0) return HVX_OK;
+    DeviceGuard guard(ctx->device);
+    const uint32_t* d_slabs = nullptr;
+    if ((rc = resolve_input(ctx, slabs, words, HVX_BUF_SLABS, &d_slabs))) return rc;
+    if ((rc = upload_descs(ctx, descs, n))) return rc;
+    TransitionParams p{};
+    p.slabs = d_slabs;
+    p.descs = ctx->d_descs;
+    p.n_chunks = n;
+    p.max_vertices = ctx->cfg.max_transition_vertices;
+    p.max_indices = ctx->cfg.max_transition_indices;
+    p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_TRANSITION_VERTICES]);
+    p.indices = static_cast<uint32_t*>(ctx->buf[HVX_BUF_TRANSITION_INDICES]);
+    p.counters = static_cast<hvx_transition_counters*>(ctx->buf[HVX_BUF_TRANSITION_COUNTERS]);
+    p.ranges = static_cast<hvx_range*>(ctx->buf[HVX_BUF_TRANSITION_RANGES]);
+    p.cells = static_cast<hvx_cell_record*>(ctx->buf[HVX_BUF_TRANSITION_CELLS]);
+    p.offsets = static_cast<hvx_cell_offset*>(ctx->buf[HVX_BUF_TRANSITION_OFFSETS]);
+    p.blocks = static_cast<hvx_scan_block*>(ctx->buf[HVX_BUF_TRANSITION_BLOCKS]);
+    p.work_counter = ctx->d_work + 1;
+    cudaError_t e = launch_transition(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_transition");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+void* hvx_buffer(hvx_ctx* ctx, int id) {
+    if (!ctx || id < 0 || id >= HVX_BUF_COUNT) return nullptr;
+    DeviceGuard guard(ctx->device);
+    if (!ctx->buf[id] && ensure_buffer(ctx, id) != HVX_OK) return nullptr;
+    return ctx->buf[id];
+}
+
+uint64_t hvx_buffer_bytes(hvx_ctx* ctx, int id) {
+    if (!ctx || id < 0 || id >= HVX_BUF_COUNT) return 0;
+    return arena_bytes(ctx->cfg, id);
+}
+
+int hvx_read(hvx_ctx* ctx, int id, uint64_t offset, uint64_t bytes, void* dst) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (id < 0 || id >= HVX_BUF_COUNT || !ctx->buf[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "buffer %d is not allocated", id);
+    if (offset + bytes > ctx->buf_bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of buffer %d", id);
+    if (bytes == 0) return HVX_OK;
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(ctx->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+int hvx_write(hvx_ctx* ctx, int id, uint64_t offset, uint64_t bytes, const void* src) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    int rc = ensure_buffer(ctx, id);
+    if (rc) return rc;
+    if (offset + bytes > ctx->buf_bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of buffer %d", id);
+    if (bytes == 0) return HVX_OK;
+    HVX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(ctx->buf[id]) + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+int hvx_read_meshes(hvx_ctx* ctx, int kind, uint32_t first, uint32_t n, hvx_vertex* vertices_out, uint64_t vertex_cap,
+                    uint32_t* indices_out, uint64_t index_cap, hvx_range* ranges_out, uint64_t* total_vertices,
+                    uint64_t* total_indices) {
+    if (!ctx || !ranges_out) return HVX_E_INVALID_ARGUMENT;
+    if (kind != 0 && kind != 1) return fail(ctx, HVX_E_INVALID_ARGUMENT, "kind must be 0 (regular) or 1 (transition)");
+    if (static_cast<uint64_t>(first) + n > ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "chunk range out of bounds");
+    const int vid = kind ? HVX_BUF_TRANSITION_VERTICES : HVX_BUF_REGULAR_VERTICES;
+    const int iid = kind ? HVX_BUF_TRANSITION_INDICES : HVX_BUF_REGULAR_INDICES;
+    const int rid = kind ? HVX_BUF_TRANSITION_RANGES : HVX_BUF_REGULAR_RANGES;
+    if (!ctx->buf[vid]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "this configuration has no %s arenas", kind ? "transition" : "regular");
+    if (total_vertices) *total_vertices = 0;
+    if (total_indices) *total_indices = 0;
+    if (n == 0) return HVX_OK;
+    DeviceGuard guard(ctx->device);
+    std::vector<hvx_range> slot(n);
+    HVX_CUDA(ctx, cudaMemcpyAsync(slot.data(), static_cast<hvx_range*>(ctx->buf[rid]) + first, n * sizeof(hvx_range),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint64_t tv = 0, ti = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        ranges_out[i].first_vertex = static_cast<uint32_t>(tv);
+        ranges_out[i].vertex_count = slot[i].vertex_count;
+        ranges_out[i].first_index = static_cast<uint32_t>(ti);
+        ranges_out[i].index_count = slot[i].index_count;
+        tv += slot[i].vertex_count;
+        ti += slot[i].index_count;
+    }
+    if (total_vertices) *total_vertices = tv;
+    if (total_indices) *total_indices = ti;
+    if (tv > 0xffffffffull || ti > 0xffffffffull) return fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: packed mesh exceeds 32-bit ranges");
+    if (tv > vertex_cap || ti > index_cap || (tv && !vertices_out) || (ti && !indices_out))
+        return fail(ctx, HVX_E_INVALID_CAPACITY, "output capacity too small: need %llu vertices / %llu indices",
+                    static_cast<unsigned long long>(tv), static_cast<unsigned long long>(ti));
+    if (tv == 0 && ti == 0) return HVX_OK;
+    auto grow = [&](void** ptr, uint64_t* have, uint64_t need) -> int {
+        if (*have >= need) return HVX_OK;
+        if (*ptr) {
+            cudaFree(*ptr);
+            ctx->allocated -= *have;
+            *ptr = nullptr;
+            *have = 0;
+        }
+        const uint64_t bytes = need + need / 4 + 4096;
+        cudaError_t e = cudaMalloc(ptr, bytes);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(pack staging)");
+        *have = bytes;
+        ctx->allocated += bytes;
+        return HVX_OK;
+    };
+    int rc;
+    if ((rc = grow(&ctx->pack_v, &ctx->pack_v_bytes, tv * sizeof(hvx_vertex)))) return rc;
+    if ((rc = grow(&ctx->pack_i, &ctx->pack_i_bytes, ti * 4))) return rc;
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed, ranges_out, n * sizeof(hvx_range), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = launch_pack(static_cast<hvx_vertex*>(ctx->buf[vid]), static_cast<uint32_t*>(ctx->buf[iid]),
+                                static_cast<hvx_range*>(ctx->buf[rid]) + first, ctx->d_packed, n,
+                                static_cast<hvx_vertex*>(ctx->pack_v), static_cast<uint32_t*>(ctx->pack_i), ctx->dev,
+                                ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_pack");
+    ctx->launches += 1;
+    if (tv) HVX_CUDA(ctx, cudaMemcpyAsync(vertices_out, ctx->pack_v, tv * sizeof(hvx_vertex), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ti) HVX_CUDA(ctx, cudaMemcpyAsync(indices_out, ctx->pack_i, ti * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+}  // extern "C"

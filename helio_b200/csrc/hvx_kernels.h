@@ -1,0 +1,79 @@
+// hvx_kernels.h -- launch interface between the C-ABI layer (hvx_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hvx.h"
+
+namespace hvx {
+
+// Device copy of one chunk's dispatch parameters (hvx_chunk_desc).
+struct ChunkDesc {
+    uint64_t generation;
+    uint64_t dirty_microbricks;
+    uint32_t transition_mask;
+    uint32_t _pad;
+};
+
+enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1 };
+
+struct RegularParams {
+    const uint32_t* samples;  // [n][(E+2)^3]
+    const ChunkDesc* descs;   // [n] device
+    uint32_t n_chunks;
+    uint32_t mode;
+    uint32_t max_vertices, max_indices;  // per-chunk slot capacity
+    hvx_vertex* vertices;                // [n][max_vertices]
+    uint32_t* indices;                   // [n][max_indices]
+    hvx_emission_counters* counters;     // [n]
+    hvx_classify_counters* classify;     // [n]
+    hvx_range* ranges;                   // [n]
+    hvx_cell_record* cells;              // debug, nullable: [n][E^3]
+    hvx_cell_offset* offsets;            // debug, nullable
+    hvx_scan_block* blocks;              // debug, nullable: [n][E^3/256]
+    uint32_t* work_counter;              // dynamic chunk queue, zeroed before launch
+};
+
+struct TransitionParams {
+    const uint32_t* slabs;  // [n][6][3][(2E+3)^2]
+    const ChunkDesc* descs;
+    uint32_t n_chunks;
+    uint32_t max_vertices, max_indices;
+    hvx_vertex* vertices;
+    uint32_t* indices;
+    hvx_transition_counters* counters;
+    hvx_range* ranges;
+    hvx_cell_record* cells;    // debug, nullable: [n][6*E^2]
+    hvx_cell_offset* offsets;  // debug, nullable
+    hvx_scan_block* blocks;    // debug, nullable: [n][6*E^2/256]
+    uint32_t* work_counter;
+};
+
+struct FillParams {
+    uint32_t kind;
+    uint32_t n_chunks;
+    const int64_t* page_xyz;  // [n][3] device
+    const uint8_t* lod;       // [n] device
+    uint32_t* out;
+};
+
+struct DeviceInfo {
+    int sm_count;
+    int max_smem_optin;
+};
+
+// Each returns the number of kernels launched (>= 1) or a negative cudaError-mapped status.
+cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_fill_samples(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
+// Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
+cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,
+                        const hvx_range* packed_ranges, uint32_t n, hvx_vertex* out_vertices,
+                        uint32_t* out_indices, const DeviceInfo& dev, cudaStream_t stream);
+
+// shared-memory footprint of the regular kernel (for resource reporting / tests)
+size_t regular_smem_bytes(int edge);
+
+}  // namespace hvx

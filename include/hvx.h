@@ -1,0 +1,263 @@
+/* hvx.h -- C ABI of libhelio_voxel_cuda.so: B200-native Transvoxel chunk extraction.
+ *
+ * This is the drop-in boundary for ONE path of Far-Beyond-Pulsar/Helio: the
+ * planetary-voxel mesh extractor.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference tree; PV =
+ * crates/passes/3d/helio-pass-planetary-voxel).  The Rust crate
+ * `helio-voxel-cuda` (rust/helio-voxel-cuda) binds exactly
+ * these symbols; so do helio_b200/ (ctypes) and include/helio_voxel_cuda.hpp.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns HVX_OK (0) or a
+ *     negative hvx_status; hvx_last_error() gives the formatted message.
+ *   - one hvx_ctx = one device + one stream + one set of output arenas.  Like
+ *     the reference extractor (`&self`, one page in flight) a ctx is not
+ *     re-entrant: calls on one ctx must be serialised by the caller.
+ *   - extraction calls are asynchronous on the ctx stream; hvx_synchronize()
+ *     or any hvx_read_*() waits.
+ *   - byte layouts of vertices, counters and per-cell records equal the
+ *     reference PODs so Rust can bytemuck::cast_slice them.
+ *   - there is no CPU fallback: without a CUDA device hvx_create fails with
+ *     HVX_E_CUDA.
+ */
+#ifndef HVX_H
+#define HVX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HVX_ABI_VERSION 1u
+
+/* Errors.  -1..-4 mirror PV/src/transvoxel_gpu.rs:445-459 TransvoxelGpuError and
+ * PV/src/transvoxel_transition_gpu.rs:712-732 TransvoxelTransitionGpuError. */
+typedef enum {
+    HVX_OK = 0,
+    HVX_E_SAMPLE_COUNT = -1,        /* SampleCount { actual, expected } */
+    HVX_E_INVALID_CAPACITY = -2,    /* InvalidExtractionCapacity */
+    HVX_E_DEVICE_LIMIT = -3,        /* DeviceLimit { name, required, available } */
+    HVX_E_TRANSITION_MASK = -4,     /* TransitionMask(u8) */
+    HVX_E_INVALID_ARGUMENT = -5,
+    HVX_E_CUDA = -6,
+    HVX_E_BATCH_CAPACITY = -7,      /* n > hvx_config.max_chunks */
+    HVX_E_FINEST_LOD = -8,          /* TransvoxelTransitionError::FinestLodHasNoFinerNeighbor */
+    HVX_E_ADDRESS = -9,             /* AddressError::{UnsupportedLod, CoordinateOverflow} */
+    /* PV/src/lod_topology.rs:369-401 TerrainLodTopologyError */
+    HVX_E_TOPOLOGY_EMPTY = -20,
+    HVX_E_TOPOLOGY_DUPLICATE = -21,
+    HVX_E_TOPOLOGY_OVERLAP = -22,
+    HVX_E_TOPOLOGY_UNBALANCED = -23,
+    HVX_E_TOPOLOGY_ROOT_LOD = -24,
+    HVX_E_TOPOLOGY_MINIMUM_LOD = -25,
+    HVX_E_TOPOLOGY_PAGE_BUDGET = -26,
+    HVX_E_TOPOLOGY_MISSING_PARENT = -27,
+    HVX_E_TOPOLOGY_COVERAGE = -28
+} hvx_status;
+
+/* PV/src/extraction.rs:72-79 GpuTerrainVertex (repr(C, align(16)), 32 B). */
+typedef struct {
+    float position[3];
+    uint32_t material;
+    float normal[3];
+    uint32_t flags;
+} hvx_vertex;
+
+/* PV/src/transvoxel_emit.rs:38-48 GpuTransvoxelEmissionCounters (32 B), one per chunk.
+ * Capacity overflow is NOT an error: *_overflow = 1, emitted_* = 0, completed = 1 and
+ * required_* is the true need (PV/tests/gpu_transvoxel_emission.rs:249-262). */
+typedef struct {
+    uint32_t required_vertices, required_indices;
+    uint32_t emitted_vertices, emitted_indices;
+    uint32_t vertex_overflow, index_overflow;
+    uint32_t completed, _pad;
+} hvx_emission_counters;
+
+/* PV/src/transvoxel_gpu.rs:134-141 GpuTransvoxelClassifyCounters (16 B), one per chunk. */
+typedef struct {
+    uint32_t visited_cells, active_cells, vertices, triangles;
+} hvx_classify_counters;
+
+/* PV/src/transvoxel_transition_gpu.rs:133-146 GpuTransvoxelTransitionCounters (48 B). */
+typedef struct {
+    uint32_t active_cells, active_faces;
+    uint32_t required_vertices, required_indices;
+    uint32_t emitted_vertices, emitted_indices;
+    uint32_t vertex_overflow, index_overflow;
+    uint32_t completed, _pad[3];
+} hvx_transition_counters;
+
+/* PV/src/transvoxel_gpu.rs:77-84 GpuTransvoxelCell and
+ * PV/src/transvoxel_transition_gpu.rs:67-74 GpuTransvoxelTransitionCell (16 B).
+ *   regular:    case | class<<8 | nv<<16 | nt<<24 | 1<<31
+ *   transition: case | class_code<<9 | nv<<17 | nt<<21 | 1<<31 */
+typedef struct {
+    uint32_t packed_case_class_counts, generation_low, generation_high, _pad;
+} hvx_cell_record;
+
+/* PV/src/transvoxel_emit.rs:14-21 GpuTransvoxelCellOffset: offsets RELATIVE to the cell's
+ * 256-cell scan block; add hvx_scan_block.first_* for the chunk-local value. */
+typedef struct {
+    uint32_t first_vertex, first_index, generation_low, generation_high;
+} hvx_cell_offset;
+
+/* PV/src/transvoxel_emit.rs:29-36 GpuTransvoxelScanBlock (one per 256 cells). */
+typedef struct {
+    uint32_t vertex_count, index_count, first_vertex, first_index;
+} hvx_scan_block;
+
+/* Where chunk k's mesh lives in the ctx arenas (elements, not bytes).  Slots are
+ * fixed-stride (k * max_vertices, k * max_indices), like the reference's per-slot
+ * banked arenas (PV/src/surface_publish.wgsl:126-220); index values are chunk-local. */
+typedef struct {
+    uint32_t first_vertex, vertex_count, first_index, index_count;
+} hvx_range;
+
+/* Per-chunk dispatch parameters: the variable part of
+ * PV/src/transvoxel_gpu.rs:15-32 GpuTransvoxelDispatch /
+ * PV/src/transvoxel_transition_gpu.rs:31-42 GpuTransvoxelTransitionDispatch. */
+typedef struct {
+    uint64_t generation;
+    uint64_t dirty_microbricks; /* 4x4x4 microbricks of (edge/4)^3 cells; bit = mx + 4*my + 16*mz */
+    uint32_t transition_mask;   /* TransitionFace bits 0..5 (-X,+X,-Y,+Y,-Z,+Z) */
+    uint32_t _pad;
+} hvx_chunk_desc;
+
+/* PV/src/transvoxel_emit.rs:57-85 TransvoxelGpuExtractorConfig +
+ * PV/src/transvoxel_transition_gpu.rs:154-181, widened to a batch of chunks. */
+typedef struct {
+    uint32_t edge;                    /* 32 (the reference's PAGE_EDGE) or 64 */
+    uint32_t max_chunks;              /* batch capacity (reference: 1) */
+    uint32_t max_vertices;            /* per chunk, regular; reference default 393,216 */
+    uint32_t max_indices;             /* per chunk, regular; reference default 491,520 */
+    uint32_t max_transition_vertices; /* per chunk; reference default 73,728; 0 = transitions unused */
+    uint32_t max_transition_indices;  /* per chunk; reference default 221,184 */
+    uint32_t flags;                   /* HVX_CFG_* */
+    uint32_t _reserved;
+} hvx_config;
+
+#define HVX_CFG_DEBUG_RECORDS 1u /* also write per-cell records, offsets and scan blocks */
+
+typedef struct hvx_ctx hvx_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* TransvoxelGpuExtractor::new / TransvoxelGpuTransitionExtractor::new
+ * (PV/src/transvoxel_emit.rs:114-231, PV/src/transvoxel_transition_gpu.rs:213-364). */
+int hvx_create(hvx_ctx** out, int device, const hvx_config* config);
+void hvx_destroy(hvx_ctx* ctx);
+/* ctx may be NULL: returns the calling thread's last creation error. */
+const char* hvx_last_error(const hvx_ctx* ctx);
+const char* hvx_status_name(int status);
+uint32_t hvx_abi_version(void);
+int hvx_get_config(const hvx_ctx* ctx, hvx_config* out);
+/* resource_stats() (PV/src/transvoxel_emit.rs:87-91): device bytes currently allocated. */
+uint64_t hvx_allocated_bytes(const hvx_ctx* ctx);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the ctx stream. */
+int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream);
+void* hvx_get_stream(const hvx_ctx* ctx);
+int hvx_synchronize(hvx_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
+uint64_t hvx_launch_count(const hvx_ctx* ctx);
+
+/* ---- K1: density / SDF fill -------------------------------------------------------- */
+/* ExtractionFixture::new (PV/src/fixture.rs:95-124) on the device.
+ * kind: 0..5 = ExtractionFixtureKind order (plane, sphere, cave, sharp_corner, thin_slab,
+ * material_seam); 16 = fBm terrain (helio-pass-sdf noise.rs terrain_sdf, Rolling), 17 = dense
+ * random.  page_xyz: host [n][3]; lod: host [n] or NULL (all 0).  d_samples: device,
+ * n*(edge+2)^3 words, x fastest; NULL = the ctx sample arena (hvx_buffer(HVX_BUF_SAMPLES)). */
+int hvx_fill_density(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
+                     uint32_t* d_samples);
+/* TransvoxelTransitionFaceFixture::slab_samples for six faces
+ * (PV/src/transvoxel_transition.rs:335-349): n * 6*3*(2*edge+3)^2 words; lod[i] >= 1. */
+int hvx_fill_slabs(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
+                   uint32_t* d_slabs);
+
+/* ---- K2-K4: regular cells ---------------------------------------------------------- */
+/* TransvoxelGpuExtractor::dispatch (PV/src/transvoxel_emit.rs:233-254) over n chunks.
+ * samples: HOST or DEVICE pointer (detected), n*(edge+2)^3 CellWords, 16-byte aligned;
+ * NULL = the ctx sample arena.  sample_words is the caller's slice length and must equal
+ * n*(edge+2)^3 (else HVX_E_SAMPLE_COUNT).  descs: host [n]. */
+int hvx_extract_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t sample_words,
+                        const hvx_chunk_desc* descs, uint32_t n);
+/* TransvoxelGpuClassifier::dispatch (PV/src/transvoxel_gpu.rs:268-286): classification +
+ * classify counters (+ cell records when HVX_CFG_DEBUG_RECORDS), no emission. */
+int hvx_classify_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t sample_words,
+                         const hvx_chunk_desc* descs, uint32_t n);
+
+/* ---- K2-K4 (T): transition cells ---------------------------------------------------- */
+/* TransvoxelGpuTransitionExtractor::dispatch (PV/src/transvoxel_transition_gpu.rs:366-380).
+ * slabs: HOST or DEVICE, n * 6*3*(2*edge+3)^2 words (face-major, then layer, v, u).
+ * descs[i].transition_mask selects faces; bits above 0x3f -> HVX_E_TRANSITION_MASK. */
+int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t slab_words,
+                           const hvx_chunk_desc* descs, uint32_t n);
+
+/* ---- outputs ------------------------------------------------------------------------ */
+typedef enum {
+    HVX_BUF_SAMPLES = 0,             /* u32  [max_chunks][(edge+2)^3]          (lazy) */
+    HVX_BUF_SLABS = 1,               /* u32  [max_chunks][6*3*(2*edge+3)^2]    (lazy) */
+    HVX_BUF_REGULAR_VERTICES = 2,    /* hvx_vertex [max_chunks][max_vertices]            vertices_buffer() */
+    HVX_BUF_REGULAR_INDICES = 3,     /* u32  [max_chunks][max_indices]                   indices_buffer()  */
+    HVX_BUF_REGULAR_COUNTERS = 4,    /* hvx_emission_counters [max_chunks]               counters_buffer() */
+    HVX_BUF_REGULAR_CLASSIFY = 5,    /* hvx_classify_counters [max_chunks]  classifier.counters_buffer() */
+    HVX_BUF_REGULAR_RANGES = 6,      /* hvx_range [max_chunks] */
+    HVX_BUF_REGULAR_CELLS = 7,       /* hvx_cell_record [max_chunks][edge^3]   (debug)  output_buffer()  */
+    HVX_BUF_REGULAR_OFFSETS = 8,     /* hvx_cell_offset [max_chunks][edge^3]   (debug)  offsets_buffer() */
+    HVX_BUF_REGULAR_BLOCKS = 9,      /* hvx_scan_block  [max_chunks][edge^3/256] (debug) blocks_buffer() */
+    HVX_BUF_TRANSITION_VERTICES = 10,
+    HVX_BUF_TRANSITION_INDICES = 11,
+    HVX_BUF_TRANSITION_COUNTERS = 12, /* hvx_transition_counters [max_chunks] */
+    HVX_BUF_TRANSITION_RANGES = 13,
+    HVX_BUF_TRANSITION_CELLS = 14,    /* [max_chunks][6*edge^2] (debug) cells_buffer() */
+    HVX_BUF_TRANSITION_OFFSETS = 15,
+    HVX_BUF_TRANSITION_BLOCKS = 16,   /* [max_chunks][6*edge^2/256] */
+    HVX_BUF_COUNT = 17
+} hvx_buffer_id;
+
+/* Device pointer / size of a ctx arena (allocating it if lazy); NULL / 0 if unavailable. */
+void* hvx_buffer(hvx_ctx* ctx, int buffer_id);
+uint64_t hvx_buffer_bytes(hvx_ctx* ctx, int buffer_id);
+/* Synchronising device->host copy of [byte_offset, byte_offset + bytes) of an arena. */
+int hvx_read(hvx_ctx* ctx, int buffer_id, uint64_t byte_offset, uint64_t bytes, void* host_dst);
+/* Host->device copy into an arena (samples / slabs upload for device-resident workflows). */
+int hvx_write(hvx_ctx* ctx, int buffer_id, uint64_t byte_offset, uint64_t bytes, const void* host_src);
+/* Gather the emitted meshes of chunks [first, first+n) into tightly packed host arrays in chunk
+ * order (vertices then indices, index values stay chunk-local).  kind 0 = regular, 1 = transition.
+ * ranges_out[n] receives the packed placement.  *_cap in elements; returns HVX_E_INVALID_CAPACITY
+ * if too small (ranges_out is still filled so the caller can size the buffers). */
+int hvx_read_meshes(hvx_ctx* ctx, int kind, uint32_t first, uint32_t n, hvx_vertex* vertices_out,
+                    uint64_t vertex_cap, uint32_t* indices_out, uint64_t index_cap, hvx_range* ranges_out,
+                    uint64_t* total_vertices, uint64_t* total_indices);
+
+/* ---- host-side LOD scheduler input (no GPU involved) --------------------------------- */
+/* PV/src/lod_topology.rs.  hvx_page is PageKey + the derived coarse-owned transition mask. */
+typedef struct {
+    int64_t page_xyz[3];
+    uint8_t lod;
+    uint8_t transition_mask;
+    uint8_t _pad[6];
+} hvx_page;
+
+typedef struct {
+    uint32_t pages, minimum_lod, maximum_lod, transition_faces;
+} hvx_lod_stats;
+
+/* TerrainLodTopology::new (PV/src/lod_topology.rs:27-100): sorts pages into PageKey order
+ * (lod, then xyz), validates and fills transition_mask. */
+int hvx_lod_topology(hvx_page* pages, uint32_t n, uint32_t edge, hvx_lod_stats* stats);
+/* HorizonLodFixturePlan::build_with_minimum_lod (PV/src/lod_topology.rs:169-217).
+ * out[max_pages]; *n_out pages written in PageKey order with masks; root_out optional. */
+int hvx_horizon_plan(const int64_t focus_lod0_cell[3], uint32_t root_lod, uint32_t minimum_lod,
+                     uint32_t max_pages, uint32_t edge, hvx_page* out, uint32_t* n_out, hvx_page* root_out,
+                     hvx_lod_stats* stats);
+/* Static multi-GPU partition: LPT-greedy assignment of chunks to ranks by cost;
+ * owner[i] in [0, ranks).  Deterministic (ties -> lower chunk index, lower rank). */
+int hvx_partition_chunks(const uint64_t* cost, uint32_t n, uint32_t ranks, uint32_t* owner);
+/* Cost model used by the scheduler: bytes a chunk moves (samples + slabs of masked faces). */
+uint64_t hvx_chunk_cost(uint32_t edge, uint32_t transition_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HVX_H */

@@ -1,0 +1,225 @@
+"""GPU parity: regular-cell extraction through the C ABI vs the CPU oracle.
+
+Mirrors PV/tests/gpu_transvoxel.rs:10-136 and PV/tests/gpu_transvoxel_emission.rs:12-264, with the
+float tolerance tightened from the reference's 1e-5 / 2e-4 to bit equality.
+"""
+import numpy as np
+import pytest
+
+import helio_b200 as H
+from oracle import oracle as O
+from hvx_testutil import ALL, FIXTURE_PAGES, assert_vertices_equal, check_offsets
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def extractor():
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig())
+    yield ex
+    ex.close()
+
+
+def _check_dispatch(ex, samples, generation, dirty, mask, label, edge=32):
+    want = O.extract_regular(samples, edge=edge, generation=generation, dirty_microbricks=dirty, transition_mask=mask)
+    ex.dispatch(samples, generation, dirty, mask)
+    counters = ex.counters_buffer()
+    assert counters["completed"] == 1, label
+    assert counters["vertex_overflow"] == 0 and counters["index_overflow"] == 0, label
+    assert counters["required_vertices"] == len(want.vertices), label
+    assert counters["required_indices"] == len(want.indices), label
+    assert counters["emitted_vertices"] == counters["required_vertices"]
+    assert counters["emitted_indices"] == counters["required_indices"]
+    got_v = ex.vertices_buffer(len(want.vertices))
+    got_i = ex.indices_buffer(len(want.indices))
+    assert_vertices_equal(got_v, want.vertices, label)
+    assert np.array_equal(got_i, want.indices), f"{label}: indices"
+    cls = ex.classify_counters_buffer()
+    assert [int(cls[k]) for k in ("visited_cells", "active_cells", "vertices", "triangles")] == list(want.classify), label
+    return want, got_v, got_i
+
+
+@pytest.mark.parametrize("name", list(FIXTURE_PAGES))
+def test_emission_matches_cpu_geometry_on_every_fixture(extractor, name):
+    kind, page = FIXTURE_PAGES[name]
+    generation = 1000 + kind
+    samples = O.fixture_fill(kind, page)
+    want, got_v, got_i = _check_dispatch(extractor, samples, generation, ALL, 0, name)
+    # per-cell records and ranges (debug outputs a6 / a11)
+    cells = extractor.cells_buffer()
+    assert np.array_equal(cells["packed_case_class_counts"], want.cell_words[:, 0]), name
+    assert np.array_equal(cells["generation_low"], want.cell_words[:, 1]), name
+    check_offsets(extractor.offsets_buffer(), extractor.blocks_buffer(), want.cell_ranges, generation, name)
+    # byte-identical on repeat (gpu_transvoxel_emission.rs:125-151)
+    extractor.dispatch(samples, generation, ALL, 0)
+    assert extractor.vertices_buffer(len(got_v)).tobytes() == got_v.tobytes()
+    assert np.array_equal(extractor.indices_buffer(len(got_i)), got_i)
+
+
+def test_published_fixture_counts(extractor):
+    """docs/planetary_voxel_extraction_benchmark.md:59-70 vertex / triangle counts."""
+    published = {"plane": (4096, 2048), "sphere": (1323, 661), "cave": (1311, 655), "sharp_corner": (3, 1),
+                 "thin_slab": (4096, 2048), "material_seam": (4096, 2048)}
+    for name, (kind, page) in FIXTURE_PAGES.items():
+        extractor.dispatch(O.fixture_fill(kind, page), 5, ALL, 0)
+        c = extractor.counters_buffer()
+        assert (int(c["emitted_vertices"]), int(c["emitted_indices"]) // 3) == published[name], name
+
+
+def test_dirty_microbrick_subset(extractor):
+    """gpu_transvoxel_emission.rs:154-214: only microbrick 12 is revisited; other cells keep stale records."""
+    samples = O.fixture_fill(O.FIELD_PLANE, [0, -1, 0])
+    extractor.dispatch(samples, 1400, ALL, 0)
+    want, _, _ = _check_dispatch(extractor, samples, 1500, 1 << 12, 0, "dirty")
+    assert len(want.vertices) > 0
+    gen = check_offsets(extractor.offsets_buffer(), extractor.blocks_buffer(), want.cell_ranges, 1500, "dirty")
+    visited = want.cell_ranges[:, 0] != 0xFFFFFFFF
+    assert visited.sum() == 512 and np.all(gen[~visited] != 1500)
+    cells = extractor.cells_buffer()
+    assert np.all(cells["generation_low"][visited] == 1500) and np.all(cells["generation_low"][~visited] == 1400)
+    cls = extractor.classify_counters_buffer()
+    assert cls["visited_cells"] == 8 * 8 * 8 and cls["active_cells"] > 0
+
+
+def test_secondary_position_on_transition_face(extractor):
+    """gpu_transvoxel_emission.rs:216-247: +X boundary vertices move to x = 31.75."""
+    samples = O.fixture_fill(O.FIELD_PLANE, [0, -1, 0])
+    mask = H.TransitionFace.PositiveX.bit()
+    _, got_v, _ = _check_dispatch(extractor, samples, 1750, ALL, mask, "secondary")
+    x, z = got_v["position"][:, 0], got_v["position"][:, 2]
+    interior = (z >= 1.0) & (z < 31.0)
+    assert np.any((np.abs(x - 31.75) <= 1e-5) & interior)
+    assert not np.any((np.abs(x - 32.0) <= 1e-5) & interior)
+
+
+@pytest.mark.parametrize("mask", [0x3F, 0x15, 0x2A, 0x01, 0x24])
+def test_secondary_positions_all_faces(extractor, mask):
+    for kind, page in [(O.FIELD_SPHERE, [0, 0, 0]), (O.FIELD_SPHERE, [-1, -1, -1]), (O.FIELD_CAVE, [-1, 0, -1])]:
+        _check_dispatch(extractor, O.fixture_fill(kind, page), 3, ALL, mask, f"mask {mask:#x} {page}")
+
+
+def test_overflow_contract():
+    """gpu_transvoxel_emission.rs:249-262: capacity (1,1) suppresses the emission, reports the need."""
+    tiny = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig.new(1, 1))
+    tiny.dispatch(O.fixture_fill(O.FIELD_PLANE, [0, -1, 0]), 2000, ALL, 0)
+    c = tiny.counters_buffer()
+    assert c["completed"] == 1 and c["vertex_overflow"] != 0 and c["index_overflow"] != 0
+    assert c["emitted_vertices"] == 0 and c["emitted_indices"] == 0
+    assert c["required_vertices"] == 4096 and c["required_indices"] == 6144
+    tiny.close()
+
+
+def test_errors_mirror_the_reference(extractor):
+    samples = O.fixture_fill(O.FIELD_PLANE, [0, -1, 0])
+    with pytest.raises(H.SampleCount) as info:
+        extractor.dispatch(samples[:-1], 1, ALL, 0)
+    assert info.value.actual == 34 ** 3 - 1 and info.value.expected == 34 ** 3
+    with pytest.raises(H.InvalidExtractionCapacity):
+        H.TransvoxelGpuExtractorConfig.new(0, 5)
+    with pytest.raises(H.InvalidExtractionCapacity):
+        H.Context(0, max_vertices=0, max_indices=4)
+    stats = extractor.resource_stats()
+    extractor.resize(3840, 2160)
+    assert extractor.resource_stats() == stats
+
+
+def test_classifier_matches_cpu(extractor):
+    """gpu_transvoxel.rs:10-136: every GpuTransvoxelCell + counters, determinism, dirty subset."""
+    clf = H.TransvoxelGpuClassifier(0)
+    for name, (kind, page) in FIXTURE_PAGES.items():
+        samples = O.fixture_fill(kind, page)
+        want = O.extract_regular(samples, generation=10 + kind)
+        clf.dispatch(samples, 10 + kind, ALL)
+        cells = clf.output_buffer()
+        assert np.array_equal(cells["packed_case_class_counts"], want.cell_words[:, 0]), name
+        assert np.array_equal(cells["generation_low"], want.cell_words[:, 1]), name
+        c = clf.counters_buffer()
+        assert [int(c[k]) for k in c.dtype.names] == list(want.classify), name
+        clf.dispatch(samples, 10 + kind, ALL)
+        assert clf.output_buffer().tobytes() == cells.tobytes()
+    samples = O.fixture_fill(O.FIELD_PLANE, [0, -1, 0])
+    want = O.extract_regular(samples, generation=100, dirty_microbricks=1 << 12)
+    clf.dispatch(samples, 100, 1 << 12)
+    c = clf.counters_buffer()
+    assert [int(c[k]) for k in c.dtype.names] == list(want.classify) and c["visited_cells"] == 512
+    with pytest.raises(H.SampleCount):
+        clf.dispatch(samples[:-1], 100, ALL)
+    clf.close()
+
+
+def test_device_resident_samples(extractor):
+    """Device pointers are used in place (no staging copy)."""
+    torch = pytest.importorskip("torch")
+    samples = O.fixture_fill(O.FIELD_CAVE, [0, 0, 0])
+    want = O.extract_regular(samples, generation=77)
+    dev = torch.from_numpy(samples.view(np.int32)).cuda()
+    extractor.dispatch(dev, 77, ALL, 0)
+    assert_vertices_equal(extractor.vertices_buffer(len(want.vertices)), want.vertices, "device input")
+    assert np.array_equal(extractor.indices_buffer(len(want.indices)), want.indices)
+
+
+# ---- edge 64 (no reference counterpart: pinned by the oracle's generalisation over the edge) ----
+
+@pytest.mark.parametrize("kind,page,lod", [
+    (O.FIELD_SPHERE, [0, 0, 0], 0), (O.FIELD_SPHERE, [-1, -1, -1], 0), (O.FIELD_PLANE, [0, -1, 0], 0),
+    (O.FIELD_CAVE, [-1, 0, 0], 0), (O.FIELD_SHARP_CORNER, [0, 0, 0], 0), (O.FIELD_MATERIAL_SEAM, [-1, -1, 0], 1),
+    (O.FIELD_TERRAIN_FBM, [0, -1, 0], 0), (O.FIELD_TERRAIN_FBM, [3, -1, -7], 0), (O.FIELD_TERRAIN_FBM, [0, -1, 0], 2),
+])
+def test_edge64_matches_oracle(kind, page, lod):
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig(262_144, 393_216), edge=64)
+    samples = O.fixture_fill(kind, page, lod=lod, edge=64)
+    for mask, dirty in [(0, ALL), (0x3F, ALL), (0x12, 0x0F0F_0000_FFFF_00F0)]:
+        want, _, _ = _check_dispatch(ex, samples, 42, dirty, mask, f"e64 kind {kind} {page} mask {mask:#x}", edge=64)
+        cells = ex.cells_buffer()
+        visited = want.cell_ranges[:, 0] != 0xFFFFFFFF
+        assert np.array_equal(cells["packed_case_class_counts"][visited], want.cell_words[visited, 0])
+        check_offsets(ex.offsets_buffer(), ex.blocks_buffer(), want.cell_ranges, 42, "e64")
+    ex.close()
+
+
+@pytest.mark.parametrize("edge", [32, 64])
+def test_dense_random_worst_case(edge):
+    """Dense adversarial field: ~6 vertices per cell, every emission batch full."""
+    cells = edge ** 3
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig(cells * 12, cells * 15), edge=edge, debug_records=False)
+    samples = O.fixture_fill(O.FIELD_DENSE_RANDOM, [1, 2, 3], edge=edge)
+    want, _, _ = _check_dispatch(ex, samples, 9, ALL, 0x3F, f"dense e{edge}", edge=edge)
+    assert len(want.vertices) > 4 * cells
+    ex.close()
+
+
+@pytest.mark.parametrize("edge", [32, 64])
+def test_batch_of_mixed_chunks(edge):
+    """N chunks per dispatch: every chunk's slot equals its single-chunk oracle result."""
+    specs = [(O.FIELD_SPHERE, [0, 0, 0]), (O.FIELD_PLANE, [0, 1, 0]), (O.FIELD_PLANE, [0, -1, 0]),
+             (O.FIELD_TERRAIN_FBM, [0, -1, 0]), (O.FIELD_CAVE, [-1, -1, -1]), (O.FIELD_PLANE, [5, -3, 2]),
+             (O.FIELD_TERRAIN_FBM, [2, -1, 1]), (O.FIELD_SHARP_CORNER, [0, 0, 0])] * 40  # 320 chunks > 148 SMs
+    n = len(specs)
+    batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=40_000, max_indices=60_000)
+    samples = np.concatenate([O.fixture_fill(k, p, edge=edge) for k, p in specs[:8]] * 40)
+    masks = [(i * 7) % 64 for i in range(n)]
+    gens = [100 + i for i in range(n)]
+    batch.extract_regular(samples, n, generation=gens, transition_mask=masks)
+    counters = batch.counters(n)
+    ranges = batch.ranges(n)
+    wants = {}
+    for i in range(n):
+        key = (i % 8, masks[i])
+        if key not in wants:
+            wants[key] = O.extract_regular(samples[(i % 8) * (edge + 2) ** 3:(i % 8 + 1) * (edge + 2) ** 3], edge=edge,
+                                           transition_mask=masks[i], debug=False)
+        want = wants[key]
+        assert counters["completed"][i] == 1 and counters["required_vertices"][i] == len(want.vertices), i
+        assert ranges["first_vertex"][i] == i * 40_000 and ranges["vertex_count"][i] == len(want.vertices)
+        assert ranges["first_index"][i] == i * 60_000 and ranges["index_count"][i] == len(want.indices)
+    # spot-check full meshes, and the packed readback of the whole batch
+    verts, idx, packed = batch.ctx.read_meshes(0, 0, n)
+    for i in list(range(0, n, 37)) + [n - 1]:
+        want = wants[(i % 8, masks[i])]
+        r = packed[i]
+        assert_vertices_equal(verts[r["first_vertex"]:r["first_vertex"] + r["vertex_count"]], want.vertices, f"chunk {i}")
+        assert np.array_equal(idx[r["first_index"]:r["first_index"] + r["index_count"]], want.indices), i
+    assert batch.ctx.launch_count >= 2
+    with pytest.raises(H.BatchCapacity):
+        batch.extract_regular(np.zeros((n + 1) * (edge + 2) ** 3, dtype=np.uint32), n + 1)
+    batch.close()
