@@ -1,0 +1,330 @@
+#!/usr/bin/env python3
+"""bench.py -- Transvoxel chunk-extraction throughput on B200 (BASELINE.json metric).
+
+Workload (BASELINE configs[1]): a 16x16x16 grid of 64^3-cell chunks of procedural
+fBm terrain (helio-pass-sdf `terrain_sdf`, TerrainConfig::rolling(), 0.1 m voxels), 4096 chunks,
+4.71 GB of CellWord samples.  One "step" = one regular-cell extraction pass over the whole batch.
+
+  value        cells/s with the samples already resident in HBM (CUDA events on the launch stream)
+  e2e          the same metric through the C-ABI call with HOST buffers: pinned host samples ->
+               H2D -> extraction -> packed mesh + counters -> D2H into pinned host memory
+  roofline     algorithmic bytes (4*(E+2)^3 + 32*V + 4*I per chunk) / kernel time vs measured HBM peak
+  cpu_baseline the CPU oracle (restating the reference's Rust CPU extractor) on this box's cores,
+               on a bounded sample of the same chunks
+
+`--impl reference` times that CPU implementation alone (the reference itself is Rust + wgpu and
+cannot be built in this image).  Multi-GPU (`torchrun ... --gpus N`): the chunk
+list grows with N (weak scaling), is partitioned by the LPT scheduler, no data-path collective.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+EDGE = 64
+GRID = 16                      # chunks per axis at N=1
+FIELD_TERRAIN_FBM = 16
+MAX_VERTICES, MAX_INDICES = 49_152, 73_728   # per-chunk slot capacity (surface chunks need ~25k / ~37k)
+
+
+def chunk_grid(n_gpus: int) -> np.ndarray:
+    """Global chunk list: page_xyz in [-8, 8)^3 per GPU, extended along +x for N > 1 (x fastest)."""
+    xs = np.arange(-GRID // 2, -GRID // 2 + GRID * n_gpus, dtype=np.int64)
+    ys = np.arange(-GRID // 2, GRID // 2, dtype=np.int64)
+    zs = np.arange(-GRID // 2, GRID // 2, dtype=np.int64)
+    z, y, x = np.meshgrid(zs, ys, xs, indexing="ij")
+    return np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+
+
+def measured_peak_gbs():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.lines = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.proc.wait()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, value in zip(names, parts[4:8]):
+                if value.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle's restatement of the reference CPU extractor, all host threads."""
+    from oracle import oracle as O
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = O.max_threads()
+    pages = chunk_grid(1)
+    sample = pages[args.cpu_offset::args.cpu_stride]          # bounded, y-uniform sample of the workload
+    words = (EDGE + 2) ** 3
+    samples = O.batch_fill(FIELD_TERRAIN_FBM, sample, EDGE, threads=threads)   # setup (untimed)
+    for _ in range(args.warmup):
+        O.batch_regular(FIELD_TERRAIN_FBM, sample[:threads], EDGE, threads=threads, do_fill=False,
+                        samples=samples[:threads * words])
+    t0 = time.perf_counter()
+    cells = 0
+    for _ in range(args.steps):
+        c, totals = O.batch_regular(FIELD_TERRAIN_FBM, sample, EDGE, threads=threads, do_fill=False, samples=samples)
+        cells += c
+    dt = time.perf_counter() - t0
+    value = cells / dt
+    desc = f"{len(sample)} of 4096 chunks (every {args.cpu_stride}th, all y layers), samples resident in host RAM"
+    print(json.dumps({
+        "impl": "reference", "metric": "voxel_cells_per_sec", "value": value, "unit": "cells/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/f32", "data": "synthetic",
+        "chunks_per_s": value / EDGE ** 3,
+        "config": {"workload": "fbm_terrain_4096x64^3", "edge": EDGE, "chunks_per_step": len(sample),
+                   "implementation": "C restatement of the reference's Rust CPU extractor (oracle/), OpenMP over chunks"},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import helio_b200 as H
+    from helio_b200 import _ffi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+
+    # ---- scheduler: global chunk list -> this rank's shard (no data-path collective) ----------
+    pages_all = chunk_grid(world)
+    if args.chunks:
+        pages_all = pages_all[:args.chunks * world]
+    costs = np.full(len(pages_all), H.chunk_cost(EDGE, 0), dtype=np.uint64)
+    owner = H.partition_chunks(costs, world)
+    pages = np.ascontiguousarray(pages_all[owner == rank])
+    n = len(pages)
+    words = (EDGE + 2) ** 3
+
+    batch = H.ChunkBatchExtractor(local_rank, edge=EDGE, max_chunks=n, max_vertices=MAX_VERTICES,
+                                  max_indices=MAX_INDICES)
+    ctx = batch.ctx
+    stream = torch.cuda.Stream(device=device)
+    ctx.set_stream(stream.cuda_stream)
+    descs = H.make_descs(n)
+
+    # ---- setup (untimed): procedural density on the device, K1 --------------------------------
+    t_fill0, t_fill1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ctx.fill_density(FIELD_TERRAIN_FBM, pages)          # warm
+        t_fill0.record(stream)
+        ctx.fill_density(FIELD_TERRAIN_FBM, pages)
+        t_fill1.record(stream)
+    stream.synchronize()
+    fill_ms = t_fill0.elapsed_time(t_fill1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- device-resident extraction: warm-up, then K timed steps -------------------------------
+    for _ in range(args.warmup):
+        ctx.extract_regular(None, descs, n)
+    barrier()
+    launches0 = ctx.launch_count
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            starts[k].record(stream)
+            ctx.extract_regular(None, descs, n)
+            stops[k].record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+    launches = ctx.launch_count - launches0
+    kernel_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = starts[0].elapsed_time(stops[-1])
+    if world > 1:
+        t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    counters = batch.counters(n)
+    total_v = int(counters["emitted_vertices"].astype(np.int64).sum())
+    total_i = int(counters["emitted_indices"].astype(np.int64).sum())
+    overflow = int((counters["vertex_overflow"] | counters["index_overflow"]).sum())
+    surface_chunks = int((counters["emitted_vertices"] > 0).sum())
+    cells_per_step = n * EDGE ** 3
+    value = world * cells_per_step * args.steps / (total_ms * 1e-3)
+
+    alg_bytes = n * words * 4 + 32 * total_v + 4 * total_i
+    avg_kernel_s = float(np.mean(kernel_ms)) * 1e-3
+    peak, peak_src = measured_peak_gbs()
+    achieved = alg_bytes / avg_kernel_s / 1e9
+
+    # ---- e2e through the C ABI with HOST buffers ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_samples = torch.empty(n * words, dtype=torch.int32, pin_memory=True)
+        ctx.synchronize()
+        # one-time (untimed) copy of the generated samples to the pinned host buffer
+        import ctypes as C
+        rc = _ffi.load().hvx_read(ctx._handle, _ffi.BUF_SAMPLES, 0, n * words * 4, C.c_void_p(host_samples.data_ptr()))
+        assert rc == 0
+        host_v = torch.empty((total_v + 1024) * 8, dtype=torch.int32, pin_memory=True)
+        host_i = torch.empty(total_i + 1024, dtype=torch.int32, pin_memory=True)
+
+        def e2e_step():
+            ctx.extract_regular(host_samples, descs, n)                       # H2D + kernel
+            tv, ti, _ = ctx.read_meshes(0, 0, n, vertices_out=host_v, indices_out=host_i)  # pack + D2H
+            c = batch.counters(n)                                             # D2H counters
+            return tv, ti, c
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(e2e_steps):
+            tv, ti, c = e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        assert tv == total_v and ti == total_i
+        e2e = {"value": world * cells_per_step * e2e_steps / e2e_s, "unit": "cells/s",
+               "h2d_bytes_per_step": n * words * 4 + n * 24 + n * 16,
+               "d2h_bytes_per_step": 32 * total_v + 4 * total_i + n * 16 + n * 32,
+               "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
+               "path": "hvx_extract_regular(host samples) + hvx_read_meshes + counters, pinned host memory"}
+
+    # ---- CPU baseline on this box's cores (rank 0, N=1 only) ------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        threads = O.max_threads()
+        idx = np.arange(args.cpu_offset, n, args.cpu_stride)
+        sample_pages = pages[idx]
+        host = np.empty(len(idx) * words, dtype=np.uint32)
+        for j, i in enumerate(idx):
+            host[j * words:(j + 1) * words] = ctx.read(_ffi.BUF_SAMPLES, int(i) * words, words)
+        t0 = time.perf_counter()
+        cells, totals = O.batch_regular(FIELD_TERRAIN_FBM, sample_pages, EDGE, threads=threads, do_fill=False, samples=host)
+        dt = time.perf_counter() - t0
+        # the sample's GPU result must equal the CPU result (counts; full parity lives in tests/)
+        assert totals[0] == int(counters["required_vertices"][idx].astype(np.int64).sum()), "CPU/GPU vertex totals differ"
+        cpu = {"value": cells / dt, "unit": "cells/s", "cores": threads, "kind": "port",
+               "sample": f"{len(idx)} of {n} chunks (every {args.cpu_stride}th), {dt:.2f} s wall, samples resident in host RAM"}
+
+    if rank == 0:
+        clk = clocks.summary()
+        print(json.dumps({
+            "metric": "voxel_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/f32",
+            "data": "synthetic", "chunks_per_s": value / EDGE ** 3,
+            "config": {"workload": "fbm_terrain_4096x64^3", "edge": EDGE, "chunks_per_gpu": n,
+                       "grid": f"{GRID * world}x{GRID}x{GRID}", "surface_chunks_per_gpu": surface_chunks,
+                       "vertices_per_step_per_gpu": total_v, "indices_per_step_per_gpu": total_i,
+                       "l2_policy": "inputs larger than L2 (4.71 GB samples per GPU vs 126 MB L2)",
+                       "slot_capacity": [MAX_VERTICES, MAX_INDICES], "overflowed_chunks": overflow,
+                       "partition": "LPT static, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": "regular_extract_kernel<64>", "kernel_ms": float(np.mean(kernel_ms)),
+                         "frac_of_8TBps_nominal": achieved / 8000.0},
+            "fill_kernel": {"ms": fill_ms, "GB/s": n * words * 4 / (fill_ms * 1e-3) / 1e9},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "wall_s_timed_region": wall,
+        }))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--chunks", type=int, default=0, help="chunks per GPU (default: the full 4096)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-stride", type=int, default=8, help="CPU baseline runs every k-th chunk of the workload")
+    ap.add_argument("--cpu-offset", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,7 @@
 // Ownership follows the reference: the ctx owns every device buffer, the caller borrows inputs
 // for the duration of the call, outputs are overwritten by the next dispatch.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -203,6 +204,8 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     p.descs = ctx->d_descs;
     p.n_chunks = n;
     p.mode = mode;
+    if (const char* dbg = getenv("HVX_DEBUG_STREAM_ONLY"))  // diagnostics only: skip all compute
+        if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY;
     p.max_vertices = ctx->cfg.max_vertices;
     p.max_indices = ctx->cfg.max_indices;
     p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);

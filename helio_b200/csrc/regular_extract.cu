@@ -26,6 +26,8 @@
 //     per VERTEX (not per cell) from the shared-memory bricks: 14 smem loads, no HBM re-read.
 //   * no single-address atomics: the reference's 5 atomicAdd per cell become one counter
 //     record written once per chunk.
+#include <cstdlib>
+
 #include "hvx_device.cuh"
 #include "hvx_kernels.h"
 
@@ -45,65 +47,75 @@ struct Cfg {
     static constexpr int ZB = ZB_;        // cell layers per step
     static constexpr int R = R_;          // ring slots (sample layers resident or in flight)
     static constexpr int NT = NT_;        // threads per CTA
+    static constexpr int NW = NT_ / 32;
     static constexpr int WIN = ZB_ + 3;   // sample layers a step touches (corners + gradient halo)
     static constexpr int LAYER_WORDS = S * S;
     static constexpr int LAYER_BYTES = LAYER_WORDS * 4;
+    static constexpr int NB = (LAYER_WORDS + 31) / 32;  // 32-sample ballot blocks per layer
+    static constexpr int BW = NB + 3;                   // + zero padding for the 4-word row window
     static constexpr int ROWS = ZB_ * E_;  // cell rows per step
+    static constexpr int ROW_WARPS = ROWS / 32;
     static constexpr int CB = NT_;         // active cells per emission batch
     static constexpr int QW = E_ / 4;      // microbrick edge == quarter-row width
     static constexpr int RPB = 256 / E_;   // rows per 256-cell scan block
     static_assert(R_ >= ZB_ + 4, "ring must hold one window plus at least one layer in flight");
     static_assert(R_ < E_ + 2, "producer may be at most one chunk ahead");
     static_assert(LAYER_BYTES % 16 == 0, "cp.async.bulk needs 16-byte multiples");
-    static_assert(E_ % ZB_ == 0 && ROWS <= NT_ && (E_ == 32 || E_ == 64), "unsupported tiling");
+    static_assert(E_ % ZB_ == 0 && ROWS <= NT_ && ROWS % 32 == 0 && (E_ == 32 || E_ == 64), "unsupported tiling");
 };
 
 template <class C>
 struct Smem {
     alignas(128) uint32_t ring[C::R][C::LAYER_WORDS];
     alignas(8) uint64_t full_bar[C::R];
-    uint64_t mask_lo[C::R][C::S];   // solid bits of sample row, x = 0..63
-    uint32_t mask_hi[C::R][C::S];   // x = 64.. (edge 64 only)
     uint64_t active[C::ROWS];       // active-cell bits of each cell row of the step
-    uint32_t row_off[C::ROWS + 1];  // exclusive prefix of popc(active)
     uint64_t dirty_row[16];         // [my + 4*mz] -> x mask of dirty microbricks
+    union {
+        uint16_t owner[C::CB * 12];        // emission: vertex -> cell slot | k<<10
+        uint64_t row_pref64[C::ROWS + 1];  // debug records: per-row exclusive (vertices | indices<<32)
+    };
+    uint64_t scan64[2][34];
+    uint32_t scan32[2][34];
+    uint32_t bits[C::R][C::BW];     // solid bit of every sample of a layer, flat x-fastest order
+    uint32_t row_off[C::ROWS + 1];  // exclusive prefix of popc(active)
     uint32_t cell_rec[C::CB];       // x | row<<8 | case<<16
-    uint32_t cell_off[C::CB];       // batch-local vertex offset | index offset << 16
-    uint16_t owner[C::CB * 12];     // vertex -> cell slot | k<<10
-    uint32_t scan_sums[40];
-    uint32_t scan_prefix[40];
-    uint64_t scan_sums64[40];
-    uint64_t scan_prefix64[40];
-    uint64_t row_pref64[C::ROWS + 1];  // debug: per-row exclusive (vertices | indices<<32)
     uint32_t chunk_ids[4];
     uint16_t case_info[256];
     uint8_t vertex_edge[256 * 12];
     uint8_t class_index[16 * 16];
 };
 
-// The four sample-row masks around one cell row, shifted so bit x is the corner at x / x+1.
+// Solid bits of the 8 corners of every cell of one cell row: bit x of a** is the corner at
+// sample x+1 (cell-local x), bit x of b** the corner at x+2; 10 = next sample row, 01 = next layer.
 struct RowCorners {
-    uint64_t a00, b00, a10, b10, a01, b01, a11, b11;  // a: corner x, b: corner x+1; 10: y+1; 01: z+1
+    uint64_t a00, b00, a10, b10, a01, b01, a11, b11;
 };
+
+// Bits [o+1, o+1+E) and [o+2, o+2+E) of a layer's flat solid-bit array, o = row * S.
+template <class C>
+__device__ __forceinline__ void row_window(const uint32_t* __restrict__ bits, int row, uint64_t& a, uint64_t& b) {
+    const int p = row * C::S + 1, w = p >> 5, sh = p & 31;
+    const uint32_t x0 = bits[w], x1 = bits[w + 1], x2 = bits[w + 2];
+    if (C::E == 64) {
+        const uint32_t x3 = bits[w + 3];
+        const uint32_t lo = __funnelshift_r(x0, x1, sh), hi = __funnelshift_r(x1, x2, sh);
+        const uint32_t nx = __funnelshift_r(x2, x3, sh);
+        a = static_cast<uint64_t>(lo) | (static_cast<uint64_t>(hi) << 32);
+        b = (a >> 1) | (static_cast<uint64_t>(nx & 1u) << 63);
+    } else {
+        const uint32_t lo = __funnelshift_r(x0, x1, sh), nx = __funnelshift_r(x1, x2, sh);
+        a = lo;
+        b = (lo >> 1) | ((nx & 1u) << 31);
+    }
+}
 
 template <class C>
 __device__ __forceinline__ RowCorners load_row_corners(const Smem<C>& sm, int slot0, int slot1, int y) {
     RowCorners rc;
-    auto shifted = [&](int slot, int row, uint64_t& a, uint64_t& b) {
-        uint64_t lo = sm.mask_lo[slot][row];
-        if (C::E == 64) {
-            uint64_t hi = sm.mask_hi[slot][row];
-            a = (lo >> 1) | (hi << 63);
-            b = (lo >> 2) | (hi << 62);
-        } else {
-            a = (lo >> 1) & 0xffffffffull;
-            b = (lo >> 2) & 0xffffffffull;
-        }
-    };
-    shifted(slot0, y + 1, rc.a00, rc.b00);
-    shifted(slot0, y + 2, rc.a10, rc.b10);
-    shifted(slot1, y + 1, rc.a01, rc.b01);
-    shifted(slot1, y + 2, rc.a11, rc.b11);
+    row_window<C>(sm.bits[slot0], y + 1, rc.a00, rc.b00);
+    row_window<C>(sm.bits[slot0], y + 2, rc.a10, rc.b10);
+    row_window<C>(sm.bits[slot1], y + 1, rc.a01, rc.b01);
+    row_window<C>(sm.bits[slot1], y + 2, rc.a11, rc.b11);
     return rc;
 }
 
@@ -114,10 +126,33 @@ __device__ __forceinline__ uint32_t case_at(const RowCorners& rc, int x) {
            static_cast<uint32_t>((rc.a11 >> x) & 1) << 6 | static_cast<uint32_t>((rc.b11 >> x) & 1) << 7;
 }
 
-template <class C>
-__device__ __forceinline__ int ring_slot(int slot_base, int delta) {
-    int s = slot_base + delta;
-    return s >= C::R ? s - C::R : s;
+// Exclusive scan over the first NWS warps' values (threads >= 32*NWS pass 0 and only read the
+// total): one warp-shuffle scan + one barrier.  `buf` is a 2-deep ping-pong so consecutive scans
+// need no trailing barrier.
+template <int NWS, typename T>
+__device__ __forceinline__ T scan_front_warps(T value, T (*buf)[34], uint32_t& flip, T& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* sums = buf[flip & 1u];
+    flip ^= 1u;
+    T incl = value;
+    if (warp < NWS) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            T up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane == 31) sums[warp] = incl;
+    }
+    __syncthreads();
+    T before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < NWS; ++w) {
+        const T s = sums[w];
+        if (w < warp) before += s;
+        all += s;
+    }
+    total = all;
+    return incl - value + before;
 }
 
 // One vertex of an active cell, from the shared-memory bricks.  (x,y,z) cell coords, slot_of(zi)
@@ -202,6 +237,7 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
     for (int i = tid; i < 256; i += NT) sm.case_info[i] = HVX_REGULAR_CASE_INFO[i];
     for (int i = tid; i < 256 * 12; i += NT) sm.vertex_edge[i] = HVX_REGULAR_VERTEX_EDGE[i / 12][i % 12];
     for (int i = tid; i < 256; i += NT) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
+    for (int i = tid; i < R * C::BW; i += NT) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. the zero padding
     if (tid == 0) {
         for (int i = 0; i < R; ++i) mbar_init(&sm.full_bar[i], 1);
         mbar_fence_init();
@@ -238,7 +274,18 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
     };
 
     // ---- consumer state (uniform across the CTA) -------------------------------------
-    uint32_t base_seq = 0;  // stream seq of sample layer 0 of the current chunk
+    // (win_slot, win_q) = (seq % R, seq / R) of sample layer z0 of the current step, kept
+    // incrementally so the hot loop has no division.
+    uint32_t base_seq = 0;
+    int win_slot = 0;
+    uint32_t win_q = 0, flip32 = 0, flip64 = 0;
+    auto advance = [&](int layers) {
+        win_slot += layers;
+        while (win_slot >= R) {
+            win_slot -= R;
+            ++win_q;
+        }
+    };
     for (uint32_t kc = 0;; ++kc, base_seq += S) {
         if (tid == 0) produce(base_seq);
         __syncthreads();
@@ -259,42 +306,53 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
         const bool debug = p.cells != nullptr;
         const bool do_emit = p.mode == MODE_EXTRACT;
 
-        uint32_t v_base = 0, i_base = 0;          // running chunk-local placement
-        uint32_t active_cells = 0;                // classify counters
-        int waited = 0;                           // sample layers [0, waited) have landed
-        int slot_base = static_cast<int>(base_seq % R);  // ring slot of sample layer 0
-        uint32_t par_base = (base_seq / R) & 1u;  // parity of slot_base's current use
-        auto slot_of_layer = [&](int zi) -> int {  // zi in [0, S)
-            int s = slot_base + (zi % R);
-            return s >= R ? s - R : s;
-        };
-        auto parity_of_layer = [&](int zi) -> uint32_t {
-            // seq = base_seq + zi;  parity = (seq / R) & 1
-            return ((base_seq + static_cast<uint32_t>(zi)) / R) & 1u;
-        };
-        (void)par_base;
+        uint32_t v_base = 0, i_base = 0;  // running chunk-local placement
+        uint32_t active_cells = 0;        // classify counters
+        int waited = 0;                   // sample layers [0, waited) of this chunk have landed
 
         for (int z0 = 0; z0 < E; z0 += ZB) {
-            if (z0 != 0) {
-                if (tid == 0) produce(base_seq + z0);
-            }
+            if (z0 != 0 && tid == 0) produce(base_seq + z0);
+            // ring slot of sample layer z0 + d, d in [0, R)
+            auto slot_of = [&](int d) -> int {
+                const int s = win_slot + d;
+                return s >= R ? s - R : s;
+            };
+            auto slot_of_layer = [&](int zi) -> int { return slot_of(zi - z0); };
             // ---- P0: wait for the window's layers ---------------------------------------
             const int need = min(S, z0 + C::WIN);
-            for (int zi = waited; zi < need; ++zi) mbar_wait(&sm.full_bar[slot_of_layer(zi)], parity_of_layer(zi));
-            // ---- P1: solid-bit row masks of the new corner layers (warp ballot) ----------
+            for (int zi = waited; zi < need; ++zi) {
+                const int s = win_slot + (zi - z0);
+                const bool wrap = s >= R;
+                mbar_wait(&sm.full_bar[wrap ? s - R : s], (win_q + (wrap ? 1u : 0u)) & 1u);
+            }
+            if (p.mode == MODE_STREAM_ONLY) {  // diagnostics: the bare HBM -> smem pipeline
+                waited = need;
+                __syncthreads();
+                advance(ZB);
+                continue;
+            }
+            // ---- P1: solid bits of the new corner layers, 32 samples per warp ballot -------
             {
                 const int first = z0 == 0 ? 1 : z0 + 2, last = z0 + ZB + 1;  // inclusive, <= E+1
-                const int rows = (last - first + 1) * S;
-                for (int r = warp; r < rows; r += NT / 32) {
-                    const int zi = first + r / S, row = r % S, slot = slot_of_layer(zi);
-                    const uint32_t* src = &sm.ring[slot][row * S];
-                    const uint32_t b0 = __ballot_sync(0xffffffffu, cw_solid(src[lane]));
-                    const uint32_t b1 = __ballot_sync(0xffffffffu, lane + 32 < S && cw_solid(src[min(lane + 32, S - 1)]));
-                    uint32_t b2 = 0;
-                    if (E == 64) b2 = __ballot_sync(0xffffffffu, lane + 64 < S && cw_solid(src[min(lane + 64, S - 1)]));
-                    if (lane == 0) {
-                        sm.mask_lo[slot][row] = static_cast<uint64_t>(b0) | (static_cast<uint64_t>(b1) << 32);
-                        sm.mask_hi[slot][row] = b2;
+                constexpr int FULL = C::LAYER_WORDS / 32, TAIL = C::LAYER_WORDS % 32;
+                for (int zi = first; zi <= last; ++zi) {
+                    const int slot = slot_of(zi - z0);
+                    // each lane reads the low (density) half of its sample: LDS.S16, ISETP, VOTE, STS
+                    const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
+                    uint32_t* dst = sm.bits[slot] + warp;
+#pragma unroll
+                    for (int k = 0; k < (FULL + C::NW - 1) / C::NW; ++k) {
+                        if (k * C::NW + C::NW <= FULL || warp < FULL - k * C::NW) {
+                            const short d = src[64 * C::NW * k];
+                            const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
+                            if (lane == 0) dst[C::NW * k] = b;
+                        }
+                    }
+                    if (TAIL != 0 && warp == C::NW - 1) {
+                        const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * FULL);
+                        const short d = lane < TAIL ? tail[2 * lane] : short(1);
+                        const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
+                        if (lane == 0) sm.bits[slot][FULL] = b;
                     }
                 }
             }
@@ -304,15 +362,21 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
             uint32_t my_count = 0;
             if (tid < C::ROWS) {
                 const int zl = tid / E, y = tid % E, z = z0 + zl;
-                const RowCorners rc = load_row_corners<C>(sm, slot_of_layer(z + 1), slot_of_layer(z + 2), y);
+                const RowCorners rc = load_row_corners<C>(sm, slot_of(zl + 1), slot_of(zl + 2), y);
                 const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
                 const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
                 const uint64_t act = any & ~all & ROWMASK & sm.dirty_row[(y / C::QW) + 4 * (z / C::QW)];
                 sm.active[tid] = act;
                 my_count = __popcll(act);
             }
+            // Most steps of most chunks see no surface at all: one barrier-with-OR decides, and only
+            // steps with active cells pay for the rank scan.  (Debug records need every step.)
+            if (!__syncthreads_or(my_count != 0) && !debug) {
+                advance(ZB);
+                continue;
+            }
             uint32_t n_active;
-            const uint32_t my_off = block_exclusive_scan<NT>(my_count, sm.scan_sums, sm.scan_prefix, n_active);
+            const uint32_t my_off = scan_front_warps<C::ROW_WARPS>(my_count, sm.scan32, flip32, n_active);
             if (tid < C::ROWS) sm.row_off[tid] = my_off;
 
             if (debug) {
@@ -326,7 +390,7 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                     zl = tid / E;
                     y = tid % E;
                     z = z0 + zl;
-                    rc = load_row_corners<C>(sm, slot_of_layer(z + 1), slot_of_layer(z + 2), y);
+                    rc = load_row_corners<C>(sm, slot_of(zl + 1), slot_of(zl + 2), y);
                     dirty_x = sm.dirty_row[(y / C::QW) + 4 * (z / C::QW)];
                     uint64_t act = sm.active[tid];
                     while (act) {
@@ -337,8 +401,7 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                     }
                 }
                 uint64_t step_tot;
-                const uint64_t row_pref =
-                    block_exclusive_scan<NT>(row_tot, sm.scan_sums64, sm.scan_prefix64, step_tot);
+                const uint64_t row_pref = scan_front_warps<C::ROW_WARPS>(row_tot, sm.scan64, flip64, step_tot);
                 if (tid < C::ROWS) sm.row_pref64[tid] = row_pref;
                 if (tid == 0) sm.row_pref64[C::ROWS] = step_tot;
                 __syncthreads();
@@ -377,7 +440,10 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                 }
             }
 
-            if (n_active == 0) continue;  // uniform: nothing on the surface in these layers
+            if (n_active == 0) {  // uniform: nothing on the surface in these layers
+                advance(ZB);
+                continue;
+            }
             active_cells += n_active;
 
             // ---- P3: emission in ordered batches of CB active cells -----------------------
@@ -404,15 +470,15 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                 uint32_t packed = 0, rec = 0, info = 0;
                 if (tid < nb) {
                     rec = sm.cell_rec[tid];
-                    const int x = rec & 63, r = rec >> 8, zl = r / E, y = r % E, z = z0 + zl;
-                    const RowCorners rc = load_row_corners<C>(sm, slot_of_layer(z + 1), slot_of_layer(z + 2), y);
+                    const int x = rec & 63, r = rec >> 8, zl = r / E, y = r % E;
+                    const RowCorners rc = load_row_corners<C>(sm, slot_of(zl + 1), slot_of(zl + 2), y);
                     const uint32_t c = case_at(rc, x);
                     info = sm.case_info[c];
                     rec |= c << 16;
                     packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
                 }
                 uint32_t batch_tot;
-                const uint32_t off = block_exclusive_scan<NT>(packed, sm.scan_sums, sm.scan_prefix, batch_tot);
+                const uint32_t off = scan_front_warps<C::NW>(packed, sm.scan32, flip32, batch_tot);
                 const uint32_t batch_v = batch_tot & 0xffffu, batch_i = batch_tot >> 16;
                 if (tid < nb && do_emit) {
                     const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
@@ -443,7 +509,9 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                 i_base += batch_i;
             }
             __syncthreads();  // ring reads of this step are done before the producer refills
+            advance(ZB);
         }
+        advance(S - E);  // the chunk's last two sample layers
 
         // ---- chunk epilogue: one counter record, no atomics --------------------------------
         if (tid == 0) {
@@ -494,6 +562,12 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
 using Cfg64 = Cfg<64, 2, 11, 512>;
 using Cfg32 = Cfg<32, 4, 16, 256>;
 
+// Tuning variants (HVX_REGULAR_VARIANT=<n>, default 0); all produce identical output.
+int variant_from_env() {
+    const char* v = getenv("HVX_REGULAR_VARIANT");
+    return v ? atoi(v) : 0;
+}
+
 }  // namespace
 
 size_t regular_smem_bytes(int edge) { return edge == 64 ? sizeof(Smem<Cfg64>) : sizeof(Smem<Cfg32>); }
@@ -502,8 +576,25 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     if (p.n_chunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    if (edge == 64) return launch_cfg<Cfg64>(p, dev, stream);
-    if (edge == 32) return launch_cfg<Cfg32>(p, dev, stream);
+    const int variant = variant_from_env();
+    if (edge == 64) {
+        switch (variant) {
+            case 1: return launch_cfg<Cfg<64, 4, 11, 512>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<64, 2, 11, 256>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<64, 4, 11, 256>>(p, dev, stream);
+            case 4: return launch_cfg<Cfg<64, 1, 10, 256>>(p, dev, stream);
+            case 5: return launch_cfg<Cfg<64, 2, 9, 512>>(p, dev, stream);
+            default: return launch_cfg<Cfg64>(p, dev, stream);
+        }
+    }
+    if (edge == 32) {
+        switch (variant) {
+            case 1: return launch_cfg<Cfg<32, 8, 20, 256>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<32, 4, 16, 128>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<32, 2, 12, 128>>(p, dev, stream);
+            default: return launch_cfg<Cfg32>(p, dev, stream);
+        }
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -810,6 +810,22 @@ int hvxo_extract_transition_face_analytic(int kind, int edge, uint32_t lod, cons
 /* ------------------------------------------------------------------------- */
 /* CPU baseline batch driver (OpenMP over chunks)                  */
 
+int hvxo_batch_fill(int kind, int edge, uint32_t lod, const int64_t* page_xyz, uint32_t n, int threads, uint32_t* out) {
+    if (!edge_ok(edge)) return -1;
+    const size_t s = (size_t)edge + 2, chunk_words = s * s * s;
+    int rc = 0;
+    if (threads < 1) threads = 1;
+#pragma omp parallel for schedule(dynamic) num_threads(threads)
+    for (uint32_t c = 0; c < n; ++c) {
+        int r = hvxo_fixture_fill(kind, edge, lod, page_xyz + 3 * (size_t)c, out + (size_t)c * chunk_words);
+        if (r) {
+#pragma omp critical
+            rc = r;
+        }
+    }
+    return rc;
+}
+
 int hvxo_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

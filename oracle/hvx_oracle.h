@@ -149,6 +149,8 @@ int hvxo_extract_transition_face_analytic(int kind, int edge, uint32_t lod,
 int64_t hvxo_batch_regular(int kind, int edge, uint32_t lod, const int64_t* page_xyz /* n*3 */,
                            uint32_t n, int do_fill, const uint32_t* samples_or_null,
                            int threads, uint64_t totals[4]);
+/* OpenMP fill of n chunks (setup helper for the CPU baseline; same result as hvxo_fixture_fill). */
+int hvxo_batch_fill(int kind, int edge, uint32_t lod, const int64_t* page_xyz, uint32_t n, int threads, uint32_t* out);
 int hvxo_max_threads(void);
 
 #ifdef __cplusplus

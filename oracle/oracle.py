@@ -79,6 +79,7 @@ def lib():
         L.hvxo_batch_regular.restype = C.c_int64
         L.hvxo_batch_regular.argtypes = [C.c_int, C.c_int, C.c_uint32, i64p, C.c_uint32, C.c_int, u32p, C.c_int,
                                          C.POINTER(C.c_uint64)]
+        L.hvxo_batch_fill.argtypes = [C.c_int, C.c_int, C.c_uint32, i64p, C.c_uint32, C.c_int, u32p]
         L.hvxo_case_topology.argtypes = [C.c_int, C.c_uint32, u32p, u32p, u32p, u32p, C.POINTER(C.c_uint16),
                                          C.POINTER(C.c_uint8)]
     return _LIB
@@ -221,6 +222,16 @@ def extract_transition_face_analytic(kind: int, page_xyz, lod: int, face: int, e
 
 def max_threads() -> int:
     return int(lib().hvxo_max_threads())
+
+
+def batch_fill(kind: int, pages: np.ndarray, edge: int, lod: int = 0, threads: int = 1) -> np.ndarray:
+    pages = np.ascontiguousarray(pages, dtype=np.int64).reshape(-1, 3)
+    out = np.empty(pages.shape[0] * (edge + 2) ** 3, dtype=np.uint32)
+    rc = lib().hvxo_batch_fill(kind, edge, lod, pages.ctypes.data_as(C.POINTER(C.c_int64)), pages.shape[0], threads,
+                               _u32p(out))
+    if rc:
+        raise ValueError(f"batch_fill failed: {rc}")
+    return out
 
 
 def batch_regular(kind: int, pages: np.ndarray, edge: int, lod: int = 0, threads: int = 1, do_fill: bool = True,
