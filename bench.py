@@ -38,11 +38,20 @@ FIELD_TERRAIN_FBM = 16
 MAX_VERTICES, MAX_INDICES = 49_152, 73_728   # per-chunk slot capacity (surface chunks need ~25k / ~37k)
 
 
+WORKLOAD = "terrain"   # --workload: "terrain" (headline), "surface" (every chunk crosses the surface), "empty"
+
+
 def chunk_grid(n_gpus: int) -> np.ndarray:
     """Global chunk list: page_xyz in [-8, 8)^3 per GPU, extended along +x for N > 1 (x fastest)."""
     xs = np.arange(-GRID // 2, -GRID // 2 + GRID * n_gpus, dtype=np.int64)
     ys = np.arange(-GRID // 2, GRID // 2, dtype=np.int64)
     zs = np.arange(-GRID // 2, GRID // 2, dtype=np.int64)
+    if WORKLOAD == "surface":      # diagnostics: 64 x 1 x 64 chunks, all on the surface layer y = -1
+        xs = np.arange(-32, -32 + 64 * n_gpus, dtype=np.int64)
+        ys = np.array([-1], dtype=np.int64)
+        zs = np.arange(-32, 32, dtype=np.int64)
+    elif WORKLOAD == "empty":      # diagnostics: nothing but air
+        ys = ys + 16
     z, y, x = np.meshgrid(zs, ys, xs, indexing="ij")
     return np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
 
@@ -288,7 +297,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16/f32",
             "data": "synthetic", "chunks_per_s": value / EDGE ** 3,
-            "config": {"workload": "fbm_terrain_4096x64^3", "edge": EDGE, "chunks_per_gpu": n,
+            "config": {"workload": "fbm_terrain_4096x64^3" if WORKLOAD == "terrain" else f"diagnostic_{WORKLOAD}_4096x64^3", "edge": EDGE, "chunks_per_gpu": n,
                        "grid": f"{GRID * world}x{GRID}x{GRID}", "surface_chunks_per_gpu": surface_chunks,
                        "vertices_per_step_per_gpu": total_v, "indices_per_step_per_gpu": total_i,
                        "l2_policy": "inputs larger than L2 (4.71 GB samples per GPU vs 126 MB L2)",
@@ -319,7 +328,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-stride", type=int, default=8, help="CPU baseline runs every k-th chunk of the workload")
     ap.add_argument("--cpu-offset", type=int, default=0)
+    ap.add_argument("--workload", choices=["terrain", "surface", "empty"], default="terrain")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:

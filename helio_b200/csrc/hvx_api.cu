@@ -205,7 +205,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     p.n_chunks = n;
     p.mode = mode;
     if (const char* dbg = getenv("HVX_DEBUG_STREAM_ONLY"))  // diagnostics only: skip all compute
-        if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY;
+        if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY; else if (dbg[0] == '2') p.mode = MODE_BITS_ONLY;
     p.max_vertices = ctx->cfg.max_vertices;
     p.max_indices = ctx->cfg.max_indices;
     p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);

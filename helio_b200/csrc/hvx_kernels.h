@@ -16,7 +16,7 @@ struct ChunkDesc {
     uint32_t _pad;
 };
 
-enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1, MODE_STREAM_ONLY = 2 };
+enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1, MODE_STREAM_ONLY = 2, MODE_BITS_ONLY = 3 };
 
 struct RegularParams {
     const uint32_t* samples;  // [n][(E+2)^3]

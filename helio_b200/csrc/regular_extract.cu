@@ -5,27 +5,28 @@
 //   scan_regular_cells      PV/src/transvoxel_emit.wgsl:131-172
 //   scan_regular_blocks     PV/src/transvoxel_emit.wgsl:174-202
 //   emit_regular_cells      PV/src/transvoxel_emit.wgsl:291-370
-// with ONE persistent kernel over a batch of chunks.  Arithmetic follows the reference's CPU
-// extractor (PV/tests/gpu_transvoxel_emission.rs:272-450), not the WGSL, so positions and
-// normals are bit-identical to the oracle.
+// with ONE persistent, warp-specialised kernel over a batch of chunks.  Arithmetic follows the
+// reference's CPU extractor (PV/tests/gpu_transvoxel_emission.rs:272-450), not the WGSL, so
+// positions and normals are bit-identical to the oracle.
 //
 // Design:
 //   * one CTA per SM pulls chunks from an atomic queue and walks each chunk front to back in z.
 //     x-fastest cell order == walk order, so vertex/index placement is a running prefix inside
 //     the CTA: order preserving by construction, no cross-CTA scan on the data path.
-//   * sample layers ((E+2)^2 words, contiguous, 16-byte aligned) are streamed HBM -> shared
-//     memory with cp.async.bulk (TMA 1-D, SASS UBLKCP) into a ring of R layers, completion on
-//     one mbarrier per slot; the producer runs up to R-(ZB+3) layers ahead, across chunk
-//     boundaries.  Every sample is read from HBM exactly once.
-//   * classification is bit-parallel: warp ballots turn a layer into one solid-bit row mask
-//     per sample row, and a cell row's 8-corner signs are 8 shifted copies of 4 row masks; the
-//     active-cell mask of a 64-cell row costs one thread ~40 integer ops.  Occupancy counts
-//     are popc of those masks.
-//   * active cells are compacted in order (row popc -> block scan -> rank scatter), their
-//     (vertex, index) counts scanned with warp shuffles, and vertices are emitted one thread
-//     per VERTEX (not per cell) from the shared-memory bricks: 14 smem loads, no HBM re-read.
-//   * no single-address atomics: the reference's 5 atomicAdd per cell become one counter
-//     record written once per chunk.
+//   * a PRODUCER warp streams sample layers ((E+2)^2 words, contiguous, 16-byte aligned) from HBM
+//     into a shared-memory ring with cp.async.bulk (TMA 1-D, SASS UBLKCP): full[slot] mbarriers
+//     carry the byte count, empty[slot] mbarriers hand slots back.  It runs up to R-4 layers
+//     ahead, across chunk boundaries.  Every sample is read from HBM exactly once.
+//   * CONSUMER warps never meet at a CTA barrier while the chunk is empty: each warp turns its
+//     share of a landed layer into solid bits (one ballot per 32 samples), two warps per cell
+//     layer derive the 64-cell active masks of its rows with shifts and AND/OR (8 corner signs =
+//     8 shifted copies of 4 bit rows) and publish a verdict through an mbarrier; everybody else
+//     just reads the verdict two layers later and releases the oldest ring slot.
+//   * layers that do contain surface cells are batched (up to EB consecutive layers) and emitted
+//     collectively: popc ranks -> warp-shuffle scan -> ordered compaction -> one thread per
+//     VERTEX reading its 14 samples from the shared-memory bricks (no HBM re-read).
+//   * no single-address atomics: the reference's 5 atomicAdd per cell become one counter record
+//     written once per chunk.
 #include <cstdlib>
 
 #include "hvx_device.cuh"
@@ -40,43 +41,51 @@ namespace {
 #define HVX_TABLE static __device__ const
 #include "transvoxel_tables.inc"
 
-template <int E_, int ZB_, int R_, int NT_>
+template <int E_, int EB_, int R_, int NW_>
 struct Cfg {
     static constexpr int E = E_;          // cells per chunk edge
     static constexpr int S = E_ + 2;      // samples per edge (1-sample halo)
-    static constexpr int ZB = ZB_;        // cell layers per step
+    static constexpr int EB = EB_;        // max cell layers per emission batch
     static constexpr int R = R_;          // ring slots (sample layers resident or in flight)
-    static constexpr int NT = NT_;        // threads per CTA
-    static constexpr int NW = NT_ / 32;
-    static constexpr int WIN = ZB_ + 3;   // sample layers a step touches (corners + gradient halo)
+    static constexpr int NW = NW_;        // consumer warps
+    static constexpr int NT = NW_ * 32;   // consumer threads
+    static constexpr int NT_ALL = NT + 32;  // + producer warp
     static constexpr int LAYER_WORDS = S * S;
     static constexpr int LAYER_BYTES = LAYER_WORDS * 4;
-    static constexpr int NB = (LAYER_WORDS + 31) / 32;  // 32-sample ballot blocks per layer
-    static constexpr int BW = NB + 3;                   // + zero padding for the 4-word row window
-    static constexpr int ROWS = ZB_ * E_;  // cell rows per step
-    static constexpr int ROW_WARPS = ROWS / 32;
-    static constexpr int CB = NT_;         // active cells per emission batch
-    static constexpr int QW = E_ / 4;      // microbrick edge == quarter-row width
-    static constexpr int RPB = 256 / E_;   // rows per 256-cell scan block
-    static_assert(R_ >= ZB_ + 4, "ring must hold one window plus at least one layer in flight");
+    static constexpr int FULL = LAYER_WORDS / 32;       // whole 32-sample ballot blocks per layer
+    static constexpr int TAIL = LAYER_WORDS % 32;
+    static constexpr int BW = FULL + 1 + 3;             // bit words per layer + zero padding
+    static constexpr int BR = EB_ <= 4 ? 8 : 16;        // bit-layer ring (>= EB + 4 live layers)
+    static constexpr int VR = BR;                       // verdict / active-mask ring
+    static constexpr int PW = E_ / 32;                  // warps classifying one cell layer
+    static constexpr int PG = NW_ / PW;                 // classification groups
+    static constexpr int ROWS = EB_ * E_;               // cell rows per emission batch
+    static constexpr int CB = NT;                       // active cells per emission sub-batch
+    static constexpr int QW = E_ / 4;                   // microbrick edge == quarter-row width
+    static constexpr int RPB = 256 / E_;                // rows per 256-cell scan block
+    static_assert(R_ >= EB_ + 3 + 2, "ring must hold an emission window plus layers in flight");
     static_assert(R_ < E_ + 2, "producer may be at most one chunk ahead");
+    static_assert(EB_ + 4 <= BR && EB_ + 4 <= VR, "bit / verdict rings too small");
     static_assert(LAYER_BYTES % 16 == 0, "cp.async.bulk needs 16-byte multiples");
-    static_assert(E_ % ZB_ == 0 && ROWS <= NT_ && ROWS % 32 == 0 && (E_ == 32 || E_ == 64), "unsupported tiling");
+    static_assert(ROWS <= NT && ROWS % 32 == 0 && NW_ % PW == 0 && (E_ == 32 || E_ == 64), "unsupported tiling");
 };
 
 template <class C>
 struct Smem {
     alignas(128) uint32_t ring[C::R][C::LAYER_WORDS];
     alignas(8) uint64_t full_bar[C::R];
-    uint64_t active[C::ROWS];       // active-cell bits of each cell row of the step
-    uint64_t dirty_row[16];         // [my + 4*mz] -> x mask of dirty microbricks
+    uint64_t empty_bar[C::R];
+    uint64_t bits_bar[C::BR];
+    uint64_t verdict_bar[C::VR];
+    uint64_t active[C::VR][C::E];   // active-cell bits per cell row, written by the classifying warps
     union {
         uint16_t owner[C::CB * 12];        // emission: vertex -> cell slot | k<<10
         uint64_t row_pref64[C::ROWS + 1];  // debug records: per-row exclusive (vertices | indices<<32)
     };
     uint64_t scan64[2][34];
     uint32_t scan32[2][34];
-    uint32_t bits[C::R][C::BW];     // solid bit of every sample of a layer, flat x-fastest order
+    uint32_t bits[C::BR][C::BW];    // solid bit of every sample of a layer, flat x-fastest order
+    uint32_t verdict_flag[C::VR][2];
     uint32_t row_off[C::ROWS + 1];  // exclusive prefix of popc(active)
     uint32_t cell_rec[C::CB];       // x | row<<8 | case<<16
     uint32_t chunk_ids[4];
@@ -84,6 +93,16 @@ struct Smem {
     uint8_t vertex_edge[256 * 12];
     uint8_t class_index[16 * 16];
 };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// barrier among the consumer warps only (the producer warp never joins)
+template <int NT>
+__device__ __forceinline__ void consumer_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
 
 // Solid bits of the 8 corners of every cell of one cell row: bit x of a** is the corner at
 // sample x+1 (cell-local x), bit x of b** the corner at x+2; 10 = next sample row, 01 = next layer.
@@ -110,12 +129,13 @@ __device__ __forceinline__ void row_window(const uint32_t* __restrict__ bits, in
 }
 
 template <class C>
-__device__ __forceinline__ RowCorners load_row_corners(const Smem<C>& sm, int slot0, int slot1, int y) {
+__device__ __forceinline__ RowCorners load_row_corners(const uint32_t* __restrict__ bits0,
+                                                       const uint32_t* __restrict__ bits1, int y) {
     RowCorners rc;
-    row_window<C>(sm.bits[slot0], y + 1, rc.a00, rc.b00);
-    row_window<C>(sm.bits[slot0], y + 2, rc.a10, rc.b10);
-    row_window<C>(sm.bits[slot1], y + 1, rc.a01, rc.b01);
-    row_window<C>(sm.bits[slot1], y + 2, rc.a11, rc.b11);
+    row_window<C>(bits0, y + 1, rc.a00, rc.b00);
+    row_window<C>(bits0, y + 2, rc.a10, rc.b10);
+    row_window<C>(bits1, y + 1, rc.a01, rc.b01);
+    row_window<C>(bits1, y + 2, rc.a11, rc.b11);
     return rc;
 }
 
@@ -126,16 +146,16 @@ __device__ __forceinline__ uint32_t case_at(const RowCorners& rc, int x) {
            static_cast<uint32_t>((rc.a11 >> x) & 1) << 6 | static_cast<uint32_t>((rc.b11 >> x) & 1) << 7;
 }
 
-// Exclusive scan over the first NWS warps' values (threads >= 32*NWS pass 0 and only read the
-// total): one warp-shuffle scan + one barrier.  `buf` is a 2-deep ping-pong so consecutive scans
-// need no trailing barrier.
-template <int NWS, typename T>
-__device__ __forceinline__ T scan_front_warps(T value, T (*buf)[34], uint32_t& flip, T& total) {
+// Exclusive scan over the values of the first `nws` consumer warps (other threads pass 0 and only
+// read the total): one warp-shuffle scan + one consumer barrier.  `buf` is a 2-deep ping-pong so
+// consecutive scans need no trailing barrier.
+template <int NT, typename T>
+__device__ __forceinline__ T scan_front_warps(T value, int nws, T (*buf)[34], uint32_t& flip, T& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     T* sums = buf[flip & 1u];
     flip ^= 1u;
     T incl = value;
-    if (warp < NWS) {
+    if (warp < nws) {
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             T up = __shfl_up_sync(0xffffffffu, incl, d);
@@ -143,10 +163,9 @@ __device__ __forceinline__ T scan_front_warps(T value, T (*buf)[34], uint32_t& f
         }
         if (lane == 31) sums[warp] = incl;
     }
-    __syncthreads();
+    consumer_sync<NT>();
     T before = 0, all = 0;
-#pragma unroll
-    for (int w = 0; w < NWS; ++w) {
+    for (int w = 0; w < nws; ++w) {
         const T s = sums[w];
         if (w < warp) before += s;
         all += s;
@@ -155,29 +174,38 @@ __device__ __forceinline__ T scan_front_warps(T value, T (*buf)[34], uint32_t& f
     return incl - value + before;
 }
 
-// One vertex of an active cell, from the shared-memory bricks.  (x,y,z) cell coords, slot_of(zi)
-// maps a sample-layer index to its ring slot.  Arithmetic: SURVEY.md Appendix A.1.
-template <class C, class SlotOf>
-__device__ __forceinline__ void emit_regular_vertex(const Smem<C>& sm, SlotOf slot_of, int x, int y, int z,
-                                                    uint32_t code, uint32_t transition_mask, hvx_vertex* dst) {
+// One vertex of an active cell, from the shared-memory bricks.  (x,y) cell coords, zl the cell
+// layer relative to the batch's first layer, z its absolute layer; layer_words(d) is the word
+// offset inside the ring of sample layer (first layer + d).  Arithmetic: SURVEY.md Appendix A.1.
+template <class C, class LayerOff>
+__device__ __forceinline__ void emit_regular_vertex(const uint32_t* __restrict__ ring, LayerOff layer_words, int x, int y,
+                                                    int zl, int z, uint32_t code, uint32_t transition_mask,
+                                                    hvx_vertex* dst) {
+    constexpr int S = C::S;
     const int c0 = code >> 4, c1 = code & 15;
     // sample-index coordinates of both edge endpoints (local + 1 for the halo)
-    const int ax = x + 1 + (c0 & 1), ay = y + 1 + ((c0 >> 1) & 1), az = z + 1 + ((c0 >> 2) & 1);
-    const int bx = x + 1 + (c1 & 1), by = y + 1 + ((c1 >> 1) & 1), bz = z + 1 + ((c1 >> 2) & 1);
-    auto word = [&](int xi, int yi, int zi) -> uint32_t { return sm.ring[slot_of(zi)][yi * C::S + xi]; };
-    auto dens = [&](int xi, int yi, int zi) -> float { return cw_density(word(xi, yi, zi)); };
-    // central difference * 0.5, one-sided (no 0.5) on the +face where local == E
-    auto grad = [&](int xi, int yi, int zi, float d, float g[3]) {
-        g[0] = xi >= C::E + 1 ? fsub(d, dens(xi - 1, yi, zi)) : fmul(fsub(dens(xi + 1, yi, zi), dens(xi - 1, yi, zi)), 0.5f);
-        g[1] = yi >= C::E + 1 ? fsub(d, dens(xi, yi - 1, zi)) : fmul(fsub(dens(xi, yi + 1, zi), dens(xi, yi - 1, zi)), 0.5f);
-        g[2] = zi >= C::E + 1 ? fsub(d, dens(xi, yi, zi - 1)) : fmul(fsub(dens(xi, yi, zi + 1), dens(xi, yi, zi - 1)), 0.5f);
+    const int ax = x + 1 + (c0 & 1), ay = y + 1 + ((c0 >> 1) & 1), adz = 1 + ((c0 >> 2) & 1);
+    const int bx = x + 1 + (c1 & 1), by = y + 1 + ((c1 >> 1) & 1), bdz = 1 + ((c1 >> 2) & 1);
+    const int az = z + adz, bz = z + bdz;  // absolute sample-layer indices
+    // one endpoint: its word, the six neighbours, central difference * 0.5 (one-sided, no 0.5, on
+    // the +face where local == E, i.e. sample index E+1)
+    auto endpoint = [&](int xi, int yi, int dz, int zi, uint32_t& w, float& d, float g[3]) {
+        const int off = yi * S + xi;
+        const uint32_t* l0 = ring + layer_words(zl + dz) + off;
+        const uint32_t* lm = ring + layer_words(zl + dz - 1) + off;
+        w = l0[0];
+        d = cw_density(w);
+        const float xm = cw_density(l0[-1]), ym = cw_density(l0[-S]), zm = cw_density(lm[0]);
+        if (xi >= C::E + 1) g[0] = fsub(d, xm); else g[0] = fmul(fsub(cw_density(l0[1]), xm), 0.5f);
+        if (yi >= C::E + 1) g[1] = fsub(d, ym); else g[1] = fmul(fsub(cw_density(l0[S]), ym), 0.5f);
+        if (zi >= C::E + 1) g[2] = fsub(d, zm);
+        else g[2] = fmul(fsub(cw_density((ring + layer_words(zl + dz + 1) + off)[0]), zm), 0.5f);
     };
-    const uint32_t wa = word(ax, ay, az), wb = word(bx, by, bz);
-    const float d0 = cw_density(wa), d1 = cw_density(wb);
+    uint32_t wa, wb;
+    float d0, d1, ga[3], gb[3];
+    endpoint(ax, ay, adz, az, wa, d0, ga);
+    endpoint(bx, by, bdz, bz, wb, d1, gb);
     const float t = edge_parameter(d0, d1);
-    float ga[3], gb[3];
-    grad(ax, ay, az, d0, ga);
-    grad(bx, by, bz, d1, gb);
     float p[3], n[3];
     p[0] = fmix(static_cast<float>(ax - 1), static_cast<float>(bx - 1), t);
     p[1] = fmix(static_cast<float>(ay - 1), static_cast<float>(by - 1), t);
@@ -225,159 +253,121 @@ __device__ __forceinline__ void emit_regular_vertex(const Smem<C>& sm, SlotOf sl
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const RegularParams p) {
+__global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const RegularParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C>& sm = *reinterpret_cast<Smem<C>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int E = C::E, S = C::S, R = C::R, ZB = C::ZB, NT = C::NT;
+    constexpr int E = C::E, S = C::S, R = C::R, NT = C::NT, NW = C::NW;
     constexpr uint64_t ROWMASK = E == 64 ? ~0ull : 0xffffffffull;
     const size_t chunk_words = static_cast<size_t>(S) * S * S;
 
-    // ---- one-time setup -------------------------------------------------------------
-    for (int i = tid; i < 256; i += NT) sm.case_info[i] = HVX_REGULAR_CASE_INFO[i];
-    for (int i = tid; i < 256 * 12; i += NT) sm.vertex_edge[i] = HVX_REGULAR_VERTEX_EDGE[i / 12][i % 12];
-    for (int i = tid; i < 256; i += NT) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
-    for (int i = tid; i < R * C::BW; i += NT) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. the zero padding
+    // ---- one-time setup (all warps) ---------------------------------------------------------
+    for (int i = tid; i < 256; i += C::NT_ALL) sm.case_info[i] = HVX_REGULAR_CASE_INFO[i];
+    for (int i = tid; i < 256 * 12; i += C::NT_ALL) sm.vertex_edge[i] = HVX_REGULAR_VERTEX_EDGE[i / 12][i % 12];
+    for (int i = tid; i < 256; i += C::NT_ALL) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
+    for (int i = tid; i < C::BR * C::BW; i += C::NT_ALL) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. zero padding
     if (tid == 0) {
-        for (int i = 0; i < R; ++i) mbar_init(&sm.full_bar[i], 1);
+        for (int i = 0; i < R; ++i) {
+            mbar_init(&sm.full_bar[i], 1);
+            mbar_init(&sm.empty_bar[i], NW);
+        }
+        for (int i = 0; i < C::BR; ++i) mbar_init(&sm.bits_bar[i], NW);
+        for (int i = 0; i < C::VR; ++i) mbar_init(&sm.verdict_bar[i], C::PW);
         mbar_fence_init();
     }
     __syncthreads();
 
-    // ---- producer state (thread 0 only) ---------------------------------------------
-    // The CTA consumes a flat stream of sample layers: local chunk k contributes layers
-    // seq = k*S .. k*S+S-1; slot = seq % R, barrier parity = (seq / R) & 1.
-    uint32_t prod_seq = 0, prod_k = 0, prod_zi = 0, prod_slot = 0;
-    bool prod_done = false;
-    auto produce = [&](uint32_t oldest_needed_seq) {
-        while (!prod_done && prod_seq < oldest_needed_seq + R) {
-            if (prod_zi == 0) {
-                uint32_t id = atomicAdd(p.work_counter, 1u);
-                sm.chunk_ids[prod_k & 3] = id;
+    // =========================================================================================
+    // PRODUCER warp: chunk queue + TMA bulk copies.  Stream position seq = local_chunk * S + layer;
+    // slot = seq % R; the n-th use of a slot waits for the (n-1)-th release (parity (n-1) & 1).
+    // =========================================================================================
+    if (warp == NW) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t round = 0;  // how many times the ring has wrapped
+            for (uint32_t k = 0;; ++k) {
+                const uint32_t id = atomicAdd(p.work_counter, 1u);
+                // chunk_ids[k & 3] was last read for local chunk k - 4, long retired (R < S)
+                sm.chunk_ids[k & 3] = id;
                 if (id >= p.n_chunks) {
-                    prod_done = true;
+                    // sentinel: complete the slot's phase without data so the consumers wake up and exit
+                    mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    mbar_arrive(&sm.full_bar[slot]);
                     break;
                 }
-            }
-            const uint32_t id = sm.chunk_ids[prod_k & 3];
-            const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words +
-                                  static_cast<size_t>(prod_zi) * C::LAYER_WORDS;
-            mbar_arrive_expect_tx(&sm.full_bar[prod_slot], C::LAYER_BYTES);
-            bulk_g2s(&sm.ring[prod_slot][0], src, C::LAYER_BYTES, &sm.full_bar[prod_slot]);
-            ++prod_seq;
-            prod_slot = prod_slot + 1 == R ? 0 : prod_slot + 1;
-            if (++prod_zi == S) {
-                prod_zi = 0;
-                ++prod_k;
-            }
-        }
-    };
-
-    // ---- consumer state (uniform across the CTA) -------------------------------------
-    // (win_slot, win_q) = (seq % R, seq / R) of sample layer z0 of the current step, kept
-    // incrementally so the hot loop has no division.
-    uint32_t base_seq = 0;
-    int win_slot = 0;
-    uint32_t win_q = 0, flip32 = 0, flip64 = 0;
-    auto advance = [&](int layers) {
-        win_slot += layers;
-        while (win_slot >= R) {
-            win_slot -= R;
-            ++win_q;
-        }
-    };
-    for (uint32_t kc = 0;; ++kc, base_seq += S) {
-        if (tid == 0) produce(base_seq);
-        __syncthreads();
-        const uint32_t chunk = sm.chunk_ids[kc & 3];
-        if (chunk >= p.n_chunks) break;
-        const ChunkDesc desc = p.descs[chunk];
-        const uint64_t dirty = desc.dirty_microbricks;
-        const uint32_t tmask = desc.transition_mask & 0x3fu;
-        if (tid < 16) {
-            // x mask of dirty microbricks for (my, mz) = (tid & 3, tid >> 2)
-            uint64_t m = 0;
-            for (int mx = 0; mx < 4; ++mx)
-                if ((dirty >> (mx + 4 * tid)) & 1ull) m |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
-            sm.dirty_row[tid] = m;
-        }
-        hvx_vertex* const out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
-        uint32_t* const out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
-        const bool debug = p.cells != nullptr;
-        const bool do_emit = p.mode == MODE_EXTRACT;
-
-        uint32_t v_base = 0, i_base = 0;  // running chunk-local placement
-        uint32_t active_cells = 0;        // classify counters
-        int waited = 0;                   // sample layers [0, waited) of this chunk have landed
-
-        for (int z0 = 0; z0 < E; z0 += ZB) {
-            if (z0 != 0 && tid == 0) produce(base_seq + z0);
-            // ring slot of sample layer z0 + d, d in [0, R)
-            auto slot_of = [&](int d) -> int {
-                const int s = win_slot + d;
-                return s >= R ? s - R : s;
-            };
-            auto slot_of_layer = [&](int zi) -> int { return slot_of(zi - z0); };
-            // ---- P0: wait for the window's layers ---------------------------------------
-            const int need = min(S, z0 + C::WIN);
-            for (int zi = waited; zi < need; ++zi) {
-                const int s = win_slot + (zi - z0);
-                const bool wrap = s >= R;
-                mbar_wait(&sm.full_bar[wrap ? s - R : s], (win_q + (wrap ? 1u : 0u)) & 1u);
-            }
-            if (p.mode == MODE_STREAM_ONLY) {  // diagnostics: the bare HBM -> smem pipeline
-                waited = need;
-                __syncthreads();
-                advance(ZB);
-                continue;
-            }
-            // ---- P1: solid bits of the new corner layers, 32 samples per warp ballot -------
-            {
-                const int first = z0 == 0 ? 1 : z0 + 2, last = z0 + ZB + 1;  // inclusive, <= E+1
-                constexpr int FULL = C::LAYER_WORDS / 32, TAIL = C::LAYER_WORDS % 32;
-                for (int zi = first; zi <= last; ++zi) {
-                    const int slot = slot_of(zi - z0);
-                    // each lane reads the low (density) half of its sample: LDS.S16, ISETP, VOTE, STS
-                    const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
-                    uint32_t* dst = sm.bits[slot] + warp;
-#pragma unroll
-                    for (int k = 0; k < (FULL + C::NW - 1) / C::NW; ++k) {
-                        if (k * C::NW + C::NW <= FULL || warp < FULL - k * C::NW) {
-                            const short d = src[64 * C::NW * k];
-                            const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                            if (lane == 0) dst[C::NW * k] = b;
-                        }
-                    }
-                    if (TAIL != 0 && warp == C::NW - 1) {
-                        const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * FULL);
-                        const short d = lane < TAIL ? tail[2 * lane] : short(1);
-                        const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                        if (lane == 0) sm.bits[slot][FULL] = b;
+                const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words;
+                for (int zi = 0; zi < S; ++zi) {
+                    mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(&sm.full_bar[slot], C::LAYER_BYTES);
+                    bulk_g2s(&sm.ring[slot][0], src + static_cast<size_t>(zi) * C::LAYER_WORDS, C::LAYER_BYTES,
+                             &sm.full_bar[slot]);
+                    if (++slot == R) {
+                        slot = 0;
+                        ++round;
                     }
                 }
             }
-            waited = need;
-            __syncthreads();
-            // ---- P2: per-row active masks + ordered ranks --------------------------------
-            uint32_t my_count = 0;
-            if (tid < C::ROWS) {
-                const int zl = tid / E, y = tid % E, z = z0 + zl;
-                const RowCorners rc = load_row_corners<C>(sm, slot_of(zl + 1), slot_of(zl + 2), y);
-                const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
-                const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
-                const uint64_t act = any & ~all & ROWMASK & sm.dirty_row[(y / C::QW) + 4 * (z / C::QW)];
-                sm.active[tid] = act;
-                my_count = __popcll(act);
+        }
+        return;
+    }
+
+    // =========================================================================================
+    // CONSUMER warps
+    // =========================================================================================
+    const uint32_t* const ring_flat = &sm.ring[0][0];
+    int slot = 0;            // ring slot of the sample layer being consumed
+    uint32_t round = 0;      // ring wraps seen by the consume pointer
+    int rel_slot = 0;        // ring slot of the oldest sample layer not yet handed back
+    uint32_t bc = 0;         // running count of layers classified into bits (ring index bc & 7)
+    uint32_t zc = 0;         // running count of cell layers given a verdict (ring index zc & 7)
+    uint32_t flip32 = 0, flip64 = 0;
+    const int p2_group = warp / C::PW, p2_sub = warp % C::PW;
+
+    for (uint32_t kc = 0;; ++kc) {
+        uint32_t chunk = 0;
+        ChunkDesc desc{};
+        uint64_t dirty = 0;
+        uint32_t tmask = 0;
+        hvx_vertex* out_v = nullptr;
+        uint32_t* out_i = nullptr;
+        const bool debug = p.cells != nullptr;
+        const bool do_emit = p.mode == MODE_EXTRACT;
+        uint32_t v_base = 0, i_base = 0, active_cells = 0;  // running chunk-local placement / counters
+        int released = 0;        // sample layers of this chunk handed back to the producer
+        int pend_first = 0, pend_count = 0;  // cell layers waiting for a collective emission
+        const uint32_t bc0 = bc;  // bits index of sample layer 1 of this chunk
+        const uint32_t zc0 = zc;  // verdict index of cell layer 0 of this chunk
+
+        auto release_through = [&](int last_layer) {  // hand back sample layers [released, last_layer]
+            while (released <= last_layer) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.empty_bar[rel_slot]);
+                if (++rel_slot == R) rel_slot = 0;
+                ++released;
             }
-            // Most steps of most chunks see no surface at all: one barrier-with-OR decides, and only
-            // steps with active cells pay for the rank scan.  (Debug records need every step.)
-            if (!__syncthreads_or(my_count != 0) && !debug) {
-                advance(ZB);
-                continue;
+        };
+
+        // ---- collective emission of cell layers [pend_first, pend_first + pend_count) -----------
+        auto flush = [&]() {
+            const int z0 = pend_first, nl = pend_count, rows = nl * E;
+            const int nrw = rows / 32;  // warps holding row threads
+            // sample layer (z0 + d) lives in ring slot rel_slot + d (released == z0 here)
+            auto layer_words = [&](int d) -> int {
+                int s = rel_slot + d;
+                if (s >= R) s -= R;
+                return s * C::LAYER_WORDS;
+            };
+            auto bits_of = [&](int sample_layer) -> const uint32_t* {  // sample_layer >= 1
+                return sm.bits[(bc0 + static_cast<uint32_t>(sample_layer - 1)) & (C::BR - 1)];
+            };
+            uint32_t my_count = 0;
+            if (tid < rows) {
+                const int zl = tid / E, y = tid % E;
+                my_count = __popcll(sm.active[(zc0 + static_cast<uint32_t>(z0 + zl)) & (C::VR - 1)][y]);
             }
             uint32_t n_active;
-            const uint32_t my_off = scan_front_warps<C::ROW_WARPS>(my_count, sm.scan32, flip32, n_active);
-            if (tid < C::ROWS) sm.row_off[tid] = my_off;
+            const uint32_t my_off = scan_front_warps<NT>(my_count, nrw, sm.scan32, flip32, n_active);
+            if (tid < rows) sm.row_off[tid] = my_off;
 
             if (debug) {
                 // ---- debug records: per-cell case words, block-relative offsets, scan blocks ----
@@ -386,13 +376,15 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                 RowCorners rc;
                 uint64_t dirty_x = 0;
                 int zl = 0, y = 0, z = 0;
-                if (tid < C::ROWS) {
+                if (tid < rows) {
                     zl = tid / E;
                     y = tid % E;
                     z = z0 + zl;
-                    rc = load_row_corners<C>(sm, slot_of(zl + 1), slot_of(zl + 2), y);
-                    dirty_x = sm.dirty_row[(y / C::QW) + 4 * (z / C::QW)];
-                    uint64_t act = sm.active[tid];
+                    rc = load_row_corners<C>(bits_of(z + 1), bits_of(z + 2), y);
+                    const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
+                    for (int mx = 0; mx < 4; ++mx)
+                        if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
+                    uint64_t act = sm.active[(zc0 + static_cast<uint32_t>(z)) & (C::VR - 1)][y];
                     while (act) {
                         const int x = __ffsll(static_cast<long long>(act)) - 1;
                         act &= act - 1;
@@ -401,11 +393,11 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                     }
                 }
                 uint64_t step_tot;
-                const uint64_t row_pref = scan_front_warps<C::ROW_WARPS>(row_tot, sm.scan64, flip64, step_tot);
-                if (tid < C::ROWS) sm.row_pref64[tid] = row_pref;
-                if (tid == 0) sm.row_pref64[C::ROWS] = step_tot;
-                __syncthreads();
-                if (tid < C::ROWS) {
+                const uint64_t row_pref = scan_front_warps<NT>(row_tot, nrw, sm.scan64, flip64, step_tot);
+                if (tid < rows) sm.row_pref64[tid] = row_pref;
+                if (tid == 0) sm.row_pref64[rows] = step_tot;
+                consumer_sync<NT>();
+                if (tid < rows) {
                     const int block_row = (tid / C::RPB) * C::RPB;  // first row of this cell's 256-block
                     const uint64_t bp = sm.row_pref64[block_row];
                     uint32_t rv = static_cast<uint32_t>(row_pref) - static_cast<uint32_t>(bp);
@@ -440,20 +432,14 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                 }
             }
 
-            if (n_active == 0) {  // uniform: nothing on the surface in these layers
-                advance(ZB);
-                continue;
-            }
             active_cells += n_active;
-
-            // ---- P3: emission in ordered batches of CB active cells -----------------------
             for (uint32_t b0 = 0; b0 < n_active; b0 += C::CB) {
                 const uint32_t nb = min(static_cast<uint32_t>(C::CB), n_active - b0);
-                __syncthreads();  // row_off / previous batch's cell_rec, owner are free
+                consumer_sync<NT>();  // row_off / previous sub-batch's cell_rec, owner are free
                 // P3a: rank scatter, one thread per quarter row
-                for (int q = tid; q < C::ROWS * 4; q += NT) {
+                for (int q = tid; q < rows * 4; q += NT) {
                     const int r = q >> 2, part = q & 3;
-                    const uint64_t m = sm.active[r];
+                    const uint64_t m = sm.active[(zc0 + static_cast<uint32_t>(z0 + r / E)) & (C::VR - 1)][r % E];
                     uint32_t sub = static_cast<uint32_t>((m >> (C::QW * part)) & ((1ull << C::QW) - 1ull));
                     if (!sub) continue;
                     uint32_t rank = sm.row_off[r] + __popcll(m & ((1ull << (C::QW * part)) - 1ull));
@@ -465,20 +451,20 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                         ++rank;
                     }
                 }
-                __syncthreads();
+                consumer_sync<NT>();
                 // P3b: case lookup, per-cell counts, ordered offsets, index emission
                 uint32_t packed = 0, rec = 0, info = 0;
                 if (tid < nb) {
                     rec = sm.cell_rec[tid];
                     const int x = rec & 63, r = rec >> 8, zl = r / E, y = r % E;
-                    const RowCorners rc = load_row_corners<C>(sm, slot_of(zl + 1), slot_of(zl + 2), y);
+                    const RowCorners rc = load_row_corners<C>(bits_of(z0 + zl + 1), bits_of(z0 + zl + 2), y);
                     const uint32_t c = case_at(rc, x);
                     info = sm.case_info[c];
                     rec |= c << 16;
                     packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
                 }
                 uint32_t batch_tot;
-                const uint32_t off = scan_front_warps<C::NW>(packed, sm.scan32, flip32, batch_tot);
+                const uint32_t off = scan_front_warps<NT>(packed, static_cast<int>((nb + 31u) / 32u), sm.scan32, flip32, batch_tot);
                 const uint32_t batch_v = batch_tot & 0xffffu, batch_i = batch_tot >> 16;
                 if (tid < nb && do_emit) {
                     const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
@@ -491,27 +477,130 @@ __global__ void __launch_bounds__(C::NT, 1) regular_extract_kernel(const Regular
                     for (uint32_t j = 0; j < ni; ++j)
                         if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + tri[j];
                 }
-                __syncthreads();
+                consumer_sync<NT>();
                 // P3c: one thread per vertex
                 if (do_emit) {
                     for (uint32_t v = tid; v < batch_v; v += NT) {
                         const uint32_t o = sm.owner[v];
-                        const uint32_t slot = o & 1023u, k = o >> 10;
-                        const uint32_t cr = sm.cell_rec[slot];
+                        const uint32_t cslot = o & 1023u, k = o >> 10;
+                        const uint32_t cr = sm.cell_rec[cslot];
                         const int x = cr & 63, r = (cr >> 8) & 255, c = cr >> 16;
-                        const int zl = r / E, y = r % E, z = z0 + zl;
+                        const int zl = r / E, y = r % E;
                         const uint32_t code = sm.vertex_edge[c * 12 + k];
                         if (v_base + v < p.max_vertices)
-                            emit_regular_vertex<C>(sm, slot_of_layer, x, y, z, code, tmask, out_v + v_base + v);
+                            emit_regular_vertex<C>(ring_flat, layer_words, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
                     }
                 }
                 v_base += batch_v;
                 i_base += batch_i;
             }
-            __syncthreads();  // ring reads of this step are done before the producer refills
-            advance(ZB);
+            consumer_sync<NT>();  // every ring / bits / active read of this batch is done
+            pend_count = 0;
+        };
+
+        // ---- verdict of cell layer z: queue it for emission or hand its oldest sample layer back ----
+        auto handle_verdict = [&](int z) {
+            const uint32_t vi = (zc0 + static_cast<uint32_t>(z));
+            mbar_wait(&sm.verdict_bar[vi & (C::VR - 1)], (vi / C::VR) & 1u);
+            const uint32_t* f = sm.verdict_flag[vi & (C::VR - 1)];
+            const bool has_surface = (f[0] | (C::PW > 1 ? f[1] : 0u)) != 0u;
+            if (has_surface || debug) {
+                if (pend_count == 0) pend_first = z;
+                if (++pend_count == C::EB) {
+                    flush();
+                    release_through(z);
+                }
+            } else {
+                if (pend_count != 0) flush();
+                release_through(z);
+            }
+        };
+
+        // ---- walk the chunk's sample layers as they land ----------------------------------------
+        bool stop = false;
+        for (int L = 0; L < S; ++L) {
+            mbar_wait(&sm.full_bar[slot], round & 1u);
+            if (L == 0) {
+                chunk = sm.chunk_ids[kc & 3];
+                if (chunk >= p.n_chunks) {
+                    stop = true;
+                    break;
+                }
+                desc = p.descs[chunk];
+                dirty = desc.dirty_microbricks;
+                tmask = desc.transition_mask & 0x3fu;
+                out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
+                out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
+            }
+            if (p.mode == MODE_STREAM_ONLY) {  // diagnostics: the bare HBM -> smem pipeline
+                release_through(L);
+            } else {
+                if (L >= 1) {
+                    // ---- P1: this warp's share of the layer's solid bits: LDS, sign test, VOTE, STS ----
+                    const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
+                    uint32_t* dst = sm.bits[bc & (C::BR - 1)] + warp;
+#pragma unroll
+                    for (int k = 0; k < (C::FULL + NW - 1) / NW; ++k) {
+                        if (k * NW + NW <= C::FULL || warp < C::FULL - k * NW) {
+                            const short d = src[64 * NW * k];
+                            const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
+                            if (lane == 0) dst[NW * k] = b;
+                        }
+                    }
+                    if (C::TAIL != 0 && warp == NW - 1) {
+                        const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * C::FULL);
+                        const short d = lane < C::TAIL ? tail[2 * lane] : short(1);
+                        const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
+                        if (lane == 0) sm.bits[bc & (C::BR - 1)][C::FULL] = b;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.bits_bar[bc & (C::BR - 1)]);
+                    ++bc;
+                }
+                if (p.mode == MODE_BITS_ONLY) { release_through(L); } else
+                if (L >= 2) {
+                    // ---- P2: one group of warps classifies cell layer z = L - 2 -------------------
+                    const int z = L - 2;
+                    if (p2_group == z % C::PG) {
+                        const uint32_t b1 = bc - 2, b2 = bc - 1;  // bits of sample layers z + 1, z + 2
+                        mbar_wait(&sm.bits_bar[b1 & (C::BR - 1)], (b1 / C::BR) & 1u);
+                        mbar_wait(&sm.bits_bar[b2 & (C::BR - 1)], (b2 / C::BR) & 1u);
+                        const int y = p2_sub * 32 + lane;
+                        const RowCorners rc = load_row_corners<C>(sm.bits[b1 & (C::BR - 1)], sm.bits[b2 & (C::BR - 1)], y);
+                        const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
+                        const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
+                        uint64_t act = any & ~all & ROWMASK;
+                        if (dirty != ~0ull) {
+                            const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
+                            uint64_t dirty_x = 0;
+#pragma unroll
+                            for (int mx = 0; mx < 4; ++mx)
+                                if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
+                            act &= dirty_x;
+                        }
+                        const uint32_t vi = zc0 + static_cast<uint32_t>(z);
+                        sm.active[vi & (C::VR - 1)][y] = act;
+                        const bool any_row = __any_sync(0xffffffffu, act != 0);
+                        if (lane == 0) {
+                            sm.verdict_flag[vi & (C::VR - 1)][p2_sub] = any_row ? 1u : 0u;
+                            mbar_arrive(&sm.verdict_bar[vi & (C::VR - 1)]);
+                        }
+                    }
+                }
+                if (L >= 3 && p.mode != MODE_BITS_ONLY) handle_verdict(L - 3);
+            }
+            if (++slot == R) {
+                slot = 0;
+                ++round;
+            }
         }
-        advance(S - E);  // the chunk's last two sample layers
+        if (stop) break;
+        if (p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY) {
+            handle_verdict(E - 1);
+            if (pend_count != 0) flush();
+            release_through(S - 1);
+            zc += E;
+        }
 
         // ---- chunk epilogue: one counter record, no atomics --------------------------------
         if (tid == 0) {
@@ -550,17 +639,17 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
                                            static_cast<int>(smem));
     if (err != cudaSuccess) return err;
     int ctas_per_sm = 1;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, regular_extract_kernel<C>, C::NT, smem);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, regular_extract_kernel<C>, C::NT_ALL, smem);
     if (err != cudaSuccess) return err;
     if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
     const uint32_t grid = static_cast<uint32_t>(
         min(static_cast<long long>(p.n_chunks), static_cast<long long>(dev.sm_count) * ctas_per_sm));
-    regular_extract_kernel<C><<<grid, C::NT, smem, stream>>>(p);
+    regular_extract_kernel<C><<<grid, C::NT_ALL, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-using Cfg64 = Cfg<64, 2, 11, 512>;
-using Cfg32 = Cfg<32, 4, 16, 256>;
+using Cfg64 = Cfg<64, 4, 11, 16>;
+using Cfg32 = Cfg<32, 4, 16, 8>;
 
 // Tuning variants (HVX_REGULAR_VARIANT=<n>, default 0); all produce identical output.
 int variant_from_env() {
@@ -579,19 +668,19 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     const int variant = variant_from_env();
     if (edge == 64) {
         switch (variant) {
-            case 1: return launch_cfg<Cfg<64, 4, 11, 512>>(p, dev, stream);
-            case 2: return launch_cfg<Cfg<64, 2, 11, 256>>(p, dev, stream);
-            case 3: return launch_cfg<Cfg<64, 4, 11, 256>>(p, dev, stream);
-            case 4: return launch_cfg<Cfg<64, 1, 10, 256>>(p, dev, stream);
-            case 5: return launch_cfg<Cfg<64, 2, 9, 512>>(p, dev, stream);
+            case 1: return launch_cfg<Cfg<64, 2, 11, 16>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<64, 4, 11, 8>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<64, 1, 11, 16>>(p, dev, stream);
+            case 4: return launch_cfg<Cfg<64, 4, 10, 16>>(p, dev, stream);
+            case 5: return launch_cfg<Cfg<64, 2, 8, 16>>(p, dev, stream);
             default: return launch_cfg<Cfg64>(p, dev, stream);
         }
     }
     if (edge == 32) {
         switch (variant) {
-            case 1: return launch_cfg<Cfg<32, 8, 20, 256>>(p, dev, stream);
-            case 2: return launch_cfg<Cfg<32, 4, 16, 128>>(p, dev, stream);
-            case 3: return launch_cfg<Cfg<32, 2, 12, 128>>(p, dev, stream);
+            case 1: return launch_cfg<Cfg<32, 8, 20, 8>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<32, 4, 16, 4>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<32, 4, 12, 8>>(p, dev, stream);
             default: return launch_cfg<Cfg32>(p, dev, stream);
         }
     }
