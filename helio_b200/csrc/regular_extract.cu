@@ -41,51 +41,56 @@ namespace {
 #define HVX_TABLE static __device__ const
 #include "transvoxel_tables.inc"
 
-template <int E_, int EB_, int R_, int NW_>
+template <int E_, int EBS_, int RS_, int NW_>
 struct Cfg {
     static constexpr int E = E_;          // cells per chunk edge
     static constexpr int S = E_ + 2;      // samples per edge (1-sample halo)
-    static constexpr int EB = EB_;        // max cell layers per emission batch
-    static constexpr int R = R_;          // ring slots (sample layers resident or in flight)
+    static constexpr int G = 2;           // sample layers per slab (one TMA copy, one hand-off)
+    static constexpr int NSLAB = S / G;   // slabs per chunk
+    static constexpr int EBS = EBS_;      // max steps (pairs of cell layers) per emission batch
+    static constexpr int RS = RS_;        // ring slots, in slabs
     static constexpr int NW = NW_;        // consumer warps
     static constexpr int NT = NW_ * 32;   // consumer threads
     static constexpr int NT_ALL = NT + 32;  // + producer warp
     static constexpr int LAYER_WORDS = S * S;
-    static constexpr int LAYER_BYTES = LAYER_WORDS * 4;
-    static constexpr int FULL = LAYER_WORDS / 32;       // whole 32-sample ballot blocks per layer
-    static constexpr int TAIL = LAYER_WORDS % 32;
-    static constexpr int BW = FULL + 1 + 3;             // bit words per layer + zero padding
-    static constexpr int BR = EB_ <= 4 ? 8 : 16;        // bit-layer ring (>= EB + 4 live layers)
-    static constexpr int VR = BR;                       // verdict / active-mask ring
-    static constexpr int PW = E_ / 32;                  // warps classifying one cell layer
-    static constexpr int PG = NW_ / PW;                 // classification groups
-    static constexpr int ROWS = EB_ * E_;               // cell rows per emission batch
-    static constexpr int CB = NT;                       // active cells per emission sub-batch
+    static constexpr int SLAB_WORDS = G * LAYER_WORDS;
+    static constexpr int SLAB_BYTES = SLAB_WORDS * 4;
+    static constexpr int FULL = SLAB_WORDS / 32;        // whole 32-sample ballot blocks per slab
+    static constexpr int TAIL = SLAB_WORDS % 32;
+    static constexpr int BPW = FULL / NW_;              // ballot blocks per warp per slab
+    static constexpr int BW = FULL + 1 + 3;             // bit words per slab + zero padding
+    static constexpr int BR = EBS_ == 1 ? 4 : 8;        // slab-bits ring / verdict ring depth
+    static constexpr int PWS = (G * E_) / 32;           // warps classifying one step (G cell layers)
+    static constexpr int PG = NW_ / PWS;                // classification groups
+    static constexpr int STEP_ROWS = G * E_;            // cell rows per step
+    static constexpr int ROWS = EBS_ * STEP_ROWS;       // cell rows per emission batch
+    static constexpr int CB = NT / 2;                   // active cells per emission sub-batch
     static constexpr int QW = E_ / 4;                   // microbrick edge == quarter-row width
     static constexpr int RPB = 256 / E_;                // rows per 256-cell scan block
-    static_assert(R_ >= EB_ + 3 + 2, "ring must hold an emission window plus layers in flight");
-    static_assert(R_ < E_ + 2, "producer may be at most one chunk ahead");
-    static_assert(EB_ + 4 <= BR && EB_ + 4 <= VR, "bit / verdict rings too small");
-    static_assert(LAYER_BYTES % 16 == 0, "cp.async.bulk needs 16-byte multiples");
-    static_assert(ROWS <= NT && ROWS % 32 == 0 && NW_ % PW == 0 && (E_ == 32 || E_ == 64), "unsupported tiling");
+    static_assert(S % G == 0 && FULL % NW_ == 0, "slab must split evenly into ballot blocks per warp");
+    static_assert(RS_ >= EBS_ + 3 + 1, "ring must hold an emission window, the slab being classified and one in flight");
+    static_assert(RS_ < NSLAB, "producer may be at most one chunk ahead");
+    static_assert(EBS_ + 3 <= BR, "bit / verdict rings too small");
+    static_assert(SLAB_BYTES % 16 == 0, "cp.async.bulk needs 16-byte multiples");
+    static_assert(ROWS <= NT && NW_ % PWS == 0 && (E_ == 32 || E_ == 64), "unsupported tiling");
 };
 
 template <class C>
 struct Smem {
-    alignas(128) uint32_t ring[C::R][C::LAYER_WORDS];
-    alignas(8) uint64_t full_bar[C::R];
-    uint64_t empty_bar[C::R];
+    alignas(128) uint32_t ring[C::RS][C::SLAB_WORDS];
+    alignas(8) uint64_t full_bar[C::RS];
+    uint64_t empty_bar[C::RS];
     uint64_t bits_bar[C::BR];
-    uint64_t verdict_bar[C::VR];
-    uint64_t active[C::VR][C::E];   // active-cell bits per cell row, written by the classifying warps
+    uint64_t verdict_bar[C::BR];
+    uint64_t active[C::BR][C::STEP_ROWS];  // active-cell bits per cell row of a step
     union {
         uint16_t owner[C::CB * 12];        // emission: vertex -> cell slot | k<<10
         uint64_t row_pref64[C::ROWS + 1];  // debug records: per-row exclusive (vertices | indices<<32)
     };
     uint64_t scan64[2][34];
     uint32_t scan32[2][34];
-    uint32_t bits[C::BR][C::BW];    // solid bit of every sample of a layer, flat x-fastest order
-    uint32_t verdict_flag[C::VR][2];
+    uint32_t bits[C::BR][C::BW];    // solid bit of every sample of a slab, flat x-fastest order
+    uint32_t verdict_flag[C::BR][C::PWS];
     uint32_t row_off[C::ROWS + 1];  // exclusive prefix of popc(active)
     uint32_t cell_rec[C::CB];       // x | row<<8 | case<<16
     uint32_t chunk_ids[4];
@@ -110,10 +115,10 @@ struct RowCorners {
     uint64_t a00, b00, a10, b10, a01, b01, a11, b11;
 };
 
-// Bits [o+1, o+1+E) and [o+2, o+2+E) of a layer's flat solid-bit array, o = row * S.
+// Bits [o+1, o+1+E) and [o+2, o+2+E) of a flat solid-bit array, o = base + row * S.
 template <class C>
-__device__ __forceinline__ void row_window(const uint32_t* __restrict__ bits, int row, uint64_t& a, uint64_t& b) {
-    const int p = row * C::S + 1, w = p >> 5, sh = p & 31;
+__device__ __forceinline__ void row_window(const uint32_t* __restrict__ bits, int base, int row, uint64_t& a, uint64_t& b) {
+    const int p = base + row * C::S + 1, w = p >> 5, sh = p & 31;
     const uint32_t x0 = bits[w], x1 = bits[w + 1], x2 = bits[w + 2];
     if (C::E == 64) {
         const uint32_t x3 = bits[w + 3];
@@ -128,14 +133,15 @@ __device__ __forceinline__ void row_window(const uint32_t* __restrict__ bits, in
     }
 }
 
+// bits0/base0: slab bit array and bit offset of sample layer z+1; bits1/base1: of sample layer z+2
 template <class C>
-__device__ __forceinline__ RowCorners load_row_corners(const uint32_t* __restrict__ bits0,
-                                                       const uint32_t* __restrict__ bits1, int y) {
+__device__ __forceinline__ RowCorners load_row_corners(const uint32_t* __restrict__ bits0, int base0,
+                                                       const uint32_t* __restrict__ bits1, int base1, int y) {
     RowCorners rc;
-    row_window<C>(bits0, y + 1, rc.a00, rc.b00);
-    row_window<C>(bits0, y + 2, rc.a10, rc.b10);
-    row_window<C>(bits1, y + 1, rc.a01, rc.b01);
-    row_window<C>(bits1, y + 2, rc.a11, rc.b11);
+    row_window<C>(bits0, base0, y + 1, rc.a00, rc.b00);
+    row_window<C>(bits0, base0, y + 2, rc.a10, rc.b10);
+    row_window<C>(bits1, base1, y + 1, rc.a01, rc.b01);
+    row_window<C>(bits1, base1, y + 2, rc.a11, rc.b11);
     return rc;
 }
 
@@ -257,7 +263,7 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C>& sm = *reinterpret_cast<Smem<C>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int E = C::E, S = C::S, R = C::R, NT = C::NT, NW = C::NW;
+    constexpr int E = C::E, S = C::S, RS = C::RS, NT = C::NT, NW = C::NW, LW = C::LAYER_WORDS;
     constexpr uint64_t ROWMASK = E == 64 ? ~0ull : 0xffffffffull;
     const size_t chunk_words = static_cast<size_t>(S) * S * S;
 
@@ -267,19 +273,21 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
     for (int i = tid; i < 256; i += C::NT_ALL) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
     for (int i = tid; i < C::BR * C::BW; i += C::NT_ALL) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. zero padding
     if (tid == 0) {
-        for (int i = 0; i < R; ++i) {
+        for (int i = 0; i < RS; ++i) {
             mbar_init(&sm.full_bar[i], 1);
             mbar_init(&sm.empty_bar[i], NW);
         }
-        for (int i = 0; i < C::BR; ++i) mbar_init(&sm.bits_bar[i], NW);
-        for (int i = 0; i < C::VR; ++i) mbar_init(&sm.verdict_bar[i], C::PW);
+        for (int i = 0; i < C::BR; ++i) {
+            mbar_init(&sm.bits_bar[i], NW);
+            mbar_init(&sm.verdict_bar[i], C::PWS);
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
     // =========================================================================================
-    // PRODUCER warp: chunk queue + TMA bulk copies.  Stream position seq = local_chunk * S + layer;
-    // slot = seq % R; the n-th use of a slot waits for the (n-1)-th release (parity (n-1) & 1).
+    // PRODUCER warp: chunk queue + TMA bulk copies, one slab (G sample layers, contiguous in HBM
+    // and in the ring) per copy.  The n-th use of a ring slot waits for its (n-1)-th release.
     // =========================================================================================
     if (warp == NW) {
         if (lane == 0) {
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
             uint32_t round = 0;  // how many times the ring has wrapped
             for (uint32_t k = 0;; ++k) {
                 const uint32_t id = atomicAdd(p.work_counter, 1u);
-                // chunk_ids[k & 3] was last read for local chunk k - 4, long retired (R < S)
+                // chunk_ids[k & 3] was last read for local chunk k - 4, long retired (RS < NSLAB)
                 sm.chunk_ids[k & 3] = id;
                 if (id >= p.n_chunks) {
                     // sentinel: complete the slot's phase without data so the consumers wake up and exit
@@ -296,12 +304,12 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                     break;
                 }
                 const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words;
-                for (int zi = 0; zi < S; ++zi) {
+                for (int j = 0; j < C::NSLAB; ++j) {
                     mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&sm.full_bar[slot], C::LAYER_BYTES);
-                    bulk_g2s(&sm.ring[slot][0], src + static_cast<size_t>(zi) * C::LAYER_WORDS, C::LAYER_BYTES,
+                    mbar_arrive_expect_tx(&sm.full_bar[slot], C::SLAB_BYTES);
+                    bulk_g2s(&sm.ring[slot][0], src + static_cast<size_t>(j) * C::SLAB_WORDS, C::SLAB_BYTES,
                              &sm.full_bar[slot]);
-                    if (++slot == R) {
+                    if (++slot == RS) {
                         slot = 0;
                         ++round;
                     }
@@ -312,16 +320,21 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
     }
 
     // =========================================================================================
-    // CONSUMER warps
+    // CONSUMER warps.  Iteration j handles slab j (sample layers 2j, 2j+1) of the chunk:
+    //   P1  every warp turns its 1/NW of the slab into solid bits;
+    //   P2  one group of PWS warps classifies step j = cell layers 2j-2, 2j-1 (needs bits of
+    //       sample layers 2j-1 .. 2j+1) and publishes active masks + a verdict;
+    //   P3  everybody consumes the verdict of step j-1 (published one iteration ago, so the wait
+    //       is normally free); its emission window is slabs j-2 .. j, all resident by now.
     // =========================================================================================
     const uint32_t* const ring_flat = &sm.ring[0][0];
-    int slot = 0;            // ring slot of the sample layer being consumed
+    int slot = 0;            // ring slot of the slab being consumed
     uint32_t round = 0;      // ring wraps seen by the consume pointer
-    int rel_slot = 0;        // ring slot of the oldest sample layer not yet handed back
-    uint32_t bc = 0;         // running count of layers classified into bits (ring index bc & 7)
-    uint32_t zc = 0;         // running count of cell layers given a verdict (ring index zc & 7)
+    int rel_slot = 0;        // ring slot of the oldest slab not yet handed back
+    uint32_t sc = 0;         // running slab counter (bits ring index sc & 3)
+    uint32_t stc = 0;        // running step counter (verdict / active ring index stc & 3)
     uint32_t flip32 = 0, flip64 = 0;
-    const int p2_group = warp / C::PW, p2_sub = warp % C::PW;
+    const int p2_group = warp / C::PWS, p2_sub = warp % C::PWS;
 
     for (uint32_t kc = 0;; ++kc) {
         uint32_t chunk = 0;
@@ -333,38 +346,44 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
         const bool debug = p.cells != nullptr;
         const bool do_emit = p.mode == MODE_EXTRACT;
         uint32_t v_base = 0, i_base = 0, active_cells = 0;  // running chunk-local placement / counters
-        int released = 0;        // sample layers of this chunk handed back to the producer
-        int pend_first = 0, pend_count = 0;  // cell layers waiting for a collective emission
-        const uint32_t bc0 = bc;  // bits index of sample layer 1 of this chunk
-        const uint32_t zc0 = zc;  // verdict index of cell layer 0 of this chunk
+        int released = 0;                    // slabs of this chunk handed back to the producer
+        int pend_first = 0, pend_count = 0;  // steps waiting for a collective emission
+        const uint32_t sc0 = sc;             // slab counter of slab 0 of this chunk
+        const uint32_t stc0 = stc;           // step counter of step 1 of this chunk
 
-        auto release_through = [&](int last_layer) {  // hand back sample layers [released, last_layer]
-            while (released <= last_layer) {
+        auto release_through = [&](int last_slab) {  // hand back slabs [released, last_slab]
+            while (released <= last_slab) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.empty_bar[rel_slot]);
-                if (++rel_slot == R) rel_slot = 0;
+                if (++rel_slot == RS) rel_slot = 0;
                 ++released;
             }
         };
+        // bit array + bit offset of sample layer `idx` of this chunk
+        auto bits_of = [&](int idx, int& base) -> const uint32_t* {
+            base = (idx & 1) * LW;
+            return sm.bits[(sc0 + static_cast<uint32_t>(idx >> 1)) & (C::BR - 1)];
+        };
+        auto active_of = [&](int step) -> uint64_t* {  // step >= 1
+            return sm.active[(stc0 + static_cast<uint32_t>(step - 1)) & (C::BR - 1)];
+        };
 
-        // ---- collective emission of cell layers [pend_first, pend_first + pend_count) -----------
+        // ---- collective emission of steps [pend_first, pend_first + pend_count) -----------------
         auto flush = [&]() {
-            const int z0 = pend_first, nl = pend_count, rows = nl * E;
-            const int nrw = rows / 32;  // warps holding row threads
-            // sample layer (z0 + d) lives in ring slot rel_slot + d (released == z0 here)
+            const int z0 = 2 * pend_first - 2;             // first cell layer of the batch (even)
+            const int rows = pend_count * C::STEP_ROWS;    // row r: cell layer z0 + r / E, y = r % E
+            const int nrw = rows / 32;                     // warps holding row threads
+            // sample layer z0 + d lives in slab (released + d/2) -> ring slot rel_slot + d/2
             auto layer_words = [&](int d) -> int {
-                int s = rel_slot + d;
-                if (s >= R) s -= R;
-                return s * C::LAYER_WORDS;
+                int s2 = rel_slot + (d >> 1);
+                if (s2 >= RS) s2 -= RS;
+                return s2 * C::SLAB_WORDS + (d & 1) * LW;
             };
-            auto bits_of = [&](int sample_layer) -> const uint32_t* {  // sample_layer >= 1
-                return sm.bits[(bc0 + static_cast<uint32_t>(sample_layer - 1)) & (C::BR - 1)];
+            auto active_row = [&](int r) -> uint64_t {
+                return active_of(pend_first + r / C::STEP_ROWS)[r % C::STEP_ROWS];
             };
             uint32_t my_count = 0;
-            if (tid < rows) {
-                const int zl = tid / E, y = tid % E;
-                my_count = __popcll(sm.active[(zc0 + static_cast<uint32_t>(z0 + zl)) & (C::VR - 1)][y]);
-            }
+            if (tid < rows) my_count = __popcll(active_row(tid));
             uint32_t n_active;
             const uint32_t my_off = scan_front_warps<NT>(my_count, nrw, sm.scan32, flip32, n_active);
             if (tid < rows) sm.row_off[tid] = my_off;
@@ -375,16 +394,18 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 uint64_t row_tot = 0;
                 RowCorners rc;
                 uint64_t dirty_x = 0;
-                int zl = 0, y = 0, z = 0;
+                int y = 0, z = 0;
                 if (tid < rows) {
-                    zl = tid / E;
                     y = tid % E;
-                    z = z0 + zl;
-                    rc = load_row_corners<C>(bits_of(z + 1), bits_of(z + 2), y);
+                    z = z0 + tid / E;
+                    int b0, b1;
+                    const uint32_t* p0 = bits_of(z + 1, b0);
+                    const uint32_t* p1 = bits_of(z + 2, b1);
+                    rc = load_row_corners<C>(p0, b0, p1, b1, y);
                     const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
                     for (int mx = 0; mx < 4; ++mx)
                         if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
-                    uint64_t act = sm.active[(zc0 + static_cast<uint32_t>(z)) & (C::VR - 1)][y];
+                    uint64_t act = active_row(tid);
                     while (act) {
                         const int x = __ffsll(static_cast<long long>(act)) - 1;
                         act &= act - 1;
@@ -439,7 +460,7 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 // P3a: rank scatter, one thread per quarter row
                 for (int q = tid; q < rows * 4; q += NT) {
                     const int r = q >> 2, part = q & 3;
-                    const uint64_t m = sm.active[(zc0 + static_cast<uint32_t>(z0 + r / E)) & (C::VR - 1)][r % E];
+                    const uint64_t m = active_row(r);
                     uint32_t sub = static_cast<uint32_t>((m >> (C::QW * part)) & ((1ull << C::QW) - 1ull));
                     if (!sub) continue;
                     uint32_t rank = sm.row_off[r] + __popcll(m & ((1ull << (C::QW * part)) - 1ull));
@@ -456,8 +477,11 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 uint32_t packed = 0, rec = 0, info = 0;
                 if (tid < nb) {
                     rec = sm.cell_rec[tid];
-                    const int x = rec & 63, r = rec >> 8, zl = r / E, y = r % E;
-                    const RowCorners rc = load_row_corners<C>(bits_of(z0 + zl + 1), bits_of(z0 + zl + 2), y);
+                    const int x = rec & 63, r = rec >> 8, z = z0 + r / E, y = r % E;
+                    int bb0, bb1;
+                    const uint32_t* p0 = bits_of(z + 1, bb0);
+                    const uint32_t* p1 = bits_of(z + 2, bb1);
+                    const RowCorners rc = load_row_corners<C>(p0, bb0, p1, bb1, y);
                     const uint32_t c = case_at(rc, x);
                     info = sm.case_info[c];
                     rec |= c << 16;
@@ -498,29 +522,66 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
             pend_count = 0;
         };
 
-        // ---- verdict of cell layer z: queue it for emission or hand its oldest sample layer back ----
-        auto handle_verdict = [&](int z) {
-            const uint32_t vi = (zc0 + static_cast<uint32_t>(z));
-            mbar_wait(&sm.verdict_bar[vi & (C::VR - 1)], (vi / C::VR) & 1u);
-            const uint32_t* f = sm.verdict_flag[vi & (C::VR - 1)];
-            const bool has_surface = (f[0] | (C::PW > 1 ? f[1] : 0u)) != 0u;
-            if (has_surface || debug) {
-                if (pend_count == 0) pend_first = z;
-                if (++pend_count == C::EB) {
-                    flush();
-                    release_through(z);
-                }
-            } else {
-                if (pend_count != 0) flush();
-                release_through(z);
+        // ---- P2: the duty group classifies step st = cell layers 2st-2, 2st-1 --------------------
+        // (needs the bits of sample layers 2st-1 .. 2st+1, i.e. slabs st-1 and st)
+        auto classify_step = [&](int st) {
+            if (p2_group != st % C::PG) return;
+            const uint32_t s1 = sc0 + static_cast<uint32_t>(st - 1), s2 = s1 + 1;
+            mbar_wait(&sm.bits_bar[s1 & (C::BR - 1)], (s1 / C::BR) & 1u);
+            mbar_wait(&sm.bits_bar[s2 & (C::BR - 1)], (s2 / C::BR) & 1u);
+            const int r = p2_sub * 32 + lane, zl = r / E, y = r % E, z = 2 * st - 2 + zl;
+            // sample layers z+1, z+2 = 2st-1+zl, 2st+zl
+            const uint32_t* bp0 = zl == 0 ? sm.bits[s1 & (C::BR - 1)] : sm.bits[s2 & (C::BR - 1)];
+            const int base0 = zl == 0 ? LW : 0;
+            const uint32_t* bp1 = sm.bits[s2 & (C::BR - 1)];
+            const int base1 = zl == 0 ? 0 : LW;
+            const RowCorners rc = load_row_corners<C>(bp0, base0, bp1, base1, y);
+            const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
+            const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
+            uint64_t act = any & ~all & ROWMASK;
+            if (dirty != ~0ull) {
+                const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
+                uint64_t dirty_x = 0;
+#pragma unroll
+                for (int mx = 0; mx < 4; ++mx)
+                    if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
+                act &= dirty_x;
+            }
+            const uint32_t vi = stc0 + static_cast<uint32_t>(st - 1);
+            sm.active[vi & (C::BR - 1)][r] = act;
+            const bool any_row = __any_sync(0xffffffffu, act != 0);
+            if (lane == 0) {
+                sm.verdict_flag[vi & (C::BR - 1)][p2_sub] = any_row ? 1u : 0u;
+                mbar_arrive(&sm.verdict_bar[vi & (C::BR - 1)]);
             }
         };
 
-        // ---- walk the chunk's sample layers as they land ----------------------------------------
+        // ---- verdict of a step: queue it for emission, or hand the oldest slab back --------------
+        // After step st is resolved, slab st - 1 (sample layers 2st-2, 2st-1) is no longer needed.
+        auto handle_verdict = [&](int st) {
+            const uint32_t vi = stc0 + static_cast<uint32_t>(st - 1);
+            mbar_wait(&sm.verdict_bar[vi & (C::BR - 1)], (vi / C::BR) & 1u);
+            const uint32_t* f = sm.verdict_flag[vi & (C::BR - 1)];
+            uint32_t any_flag = 0;
+#pragma unroll
+            for (int i = 0; i < C::PWS; ++i) any_flag |= f[i];
+            if (any_flag != 0u || debug) {
+                if (pend_count == 0) pend_first = st;
+                if (++pend_count == C::EBS) {
+                    flush();
+                    release_through(st - 1);
+                }
+            } else {
+                if (pend_count != 0) flush();
+                release_through(st - 1);
+            }
+        };
+
+        // ---- walk the chunk's slabs as they land ----------------------------------------------
         bool stop = false;
-        for (int L = 0; L < S; ++L) {
+        for (int j = 0; j < C::NSLAB; ++j) {
             mbar_wait(&sm.full_bar[slot], round & 1u);
-            if (L == 0) {
+            if (j == 0) {
                 chunk = sm.chunk_ids[kc & 3];
                 if (chunk >= p.n_chunks) {
                     stop = true;
@@ -533,73 +594,51 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
             }
             if (p.mode == MODE_STREAM_ONLY) {  // diagnostics: the bare HBM -> smem pipeline
-                release_through(L);
+                release_through(j);
             } else {
-                if (L >= 1) {
-                    // ---- P1: this warp's share of the layer's solid bits: LDS, sign test, VOTE, STS ----
+                {
+                    // ---- P1: this warp's BPW ballot blocks of the slab: LDS, sign test, VOTE, STS ----
                     const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
-                    uint32_t* dst = sm.bits[bc & (C::BR - 1)] + warp;
+                    uint32_t* dst = sm.bits[sc & (C::BR - 1)] + warp;
 #pragma unroll
-                    for (int k = 0; k < (C::FULL + NW - 1) / NW; ++k) {
-                        if (k * NW + NW <= C::FULL || warp < C::FULL - k * NW) {
-                            const short d = src[64 * NW * k];
-                            const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                            if (lane == 0) dst[NW * k] = b;
-                        }
+                    for (int k = 0; k < C::BPW; ++k) {
+                        const short d = src[64 * NW * k];
+                        const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
+                        if (lane == 0) dst[NW * k] = b;
                     }
                     if (C::TAIL != 0 && warp == NW - 1) {
                         const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * C::FULL);
                         const short d = lane < C::TAIL ? tail[2 * lane] : short(1);
                         const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                        if (lane == 0) sm.bits[bc & (C::BR - 1)][C::FULL] = b;
+                        if (lane == 0) sm.bits[sc & (C::BR - 1)][C::FULL] = b;
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.bits_bar[bc & (C::BR - 1)]);
-                    ++bc;
+                    if (lane == 0) mbar_arrive(&sm.bits_bar[sc & (C::BR - 1)]);
                 }
-                if (p.mode == MODE_BITS_ONLY) { release_through(L); } else
-                if (L >= 2) {
-                    // ---- P2: one group of warps classifies cell layer z = L - 2 -------------------
-                    const int z = L - 2;
-                    if (p2_group == z % C::PG) {
-                        const uint32_t b1 = bc - 2, b2 = bc - 1;  // bits of sample layers z + 1, z + 2
-                        mbar_wait(&sm.bits_bar[b1 & (C::BR - 1)], (b1 / C::BR) & 1u);
-                        mbar_wait(&sm.bits_bar[b2 & (C::BR - 1)], (b2 / C::BR) & 1u);
-                        const int y = p2_sub * 32 + lane;
-                        const RowCorners rc = load_row_corners<C>(sm.bits[b1 & (C::BR - 1)], sm.bits[b2 & (C::BR - 1)], y);
-                        const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
-                        const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
-                        uint64_t act = any & ~all & ROWMASK;
-                        if (dirty != ~0ull) {
-                            const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
-                            uint64_t dirty_x = 0;
-#pragma unroll
-                            for (int mx = 0; mx < 4; ++mx)
-                                if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
-                            act &= dirty_x;
-                        }
-                        const uint32_t vi = zc0 + static_cast<uint32_t>(z);
-                        sm.active[vi & (C::VR - 1)][y] = act;
-                        const bool any_row = __any_sync(0xffffffffu, act != 0);
-                        if (lane == 0) {
-                            sm.verdict_flag[vi & (C::VR - 1)][p2_sub] = any_row ? 1u : 0u;
-                            mbar_arrive(&sm.verdict_bar[vi & (C::VR - 1)]);
-                        }
-                    }
+                if (p.mode == MODE_BITS_ONLY) {
+                    release_through(j);
+                } else {
+                    // P2 runs one slab behind P1 (its bits have been complete for a whole iteration, so
+                    // the duty group does not block) and the verdict is consumed one slab later still.
+                    if (j >= 2) classify_step(j - 1);
+                    if (j >= 3) handle_verdict(j - 2);
                 }
-                if (L >= 3 && p.mode != MODE_BITS_ONLY) handle_verdict(L - 3);
             }
-            if (++slot == R) {
+            ++sc;
+            if (++slot == RS) {
                 slot = 0;
                 ++round;
             }
         }
         if (stop) break;
         if (p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY) {
-            handle_verdict(E - 1);
+            // drain: the last step covers cell layers E-2, E-1 (one-sided gradient on the +z face)
+            classify_step(C::NSLAB - 1);
+            handle_verdict(C::NSLAB - 2);
+            handle_verdict(C::NSLAB - 1);
             if (pend_count != 0) flush();
-            release_through(S - 1);
-            zc += E;
+            release_through(C::NSLAB - 1);
+            stc += C::NSLAB - 1;
         }
 
         // ---- chunk epilogue: one counter record, no atomics --------------------------------
@@ -648,8 +687,8 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
     return cudaGetLastError();
 }
 
-using Cfg64 = Cfg<64, 4, 11, 16>;
-using Cfg32 = Cfg<32, 4, 16, 8>;
+using Cfg64 = Cfg<64, 1, 6, 16>;
+using Cfg32 = Cfg<32, 2, 10, 8>;
 
 // Tuning variants (HVX_REGULAR_VARIANT=<n>, default 0); all produce identical output.
 int variant_from_env() {
@@ -668,19 +707,18 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     const int variant = variant_from_env();
     if (edge == 64) {
         switch (variant) {
-            case 1: return launch_cfg<Cfg<64, 2, 11, 16>>(p, dev, stream);
-            case 2: return launch_cfg<Cfg<64, 4, 11, 8>>(p, dev, stream);
-            case 3: return launch_cfg<Cfg<64, 1, 11, 16>>(p, dev, stream);
-            case 4: return launch_cfg<Cfg<64, 4, 10, 16>>(p, dev, stream);
-            case 5: return launch_cfg<Cfg<64, 2, 8, 16>>(p, dev, stream);
+            case 1: return launch_cfg<Cfg<64, 2, 6, 16>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<64, 1, 5, 16>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<64, 1, 6, 8>>(p, dev, stream);
+            case 4: return launch_cfg<Cfg<64, 2, 6, 8>>(p, dev, stream);
             default: return launch_cfg<Cfg64>(p, dev, stream);
         }
     }
     if (edge == 32) {
         switch (variant) {
-            case 1: return launch_cfg<Cfg<32, 8, 20, 8>>(p, dev, stream);
-            case 2: return launch_cfg<Cfg<32, 4, 16, 4>>(p, dev, stream);
-            case 3: return launch_cfg<Cfg<32, 4, 12, 8>>(p, dev, stream);
+            case 1: return launch_cfg<Cfg<32, 1, 6, 8>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<32, 2, 8, 8>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<32, 2, 10, 4>>(p, dev, stream);
             default: return launch_cfg<Cfg32>(p, dev, stream);
         }
     }
