@@ -206,6 +206,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     p.mode = mode;
     if (const char* dbg = getenv("HVX_DEBUG_STREAM_ONLY"))  // diagnostics only: skip all compute
         if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY; else if (dbg[0] == '2') p.mode = MODE_BITS_ONLY;
+    if (const char* f = getenv("HVX_DEBUG_FLAGS")) p.debug_flags = static_cast<uint32_t>(atoi(f));
     p.max_vertices = ctx->cfg.max_vertices;
     p.max_indices = ctx->cfg.max_indices;
     p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);

@@ -23,6 +23,7 @@ struct RegularParams {
     const ChunkDesc* descs;   // [n] device
     uint32_t n_chunks;
     uint32_t mode;
+    uint32_t debug_flags;  // diagnostics: bit 0 disables the classification fast-reject
     uint32_t max_vertices, max_indices;  // per-chunk slot capacity
     hvx_vertex* vertices;                // [n][max_vertices]
     uint32_t* indices;                   // [n][max_indices]

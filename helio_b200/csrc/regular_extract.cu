@@ -57,22 +57,22 @@ struct Cfg {
     static constexpr int SLAB_BYTES = SLAB_WORDS * 4;
     static constexpr int FULL = SLAB_WORDS / 32;        // whole 32-sample ballot blocks per slab
     static constexpr int TAIL = SLAB_WORDS % 32;
-    static constexpr int BPW = FULL / NW_;              // ballot blocks per warp per slab
+    static constexpr int BPW = (FULL + NW_ - 1) / NW_;  // ballot blocks per warp per slab (last one guarded)
     static constexpr int BW = FULL + 1 + 3;             // bit words per slab + zero padding
     static constexpr int BR = EBS_ == 1 ? 4 : 8;        // slab-bits ring / verdict ring depth
     static constexpr int PWS = (G * E_) / 32;           // warps classifying one step (G cell layers)
-    static constexpr int PG = NW_ / PWS;                // classification groups
+    static constexpr int PG = NW_ / PWS;                // classification groups (left-over warps never classify)
     static constexpr int STEP_ROWS = G * E_;            // cell rows per step
     static constexpr int ROWS = EBS_ * STEP_ROWS;       // cell rows per emission batch
     static constexpr int CB = NT / 2;                   // active cells per emission sub-batch
     static constexpr int QW = E_ / 4;                   // microbrick edge == quarter-row width
     static constexpr int RPB = 256 / E_;                // rows per 256-cell scan block
-    static_assert(S % G == 0 && FULL % NW_ == 0, "slab must split evenly into ballot blocks per warp");
+    static_assert(S % G == 0, "chunk must split evenly into slabs");
     static_assert(RS_ >= EBS_ + 3 + 1, "ring must hold an emission window, the slab being classified and one in flight");
     static_assert(RS_ < NSLAB, "producer may be at most one chunk ahead");
     static_assert(EBS_ + 3 <= BR, "bit / verdict rings too small");
     static_assert(SLAB_BYTES % 16 == 0, "cp.async.bulk needs 16-byte multiples");
-    static_assert(ROWS <= NT && NW_ % PWS == 0 && (E_ == 32 || E_ == 64), "unsupported tiling");
+    static_assert(ROWS <= NT && NW_ >= PWS && (E_ == 32 || E_ == 64), "unsupported tiling");
 };
 
 template <class C>
@@ -602,9 +602,11 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                     uint32_t* dst = sm.bits[sc & (C::BR - 1)] + warp;
 #pragma unroll
                     for (int k = 0; k < C::BPW; ++k) {
-                        const short d = src[64 * NW * k];
-                        const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                        if (lane == 0) dst[NW * k] = b;
+                        if (k * NW + NW <= C::FULL || warp < C::FULL - k * NW) {
+                            const short d = src[64 * NW * k];
+                            const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
+                            if (lane == 0) dst[NW * k] = b;
+                        }
                     }
                     if (C::TAIL != 0 && warp == NW - 1) {
                         const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * C::FULL);
@@ -708,8 +710,8 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     if (edge == 64) {
         switch (variant) {
             case 1: return launch_cfg<Cfg<64, 2, 6, 16>>(p, dev, stream);
-            case 2: return launch_cfg<Cfg<64, 1, 5, 16>>(p, dev, stream);
-            case 3: return launch_cfg<Cfg<64, 1, 6, 8>>(p, dev, stream);
+            case 2: return launch_cfg<Cfg<64, 1, 6, 15>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<64, 1, 6, 11>>(p, dev, stream);
             case 4: return launch_cfg<Cfg<64, 2, 6, 8>>(p, dev, stream);
             default: return launch_cfg<Cfg64>(p, dev, stream);
         }
