@@ -1,0 +1,55 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep capture (ncu -i ... --page raw/source --csv) into a small text file for profiles/."""
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "dram__bytes.sum.per_second", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "lts__t_sector_hit_rate.pct",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    lines = [f"# ncu --set full summary of {rep}", f"kernel: {vals[hdr.index('Kernel Name')]}", ""]
+    for i, h in enumerate(hdr):
+        if h in KEYS:
+            lines.append(f"{h:75s} {vals[i]:>18s} {units[i]}")
+    lines.append("")
+    lines.append("warp stall reasons (average warps stalled per issue-active cycle):")
+    for i, h in enumerate(hdr):
+        if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and float(vals[i] or 0) >= 0.1:
+            lines.append(f"  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''):28s} {float(vals[i]):6.2f}")
+    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(src.splitlines()))
+    hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
+    hdr2, data = rows[hi], rows[hi + 1:]
+    iex, ismp = hdr2.index("Instructions Executed"), hdr2.index("Warp Stall Sampling (All Samples)")
+
+    def f(x):
+        try:
+            return float(x)
+        except ValueError:
+            return 0.0
+    cand = [r for r in data if len(r) > iex and r[0].strip().isdigit()]
+    cand.sort(key=lambda r: -f(r[ismp]))
+    lines.append("")
+    lines.append("hottest CUDA source lines (line | executed warp instructions | stall samples):")
+    for r in cand[:25]:
+        lines.append(f"  {r[0].strip():>5s} | {int(f(r[iex])):>11d} | {int(f(r[ismp])):>6d} | {r[1].strip()[:100]}")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:30]))
+
+
+if __name__ == "__main__":
+    main()
