@@ -1,0 +1,177 @@
+// helio_voxel_cuda.hpp -- header-only C++ mirror of the reference's extractor objects, over the
+// C ABI in hvx.h.  Same names, argument order and error behaviour as
+//   TransvoxelGpuExtractorConfig / TransvoxelGpuExtractor      PV/src/transvoxel_emit.rs:57-396
+//   TransvoxelGpuClassifier                                    PV/src/transvoxel_gpu.rs:148-356
+//   TransvoxelGpuTransitionExtractor(+Config)                  PV/src/transvoxel_transition_gpu.rs:148-520
+// (PV = crates/passes/3d/helio-pass-planetary-voxel in the reference tree).  Where the Rust takes
+// (&wgpu::Device, &wgpu::Queue) these take a CUDA device ordinal at construction; Result<_, enum>
+// becomes an exception carrying the hvx_status.  No CUDA headers are needed to use this file.
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hvx.h"
+
+namespace helio_voxel_cuda {
+
+constexpr uint32_t PAGE_EDGE = 32;  // helio-planet-voxel-core/src/types.rs:6
+
+/// TransvoxelGpuError / TransvoxelTransitionGpuError (PV/src/transvoxel_gpu.rs:445-459,
+/// PV/src/transvoxel_transition_gpu.rs:712-732) plus the ABI's own failures.
+class Error : public std::runtime_error {
+   public:
+    Error(int status, const std::string& what) : std::runtime_error(what), status_(status) {}
+    int status() const { return status_; }
+    bool is_sample_count() const { return status_ == HVX_E_SAMPLE_COUNT; }
+    bool is_invalid_extraction_capacity() const { return status_ == HVX_E_INVALID_CAPACITY; }
+    bool is_device_limit() const { return status_ == HVX_E_DEVICE_LIMIT; }
+    bool is_transition_mask() const { return status_ == HVX_E_TRANSITION_MASK; }
+
+   private:
+    int status_;
+};
+
+/// PV/src/transvoxel_emit.rs:57-85
+struct TransvoxelGpuExtractorConfig {
+    uint32_t max_vertices = 393216;
+    uint32_t max_indices = 491520;
+    static TransvoxelGpuExtractorConfig create(uint32_t max_vertices, uint32_t max_indices) {
+        if (max_vertices == 0 || max_indices == 0)
+            throw Error(HVX_E_INVALID_CAPACITY, "Transvoxel extraction capacities must be nonzero");
+        return {max_vertices, max_indices};
+    }
+};
+
+/// PV/src/transvoxel_transition_gpu.rs:148-181
+struct TransvoxelGpuTransitionExtractorConfig {
+    uint32_t max_vertices = 73728;
+    uint32_t max_indices = 221184;
+    static TransvoxelGpuTransitionExtractorConfig create(uint32_t max_vertices, uint32_t max_indices) {
+        if (max_vertices == 0 || max_indices == 0)
+            throw Error(HVX_E_INVALID_CAPACITY, "Transvoxel transition capacities must be nonzero");
+        return {max_vertices, max_indices};
+    }
+};
+
+struct ResourceStats {
+    uint32_t buffers;
+    uint64_t allocated_bytes;
+};
+
+namespace detail {
+class Ctx {
+   public:
+    Ctx(int device, const hvx_config& cfg) {
+        const int rc = hvx_create(&ctx_, device, &cfg);
+        if (rc != HVX_OK) throw Error(rc, hvx_last_error(nullptr));
+    }
+    ~Ctx() { hvx_destroy(ctx_); }
+    Ctx(const Ctx&) = delete;
+    Ctx& operator=(const Ctx&) = delete;
+    hvx_ctx* get() const { return ctx_; }
+    void check(int rc) const {
+        if (rc != HVX_OK) throw Error(rc, hvx_last_error(ctx_));
+    }
+    template <typename T>
+    std::vector<T> read(int buffer, uint64_t first, uint64_t count) const {
+        std::vector<T> out(count);
+        check(hvx_read(ctx_, buffer, first * sizeof(T), count * sizeof(T), out.data()));
+        return out;
+    }
+    ResourceStats stats() const {
+        uint32_t n = 0;
+        for (int b = 0; b < HVX_BUF_COUNT; ++b) n += hvx_buffer_bytes(ctx_, b) != 0;
+        return {n, hvx_allocated_bytes(ctx_)};
+    }
+
+   private:
+    hvx_ctx* ctx_ = nullptr;
+};
+inline hvx_chunk_desc desc(uint64_t generation, uint64_t dirty, uint32_t mask) { return {generation, dirty, mask, 0}; }
+}  // namespace detail
+
+/// One page per dispatch, like the reference (PV/src/transvoxel_emit.rs:92-396).
+class TransvoxelGpuExtractor {
+   public:
+    explicit TransvoxelGpuExtractor(int device, TransvoxelGpuExtractorConfig config = {}, uint32_t edge = PAGE_EDGE,
+                                    bool debug_records = true)
+        : config_(TransvoxelGpuExtractorConfig::create(config.max_vertices, config.max_indices)),
+          ctx_(device, hvx_config{edge, 1, config.max_vertices, config.max_indices, 0, 0,
+                                  debug_records ? HVX_CFG_DEBUG_RECORDS : 0u, 0}),
+          cells_(uint64_t(edge) * edge * edge) {}
+
+    /// dispatch(samples, generation, dirty_microbricks, transition_mask)  -- transvoxel_emit.rs:233-254
+    void dispatch(const uint32_t* samples, size_t sample_count, uint64_t generation, uint64_t dirty_microbricks,
+                  uint8_t transition_mask) {
+        const hvx_chunk_desc d = detail::desc(generation, dirty_microbricks, transition_mask);
+        ctx_.check(hvx_extract_regular(ctx_.get(), samples, sample_count, &d, 1));
+    }
+    hvx_emission_counters counters_buffer() const { return ctx_.read<hvx_emission_counters>(HVX_BUF_REGULAR_COUNTERS, 0, 1)[0]; }
+    std::vector<hvx_vertex> vertices_buffer(uint64_t count) const { return ctx_.read<hvx_vertex>(HVX_BUF_REGULAR_VERTICES, 0, count); }
+    std::vector<uint32_t> indices_buffer(uint64_t count) const { return ctx_.read<uint32_t>(HVX_BUF_REGULAR_INDICES, 0, count); }
+    std::vector<hvx_cell_offset> offsets_buffer() const { return ctx_.read<hvx_cell_offset>(HVX_BUF_REGULAR_OFFSETS, 0, cells_); }
+    std::vector<hvx_scan_block> blocks_buffer() const { return ctx_.read<hvx_scan_block>(HVX_BUF_REGULAR_BLOCKS, 0, cells_ / 256); }
+    /// device pointers for zero-copy consumers (the arenas are overwritten by the next dispatch)
+    const hvx_vertex* device_vertices() const { return static_cast<const hvx_vertex*>(hvx_buffer(ctx_.get(), HVX_BUF_REGULAR_VERTICES)); }
+    const uint32_t* device_indices() const { return static_cast<const uint32_t*>(hvx_buffer(ctx_.get(), HVX_BUF_REGULAR_INDICES)); }
+    TransvoxelGpuExtractorConfig config() const { return config_; }
+    ResourceStats resource_stats() const { return ctx_.stats(); }
+    void resize(uint32_t, uint32_t) {}  // extraction owns no surface-size-dependent resources
+
+   private:
+    TransvoxelGpuExtractorConfig config_;
+    detail::Ctx ctx_;
+    uint64_t cells_;
+};
+
+/// PV/src/transvoxel_gpu.rs:148-356
+class TransvoxelGpuClassifier {
+   public:
+    explicit TransvoxelGpuClassifier(int device, uint32_t edge = PAGE_EDGE)
+        : ctx_(device, hvx_config{edge, 1, 393216, 491520, 0, 0, HVX_CFG_DEBUG_RECORDS, 0}), cells_(uint64_t(edge) * edge * edge) {}
+    void dispatch(const uint32_t* samples, size_t sample_count, uint64_t generation, uint64_t dirty_microbricks) {
+        const hvx_chunk_desc d = detail::desc(generation, dirty_microbricks, 0);
+        ctx_.check(hvx_classify_regular(ctx_.get(), samples, sample_count, &d, 1));
+    }
+    std::vector<hvx_cell_record> output_buffer() const { return ctx_.read<hvx_cell_record>(HVX_BUF_REGULAR_CELLS, 0, cells_); }
+    hvx_classify_counters counters_buffer() const { return ctx_.read<hvx_classify_counters>(HVX_BUF_REGULAR_CLASSIFY, 0, 1)[0]; }
+    ResourceStats resource_stats() const { return ctx_.stats(); }
+    void resize(uint32_t, uint32_t) {}
+
+   private:
+    detail::Ctx ctx_;
+    uint64_t cells_;
+};
+
+/// PV/src/transvoxel_transition_gpu.rs:190-520
+class TransvoxelGpuTransitionExtractor {
+   public:
+    explicit TransvoxelGpuTransitionExtractor(int device, TransvoxelGpuTransitionExtractorConfig config = {},
+                                              uint32_t edge = PAGE_EDGE, bool debug_records = true)
+        : config_(TransvoxelGpuTransitionExtractorConfig::create(config.max_vertices, config.max_indices)),
+          ctx_(device, hvx_config{edge, 1, 1, 1, config.max_vertices, config.max_indices,
+                                  debug_records ? HVX_CFG_DEBUG_RECORDS : 0u, 0}),
+          cells_(6ull * edge * edge) {}
+    /// dispatch(face_slabs, transition_mask, generation)  -- transvoxel_transition_gpu.rs:366-380
+    void dispatch(const uint32_t* face_slabs, size_t sample_count, uint8_t transition_mask, uint64_t generation) {
+        const hvx_chunk_desc d = detail::desc(generation, ~0ull, transition_mask);
+        ctx_.check(hvx_extract_transition(ctx_.get(), face_slabs, sample_count, &d, 1));
+    }
+    hvx_transition_counters counters_buffer() const { return ctx_.read<hvx_transition_counters>(HVX_BUF_TRANSITION_COUNTERS, 0, 1)[0]; }
+    std::vector<hvx_vertex> vertices_buffer(uint64_t count) const { return ctx_.read<hvx_vertex>(HVX_BUF_TRANSITION_VERTICES, 0, count); }
+    std::vector<uint32_t> indices_buffer(uint64_t count) const { return ctx_.read<uint32_t>(HVX_BUF_TRANSITION_INDICES, 0, count); }
+    std::vector<hvx_cell_record> cells_buffer() const { return ctx_.read<hvx_cell_record>(HVX_BUF_TRANSITION_CELLS, 0, cells_); }
+    TransvoxelGpuTransitionExtractorConfig config() const { return config_; }
+    ResourceStats resource_stats() const { return ctx_.stats(); }
+    void resize(uint32_t, uint32_t) {}
+
+   private:
+    TransvoxelGpuTransitionExtractorConfig config_;
+    detail::Ctx ctx_;
+    uint64_t cells_;
+};
+
+}  // namespace helio_voxel_cuda

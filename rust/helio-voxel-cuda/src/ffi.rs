@@ -1,0 +1,71 @@
+//! Raw `extern "C"` declarations: a line-for-line image of include/hvx.h.
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct hvx_ctx { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct hvx_config {
+    pub edge: u32,
+    pub max_chunks: u32,
+    pub max_vertices: u32,
+    pub max_indices: u32,
+    pub max_transition_vertices: u32,
+    pub max_transition_indices: u32,
+    pub flags: u32,
+    pub _reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct hvx_chunk_desc {
+    pub generation: u64,
+    pub dirty_microbricks: u64,
+    pub transition_mask: u32,
+    pub _pad: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_range { pub first_vertex: u32, pub vertex_count: u32, pub first_index: u32, pub index_count: u32 }
+
+pub const HVX_OK: c_int = 0;
+pub const HVX_E_SAMPLE_COUNT: c_int = -1;
+pub const HVX_E_INVALID_CAPACITY: c_int = -2;
+pub const HVX_E_DEVICE_LIMIT: c_int = -3;
+pub const HVX_E_TRANSITION_MASK: c_int = -4;
+pub const HVX_CFG_DEBUG_RECORDS: u32 = 1;
+
+pub const HVX_BUF_REGULAR_VERTICES: c_int = 2;
+pub const HVX_BUF_REGULAR_INDICES: c_int = 3;
+pub const HVX_BUF_REGULAR_COUNTERS: c_int = 4;
+pub const HVX_BUF_REGULAR_CLASSIFY: c_int = 5;
+pub const HVX_BUF_REGULAR_RANGES: c_int = 6;
+pub const HVX_BUF_REGULAR_CELLS: c_int = 7;
+pub const HVX_BUF_REGULAR_OFFSETS: c_int = 8;
+pub const HVX_BUF_REGULAR_BLOCKS: c_int = 9;
+pub const HVX_BUF_TRANSITION_VERTICES: c_int = 10;
+pub const HVX_BUF_TRANSITION_INDICES: c_int = 11;
+pub const HVX_BUF_TRANSITION_COUNTERS: c_int = 12;
+pub const HVX_BUF_TRANSITION_CELLS: c_int = 14;
+
+extern "C" {
+    pub fn hvx_create(out: *mut *mut hvx_ctx, device: c_int, config: *const hvx_config) -> c_int;
+    pub fn hvx_destroy(ctx: *mut hvx_ctx);
+    pub fn hvx_last_error(ctx: *const hvx_ctx) -> *const c_char;
+    pub fn hvx_allocated_bytes(ctx: *const hvx_ctx) -> u64;
+    pub fn hvx_synchronize(ctx: *mut hvx_ctx) -> c_int;
+    pub fn hvx_fill_density(ctx: *mut hvx_ctx, kind: u32, page_xyz: *const i64, lod: *const u8, n: u32, d_samples: *mut u32) -> c_int;
+    pub fn hvx_fill_slabs(ctx: *mut hvx_ctx, kind: u32, page_xyz: *const i64, lod: *const u8, n: u32, d_slabs: *mut u32) -> c_int;
+    pub fn hvx_extract_regular(ctx: *mut hvx_ctx, samples: *const u32, sample_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
+    pub fn hvx_classify_regular(ctx: *mut hvx_ctx, samples: *const u32, sample_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
+    pub fn hvx_extract_transition(ctx: *mut hvx_ctx, slabs: *const u32, slab_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
+    pub fn hvx_buffer(ctx: *mut hvx_ctx, buffer_id: c_int) -> *mut c_void;
+    pub fn hvx_buffer_bytes(ctx: *mut hvx_ctx, buffer_id: c_int) -> u64;
+    pub fn hvx_read(ctx: *mut hvx_ctx, buffer_id: c_int, byte_offset: u64, bytes: u64, host_dst: *mut c_void) -> c_int;
+    pub fn hvx_read_meshes(ctx: *mut hvx_ctx, kind: c_int, first: u32, n: u32, vertices_out: *mut c_void, vertex_cap: u64,
+                           indices_out: *mut u32, index_cap: u64, ranges_out: *mut hvx_range,
+                           total_vertices: *mut u64, total_indices: *mut u64) -> c_int;
+}

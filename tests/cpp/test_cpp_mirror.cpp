@@ -1,0 +1,54 @@
+// GPU check of the header-only C++ mirror (include/helio_voxel_cuda.hpp): the reference's sphere
+// fixture must give 1,323 vertices / 661 triangles (docs/planetary_voxel_extraction_benchmark.md:61),
+// the error enum must map like the Rust one.  Built and run by tests/test_gpu_cpp_mirror.py.
+#include <cstdio>
+#include <vector>
+
+#include "helio_voxel_cuda.hpp"
+
+using namespace helio_voxel_cuda;
+
+static uint32_t cellword(int density, uint32_t material) { return (uint32_t(density) & 0xffffu) | (material << 16); }
+
+int main() {
+    std::vector<uint32_t> samples(34 * 34 * 34);
+    size_t i = 0;
+    for (int z = -1; z <= 32; ++z)
+        for (int y = -1; y <= 32; ++y)
+            for (int x = -1; x <= 32; ++x) {
+                long d = long(x) * x + long(y) * y + long(z) * z - 144;  // ExtractionFixtureKind::Sphere
+                d = d < -32768 ? -32768 : d > 32767 ? 32767 : d;
+                samples[i++] = cellword(int(d), d <= 0 ? 1u : 0u);
+            }
+    TransvoxelGpuExtractor extractor(0);
+    extractor.dispatch(samples.data(), samples.size(), 1000, ~0ull, 0);
+    const hvx_emission_counters c = extractor.counters_buffer();
+    if (c.completed != 1 || c.emitted_vertices != 1323 || c.emitted_indices != 661 * 3) {
+        std::printf("FAIL counters %u %u %u\n", c.completed, c.emitted_vertices, c.emitted_indices);
+        return 1;
+    }
+    const auto v = extractor.vertices_buffer(c.emitted_vertices);
+    if (v[0].position[0] != 12.0f || v[0].normal[0] != 1.0f || v[0].material != 1) {
+        std::printf("FAIL first vertex\n");
+        return 1;
+    }
+    try {
+        extractor.dispatch(samples.data(), samples.size() - 1, 1, ~0ull, 0);
+        std::printf("FAIL no SampleCount error\n");
+        return 1;
+    } catch (const Error& e) {
+        if (!e.is_sample_count()) return 1;
+    }
+    try {
+        TransvoxelGpuExtractorConfig::create(0, 1);
+        return 1;
+    } catch (const Error& e) {
+        if (!e.is_invalid_extraction_capacity()) return 1;
+    }
+    TransvoxelGpuExtractor tiny(0, TransvoxelGpuExtractorConfig::create(1, 1));
+    tiny.dispatch(samples.data(), samples.size(), 2000, ~0ull, 0);
+    const hvx_emission_counters t = tiny.counters_buffer();
+    if (!(t.completed == 1 && t.vertex_overflow && t.index_overflow && t.emitted_vertices == 0 && t.required_vertices == 1323)) return 1;
+    std::printf("OK cpp mirror: 1323 vertices / 661 triangles, errors and overflow contract as the reference\n");
+    return 0;
+}
