@@ -59,20 +59,20 @@ struct Cfg {
     static constexpr int TAIL = SLAB_WORDS % 32;
     static constexpr int BPW = (FULL + NW_ - 1) / NW_;  // ballot blocks per warp per slab (last one guarded)
     static constexpr int BW = FULL + 1 + 3;             // bit words per slab + zero padding
-    static constexpr int BR = EBS_ == 1 ? 4 : 8;        // slab-bits ring / verdict ring depth
+    static constexpr int BR = 4;                        // slab-bits / verdict / active-mask ring depth
     static constexpr int PWS = (G * E_) / 32;           // warps classifying one step (G cell layers)
     static constexpr int PG = NW_ / PWS;                // classification groups (left-over warps never classify)
     static constexpr int STEP_ROWS = G * E_;            // cell rows per step
     static constexpr int ROWS = EBS_ * STEP_ROWS;       // cell rows per emission batch
-    static constexpr int CB = NT / 2;                   // active cells per emission sub-batch
+    static constexpr int CB = NT < 512 ? NT : 512;      // active cells per emission sub-batch (one thread per cell)
     static constexpr int QW = E_ / 4;                   // microbrick edge == quarter-row width
     static constexpr int RPB = 256 / E_;                // rows per 256-cell scan block
     static_assert(S % G == 0, "chunk must split evenly into slabs");
     static_assert(RS_ >= EBS_ + 3 + 1, "ring must hold an emission window, the slab being classified and one in flight");
     static_assert(RS_ < NSLAB, "producer may be at most one chunk ahead");
-    static_assert(EBS_ + 3 <= BR, "bit / verdict rings too small");
+    static_assert(EBS_ + 2 <= BR && EBS_ <= 2, "bit / verdict rings too small");
     static_assert(SLAB_BYTES % 16 == 0, "cp.async.bulk needs 16-byte multiples");
-    static_assert(ROWS <= NT && NW_ >= PWS && (E_ == 32 || E_ == 64), "unsupported tiling");
+    static_assert(ROWS * 2 <= NT && ROWS <= 256 && NW_ >= PWS && (E_ == 32 || E_ == 64), "unsupported tiling");
 };
 
 template <class C>
@@ -83,16 +83,13 @@ struct Smem {
     uint64_t bits_bar[C::BR];
     uint64_t verdict_bar[C::BR];
     uint64_t active[C::BR][C::STEP_ROWS];  // active-cell bits per cell row of a step
-    union {
-        uint16_t owner[C::CB * 12];        // emission: vertex -> cell slot | k<<10
-        uint64_t row_pref64[C::ROWS + 1];  // debug records: per-row exclusive (vertices | indices<<32)
-    };
+    uint64_t row_pref[C::ROWS + 1];        // debug records: per-row exclusive (cells | vertices<<16 | indices<<40)
     uint64_t scan64[2][34];
     uint32_t scan32[2][34];
-    uint32_t bits[C::BR][C::BW];    // solid bit of every sample of a slab, flat x-fastest order
+    uint32_t bits[C::BR][C::BW];           // solid bit of every sample of a slab, flat x-fastest order
     uint32_t verdict_flag[C::BR][C::PWS];
-    uint32_t row_off[C::ROWS + 1];  // exclusive prefix of popc(active)
-    uint32_t cell_rec[C::CB];       // x | row<<8 | case<<16
+    uint32_t cell_rec[C::CB];              // emission sub-batch: x | row<<8 | case<<16
+    uint16_t cell_vo[C::CB];               // sub-batch-relative first vertex of each cell
     uint32_t chunk_ids[4];
     uint16_t case_info[256];
     uint8_t vertex_edge[256 * 12];
@@ -359,77 +356,72 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 ++released;
             }
         };
-        // bit array + bit offset of sample layer `idx` of this chunk
-        auto bits_of = [&](int idx, int& base) -> const uint32_t* {
-            base = (idx & 1) * LW;
-            return sm.bits[(sc0 + static_cast<uint32_t>(idx >> 1)) & (C::BR - 1)];
-        };
-        auto active_of = [&](int step) -> uint64_t* {  // step >= 1
-            return sm.active[(stc0 + static_cast<uint32_t>(step - 1)) & (C::BR - 1)];
-        };
-
         // ---- collective emission of steps [pend_first, pend_first + pend_count) -----------------
         auto flush = [&]() {
             const int z0 = 2 * pend_first - 2;             // first cell layer of the batch (even)
             const int rows = pend_count * C::STEP_ROWS;    // row r: cell layer z0 + r / E, y = r % E
-            const int nrw = rows / 32;                     // warps holding row threads
             // sample layer z0 + d lives in slab (released + d/2) -> ring slot rel_slot + d/2
             auto layer_words = [&](int d) -> int {
                 int s2 = rel_slot + (d >> 1);
                 if (s2 >= RS) s2 -= RS;
                 return s2 * C::SLAB_WORDS + (d & 1) * LW;
             };
-            auto active_row = [&](int r) -> uint64_t {
-                return active_of(pend_first + r / C::STEP_ROWS)[r % C::STEP_ROWS];
+            // Transvoxel case of one cell straight from the bricks: bit i = corner (i&1, i>>1&1, i>>2&1)
+            auto case_of = [&](int x, int y, int zl) -> uint32_t {
+                const uint32_t* l0 = ring_flat + layer_words(zl + 1) + (y + 1) * S + (x + 1);
+                const uint32_t* l1 = ring_flat + layer_words(zl + 2) + (y + 1) * S + (x + 1);
+                return (cw_solid(l0[0]) ? 1u : 0u) | (cw_solid(l0[1]) ? 2u : 0u) | (cw_solid(l0[S]) ? 4u : 0u) |
+                       (cw_solid(l0[S + 1]) ? 8u : 0u) | (cw_solid(l1[0]) ? 16u : 0u) | (cw_solid(l1[1]) ? 32u : 0u) |
+                       (cw_solid(l1[S]) ? 64u : 0u) | (cw_solid(l1[S + 1]) ? 128u : 0u);
             };
-            uint32_t my_count = 0;
-            if (tid < rows) my_count = __popcll(active_row(tid));
+            auto active_row = [&](int r) -> uint64_t {
+                return sm.active[(stc0 + static_cast<uint32_t>(pend_first - 1 + r / C::STEP_ROWS)) & (C::BR - 1)][r % C::STEP_ROWS];
+            };
+            // ---- A: ranks.  Each thread owns two adjacent quarter rows (QW cells each); one scan over
+            //      their popcounts gives every quarter its first rank in x-fastest cell order. ----------
+            const int q0 = 2 * tid;                        // quarter rows q0, q0 + 1 of row q0 >> 2
+            uint32_t sub0 = 0, sub1 = 0;
+            if (q0 < rows * 4) {
+                const uint64_t m = active_row(q0 >> 2);
+                const int part = q0 & 3;                   // 0 or 2
+                sub0 = static_cast<uint32_t>((m >> (C::QW * part)) & ((1ull << C::QW) - 1ull));
+                sub1 = static_cast<uint32_t>((m >> (C::QW * (part + 1))) & ((1ull << C::QW) - 1ull));
+            }
+            const uint32_t c0 = __popc(sub0), c1 = __popc(sub1);
             uint32_t n_active;
-            const uint32_t my_off = scan_front_warps<NT>(my_count, nrw, sm.scan32, flip32, n_active);
-            if (tid < rows) sm.row_off[tid] = my_off;
+            const uint32_t excl = scan_front_warps<NT>(c0 + c1, (rows * 2 + 31) / 32, sm.scan32, flip32, n_active);
 
             if (debug) {
                 // ---- debug records: per-cell case words, block-relative offsets, scan blocks ----
-                // (GpuTransvoxelCell / GpuTransvoxelCellOffset / GpuTransvoxelScanBlock)
-                uint64_t row_tot = 0;
-                RowCorners rc;
-                uint64_t dirty_x = 0;
-                int y = 0, z = 0;
+                // (GpuTransvoxelCell / GpuTransvoxelCellOffset / GpuTransvoxelScanBlock); one thread per row
+                uint64_t row_tot = 0, dirty_x = 0;
+                const int my_zl = tid / E, my_y = tid % E, z = z0 + my_zl;
                 if (tid < rows) {
-                    y = tid % E;
-                    z = z0 + tid / E;
-                    int b0, b1;
-                    const uint32_t* p0 = bits_of(z + 1, b0);
-                    const uint32_t* p1 = bits_of(z + 2, b1);
-                    rc = load_row_corners<C>(p0, b0, p1, b1, y);
-                    const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
+                    const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((my_y / C::QW) + 4 * (z / C::QW)))) & 15u;
                     for (int mx = 0; mx < 4; ++mx)
                         if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
-                    uint64_t act = active_row(tid);
-                    while (act) {
-                        const int x = __ffsll(static_cast<long long>(act)) - 1;
-                        act &= act - 1;
-                        const uint32_t info = sm.case_info[case_at(rc, x)];
+                    for (uint64_t m = active_row(tid); m != 0; m &= m - 1) {
+                        const uint32_t info = sm.case_info[case_of(__ffsll(static_cast<long long>(m)) - 1, my_y, my_zl)];
                         row_tot += (info & 15u) | (static_cast<uint64_t>(3u * ((info >> 4) & 15u)) << 32);
                     }
                 }
                 uint64_t step_tot;
-                const uint64_t row_pref = scan_front_warps<NT>(row_tot, nrw, sm.scan64, flip64, step_tot);
-                if (tid < rows) sm.row_pref64[tid] = row_pref;
-                if (tid == 0) sm.row_pref64[rows] = step_tot;
+                const uint64_t row_pref = scan_front_warps<NT>(row_tot, rows / 32, sm.scan64, flip64, step_tot);
+                if (tid < rows) sm.row_pref[tid] = row_pref;
+                if (tid == 0) sm.row_pref[rows] = step_tot;
                 consumer_sync<NT>();
                 if (tid < rows) {
                     const int block_row = (tid / C::RPB) * C::RPB;  // first row of this cell's 256-block
-                    const uint64_t bp = sm.row_pref64[block_row];
+                    const uint64_t bp = sm.row_pref[block_row];
                     uint32_t rv = static_cast<uint32_t>(row_pref) - static_cast<uint32_t>(bp);
                     uint32_t ri = static_cast<uint32_t>(row_pref >> 32) - static_cast<uint32_t>(bp >> 32);
                     const size_t cell0 = static_cast<size_t>(chunk) * E * E * E + static_cast<size_t>(z) * E * E +
-                                         static_cast<size_t>(y) * E;
+                                         static_cast<size_t>(my_y) * E;
                     const uint32_t glo = static_cast<uint32_t>(desc.generation);
                     const uint32_t ghi = static_cast<uint32_t>(desc.generation >> 32);
                     for (int x = 0; x < E; ++x) {
                         if (!((dirty_x >> x) & 1ull)) continue;
-                        const uint32_t c = case_at(rc, x);
+                        const uint32_t c = case_of(x, my_y, my_zl);
                         const uint32_t info = sm.case_info[c];
                         const uint32_t nv = info & 15u, nt = (info >> 4) & 15u, cls = info >> 8;
                         uint4 rec = make_uint4(c | (cls << 8) | (nv << 16) | (nt << 24) | 0x80000000u, glo, ghi, 0u);
@@ -440,14 +432,14 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                         ri += 3u * nt;
                     }
                     if (tid % C::RPB == 0) {
-                        const uint64_t nx = sm.row_pref64[block_row + C::RPB];
+                        const uint64_t nx = sm.row_pref[block_row + C::RPB];
                         hvx_scan_block blk;
                         blk.vertex_count = static_cast<uint32_t>(nx) - static_cast<uint32_t>(bp);
                         blk.index_count = static_cast<uint32_t>(nx >> 32) - static_cast<uint32_t>(bp >> 32);
                         blk.first_vertex = v_base + static_cast<uint32_t>(bp);
                         blk.first_index = i_base + static_cast<uint32_t>(bp >> 32);
                         const size_t b = static_cast<size_t>(chunk) * (E * E * E / 256) +
-                                         (static_cast<size_t>(z) * E * E + static_cast<size_t>(y) * E) / 256;
+                                         (static_cast<size_t>(z) * E * E + static_cast<size_t>(my_y) * E) / 256;
                         p.blocks[b] = blk;
                     }
                 }
@@ -456,33 +448,24 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
             active_cells += n_active;
             for (uint32_t b0 = 0; b0 < n_active; b0 += C::CB) {
                 const uint32_t nb = min(static_cast<uint32_t>(C::CB), n_active - b0);
-                consumer_sync<NT>();  // row_off / previous sub-batch's cell_rec, owner are free
-                // P3a: rank scatter, one thread per quarter row
-                for (int q = tid; q < rows * 4; q += NT) {
-                    const int r = q >> 2, part = q & 3;
-                    const uint64_t m = active_row(r);
-                    uint32_t sub = static_cast<uint32_t>((m >> (C::QW * part)) & ((1ull << C::QW) - 1ull));
-                    if (!sub) continue;
-                    uint32_t rank = sm.row_off[r] + __popcll(m & ((1ull << (C::QW * part)) - 1ull));
-                    while (sub) {
-                        const int bit = __ffs(sub) - 1;
-                        sub &= sub - 1;
-                        const uint32_t rel = rank - b0;  // wraps for rank < b0
-                        if (rel < nb) sm.cell_rec[rel] = static_cast<uint32_t>(C::QW * part + bit) | (r << 8);
-                        ++rank;
-                    }
+                if (b0 != 0) consumer_sync<NT>();  // the previous sub-batch's records are consumed
+                // ---- B: ordered compaction: scatter (x, row) of the cells whose rank is in this sub-batch
+                {
+                    uint32_t rank = excl;
+                    const int r = q0 >> 2, xbase = C::QW * (q0 & 3);
+                    for (uint32_t s = sub0; s != 0; s &= s - 1, ++rank)
+                        if (rank - b0 < nb) sm.cell_rec[rank - b0] = static_cast<uint32_t>(xbase + __ffs(s) - 1) | (r << 8);
+                    rank = excl + c0;
+                    for (uint32_t s = sub1; s != 0; s &= s - 1, ++rank)
+                        if (rank - b0 < nb) sm.cell_rec[rank - b0] = static_cast<uint32_t>(xbase + C::QW + __ffs(s) - 1) | (r << 8);
                 }
                 consumer_sync<NT>();
-                // P3b: case lookup, per-cell counts, ordered offsets, index emission
+                // ---- C: one thread per active cell: case, counts, ordered offsets, indices -----------
                 uint32_t packed = 0, rec = 0, info = 0;
                 if (tid < nb) {
                     rec = sm.cell_rec[tid];
-                    const int x = rec & 63, r = rec >> 8, z = z0 + r / E, y = r % E;
-                    int bb0, bb1;
-                    const uint32_t* p0 = bits_of(z + 1, bb0);
-                    const uint32_t* p1 = bits_of(z + 2, bb1);
-                    const RowCorners rc = load_row_corners<C>(p0, bb0, p1, bb1, y);
-                    const uint32_t c = case_at(rc, x);
+                    const int x = rec & 63, r = rec >> 8;
+                    const uint32_t c = case_of(x, r % E, r / E);
                     info = sm.case_info[c];
                     rec |= c << 16;
                     packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
@@ -490,24 +473,31 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 uint32_t batch_tot;
                 const uint32_t off = scan_front_warps<NT>(packed, static_cast<int>((nb + 31u) / 32u), sm.scan32, flip32, batch_tot);
                 const uint32_t batch_v = batch_tot & 0xffffu, batch_i = batch_tot >> 16;
-                if (tid < nb && do_emit) {
-                    const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
+                if (tid < nb) {
                     const uint32_t vo = off & 0xffffu, io = off >> 16;
                     sm.cell_rec[tid] = rec;
-                    for (uint32_t k = 0; k < nv; ++k) sm.owner[vo + k] = static_cast<uint16_t>(tid | (k << 10));
-                    const uint32_t first_vertex = v_base + vo;
-                    const uint32_t dst = i_base + io;
-                    const uint8_t* tri = &sm.class_index[cls * 16];
-                    for (uint32_t j = 0; j < ni; ++j)
-                        if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + tri[j];
+                    sm.cell_vo[tid] = vo;
+                    if (do_emit) {
+                        const uint32_t ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
+                        const uint32_t first_vertex = v_base + vo, dst = i_base + io;
+                        const uint8_t* tri = &sm.class_index[cls * 16];
+                        for (uint32_t j = 0; j < ni; ++j)
+                            if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + tri[j];
+                    }
                 }
                 consumer_sync<NT>();
-                // P3c: one thread per vertex
+                // ---- D: one thread per vertex; its cell by binary search over the cells' first vertices
                 if (do_emit) {
                     for (uint32_t v = tid; v < batch_v; v += NT) {
-                        const uint32_t o = sm.owner[v];
-                        const uint32_t cslot = o & 1023u, k = o >> 10;
-                        const uint32_t cr = sm.cell_rec[cslot];
+                        uint32_t lo = 0, hi = nb;
+#pragma unroll
+                        for (int step = 0; step < 10; ++step) {  // 2^10 >= CB
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (hi - lo > 1) {
+                                if (sm.cell_vo[mid] <= v) lo = mid; else hi = mid;
+                            }
+                        }
+                        const uint32_t cr = sm.cell_rec[lo], k = v - sm.cell_vo[lo];
                         const int x = cr & 63, r = (cr >> 8) & 255, c = cr >> 16;
                         const int zl = r / E, y = r % E;
                         const uint32_t code = sm.vertex_edge[c * 12 + k];
@@ -518,7 +508,7 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 v_base += batch_v;
                 i_base += batch_i;
             }
-            consumer_sync<NT>();  // every ring / bits / active read of this batch is done
+            consumer_sync<NT>();  // every ring / active read of this batch is done
             pend_count = 0;
         };
 
@@ -689,7 +679,7 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
     return cudaGetLastError();
 }
 
-using Cfg64 = Cfg<64, 1, 6, 16>;
+using Cfg64 = Cfg<64, 2, 6, 16>;
 using Cfg32 = Cfg<32, 2, 10, 8>;
 
 // Tuning variants (HVX_REGULAR_VARIANT=<n>, default 0); all produce identical output.
@@ -709,10 +699,10 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     const int variant = variant_from_env();
     if (edge == 64) {
         switch (variant) {
-            case 1: return launch_cfg<Cfg<64, 2, 6, 16>>(p, dev, stream);
+            case 1: return launch_cfg<Cfg<64, 1, 6, 16>>(p, dev, stream);
             case 2: return launch_cfg<Cfg<64, 1, 6, 15>>(p, dev, stream);
             case 3: return launch_cfg<Cfg<64, 1, 6, 11>>(p, dev, stream);
-            case 4: return launch_cfg<Cfg<64, 2, 6, 8>>(p, dev, stream);
+            case 4: return launch_cfg<Cfg<64, 1, 5, 16>>(p, dev, stream);
             default: return launch_cfg<Cfg64>(p, dev, stream);
         }
     }
@@ -720,7 +710,7 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
         switch (variant) {
             case 1: return launch_cfg<Cfg<32, 1, 6, 8>>(p, dev, stream);
             case 2: return launch_cfg<Cfg<32, 2, 8, 8>>(p, dev, stream);
-            case 3: return launch_cfg<Cfg<32, 2, 10, 4>>(p, dev, stream);
+            case 3: return launch_cfg<Cfg<32, 1, 8, 4>>(p, dev, stream);
             default: return launch_cfg<Cfg32>(p, dev, stream);
         }
     }
