@@ -590,13 +590,18 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                     // ---- P1: this warp's BPW ballot blocks of the slab: LDS, sign test, VOTE, STS ----
                     const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
                     uint32_t* dst = sm.bits[sc & (C::BR - 1)] + warp;
+                    // all loads first (the compiler does not hoist shared loads across ballots), then
+                    // the votes: BPW independent LDS in flight instead of one
+                    short dens[C::BPW];
 #pragma unroll
                     for (int k = 0; k < C::BPW; ++k) {
-                        if (k * NW + NW <= C::FULL || warp < C::FULL - k * NW) {
-                            const short d = src[64 * NW * k];
-                            const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                            if (lane == 0) dst[NW * k] = b;
-                        }
+                        const bool in_range = k * NW + NW <= C::FULL || warp < C::FULL - k * NW;
+                        dens[k] = in_range ? src[64 * NW * k] : short(1);
+                    }
+#pragma unroll
+                    for (int k = 0; k < C::BPW; ++k) {
+                        const uint32_t b = __ballot_sync(0xffffffffu, dens[k] <= 0);
+                        if (lane == 0 && (k * NW + NW <= C::FULL || warp < C::FULL - k * NW)) dst[NW * k] = b;
                     }
                     if (C::TAIL != 0 && warp == NW - 1) {
                         const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * C::FULL);
