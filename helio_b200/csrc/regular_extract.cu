@@ -83,7 +83,11 @@ struct Smem {
     uint64_t bits_bar[C::BR];
     uint64_t verdict_bar[C::BR];
     uint64_t active[C::BR][C::STEP_ROWS];  // active-cell bits per cell row of a step
-    uint64_t row_pref[C::ROWS + 1];        // debug records: per-row exclusive (cells | vertices<<16 | indices<<40)
+    union {
+        uint64_t row_pref[C::ROWS + 1];    // debug records: per-row exclusive (vertices | indices<<32)
+        uint8_t owner[C::CB * 12];         // emission: vertex -> (cell slot of the sub-batch) >> 1
+    };
+    uint32_t layer_off[8];                 // ring word offset of sample layer z0 + d of the batch being emitted
     uint64_t scan64[2][34];
     uint32_t scan32[2][34];
     uint32_t bits[C::BR][C::BW];           // solid bit of every sample of a slab, flat x-fastest order
@@ -168,10 +172,17 @@ __device__ __forceinline__ T scan_front_warps(T value, int nws, T (*buf)[34], ui
     }
     consumer_sync<NT>();
     T before = 0, all = 0;
-    for (int w = 0; w < nws; ++w) {
-        const T s = sums[w];
-        if (w < warp) before += s;
-        all += s;
+    if constexpr (sizeof(T) == 4) {
+        // second level in one shot: lane w holds warp w's sum, two REDUX.ADD give prefix and total
+        const uint32_t mine = lane < nws ? sums[lane] : 0u;
+        before = __reduce_add_sync(0xffffffffu, lane < warp ? mine : 0u);
+        all = __reduce_add_sync(0xffffffffu, mine);
+    } else {
+        for (int w = 0; w < nws; ++w) {
+            const T s = sums[w];
+            if (w < warp) before += s;
+            all += s;
+        }
     }
     total = all;
     return incl - value + before;
@@ -360,12 +371,14 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
         auto flush = [&]() {
             const int z0 = 2 * pend_first - 2;             // first cell layer of the batch (even)
             const int rows = pend_count * C::STEP_ROWS;    // row r: cell layer z0 + r / E, y = r % E
-            // sample layer z0 + d lives in slab (released + d/2) -> ring slot rel_slot + d/2
-            auto layer_words = [&](int d) -> int {
-                int s2 = rel_slot + (d >> 1);
+            // sample layer z0 + d lives in slab (released + d/2) -> ring slot rel_slot + d/2; the word
+            // offsets go through a tiny smem table (published by the rank scan's barrier below)
+            if (tid < 8) {
+                int s2 = rel_slot + (tid >> 1);
                 if (s2 >= RS) s2 -= RS;
-                return s2 * C::SLAB_WORDS + (d & 1) * LW;
-            };
+                sm.layer_off[tid] = static_cast<uint32_t>(s2 * C::SLAB_WORDS + (tid & 1) * LW);
+            }
+            auto layer_words = [&](int d) -> int { return static_cast<int>(sm.layer_off[d]); };
             // Transvoxel case of one cell straight from the bricks: bit i = corner (i&1, i>>1&1, i>>2&1)
             auto case_of = [&](int x, int y, int zl) -> uint32_t {
                 const uint32_t* l0 = ring_flat + layer_words(zl + 1) + (y + 1) * S + (x + 1);
@@ -476,27 +489,30 @@ __global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const Reg
                 if (tid < nb) {
                     const uint32_t vo = off & 0xffffu, io = off >> 16;
                     sm.cell_rec[tid] = rec;
-                    sm.cell_vo[tid] = vo;
+                    sm.cell_vo[tid] = static_cast<uint16_t>(vo);
                     if (do_emit) {
-                        const uint32_t ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
+                        const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
+                        for (uint32_t k = 0; k < nv; ++k) sm.owner[vo + k] = static_cast<uint8_t>(tid >> 1);
                         const uint32_t first_vertex = v_base + vo, dst = i_base + io;
-                        const uint8_t* tri = &sm.class_index[cls * 16];
-                        for (uint32_t j = 0; j < ni; ++j)
-                            if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + tri[j];
+                        // the class's <= 15 local indices are one aligned 16-byte row
+                        const uint4 row = *reinterpret_cast<const uint4*>(&sm.class_index[cls * 16]);
+                        const uint32_t words[4] = {row.x, row.y, row.z, row.w};
+                        if (dst + ni <= p.max_indices) {
+#pragma unroll
+                            for (uint32_t j = 0; j < 15; ++j)
+                                if (j < ni) out_i[dst + j] = first_vertex + ((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
+                        } else {
+                            for (uint32_t j = 0; j < ni; ++j)
+                                if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + ((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
+                        }
                     }
                 }
                 consumer_sync<NT>();
-                // ---- D: one thread per vertex; its cell by binary search over the cells' first vertices
+                // ---- D: one thread per vertex; the owner map names a pair of cells, one compare picks
                 if (do_emit) {
                     for (uint32_t v = tid; v < batch_v; v += NT) {
-                        uint32_t lo = 0, hi = nb;
-#pragma unroll
-                        for (int step = 0; step < 10; ++step) {  // 2^10 >= CB
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (hi - lo > 1) {
-                                if (sm.cell_vo[mid] <= v) lo = mid; else hi = mid;
-                            }
-                        }
+                        uint32_t lo = 2u * sm.owner[v];
+                        if (lo + 1 < nb && sm.cell_vo[lo + 1] <= v) ++lo;
                         const uint32_t cr = sm.cell_rec[lo], k = v - sm.cell_vo[lo];
                         const int x = cr & 63, r = (cr >> 8) & 255, c = cr >> 16;
                         const int zl = r / E, y = r % E;
