@@ -267,7 +267,7 @@ __device__ __forceinline__ void emit_regular_vertex(const uint32_t* __restrict__
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT_ALL, 1) regular_extract_kernel(const RegularParams p) {
+__global__ void __launch_bounds__(C::NT_ALL, C::E == 32 ? 2 : 1) regular_extract_kernel(const RegularParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem<C>& sm = *reinterpret_cast<Smem<C>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
