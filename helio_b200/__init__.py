@@ -7,7 +7,7 @@ does, and fails loudly if it is missing -- there is no CPU fallback.
 """
 from . import _ffi
 from .context import (CELL_OFFSET_DTYPE, CELL_RECORD_DTYPE, CLASSIFY_COUNTERS_DTYPE, EMISSION_COUNTERS_DTYPE,
-                      RANGE_DTYPE, SCAN_BLOCK_DTYPE, TRANSITION_COUNTERS_DTYPE, VERTEX_DTYPE, Context, make_descs)
+                      MESHLET_BOUNDS_DTYPE, MESHLET_DTYPE, RANGE_DTYPE, TERRAIN_MESHLET_BUILD_INDICES, SCAN_BLOCK_DTYPE, TRANSITION_COUNTERS_DTYPE, VERTEX_DTYPE, Context, make_descs)
 from .errors import (AddressError, BatchCapacity, CudaError, DeviceLimit, FinestLodHasNoFinerNeighbor, HvxError,
                      InvalidExtractionCapacity, SampleCount, TerrainLodTopologyError, TransitionDeviceLimit,
                      TransitionInvalidExtractionCapacity, TransitionMask, TransitionSampleCount,

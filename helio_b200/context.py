@@ -24,7 +24,12 @@ SCAN_BLOCK_DTYPE = np.dtype([("vertex_count", "<u4"), ("index_count", "<u4"), ("
                              ("first_index", "<u4")])
 RANGE_DTYPE = np.dtype([("first_vertex", "<u4"), ("vertex_count", "<u4"), ("first_index", "<u4"),
                         ("index_count", "<u4")])
-assert VERTEX_DTYPE.itemsize == 32 and EMISSION_COUNTERS_DTYPE.itemsize == 32
+MESHLET_DTYPE = np.dtype([(n, "<u4") for n in ("first_index", "index_count", "first_vertex", "vertex_count",
+                                                 "bounds_offset", "generation_low", "generation_high", "_pad")])
+MESHLET_BOUNDS_DTYPE = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("cone_apex", "<f4", 3),
+                                 ("cone_cutoff", "<f4"), ("cone_axis", "<f4", 3), ("_pad", "<f4")])
+TERRAIN_MESHLET_BUILD_INDICES = 63  # PV/src/terrain_meshlet.rs:7-8
+assert VERTEX_DTYPE.itemsize == 32 and EMISSION_COUNTERS_DTYPE.itemsize == 32 and MESHLET_BOUNDS_DTYPE.itemsize == 48
 assert TRANSITION_COUNTERS_DTYPE.itemsize == 48 and CLASSIFY_COUNTERS_DTYPE.itemsize == 16
 
 _BUF_DTYPES = {
@@ -37,6 +42,9 @@ _BUF_DTYPES = {
     _ffi.BUF_TRANSITION_COUNTERS: TRANSITION_COUNTERS_DTYPE, _ffi.BUF_TRANSITION_RANGES: RANGE_DTYPE,
     _ffi.BUF_TRANSITION_CELLS: CELL_RECORD_DTYPE, _ffi.BUF_TRANSITION_OFFSETS: CELL_OFFSET_DTYPE,
     _ffi.BUF_TRANSITION_BLOCKS: SCAN_BLOCK_DTYPE,
+    _ffi.BUF_REGULAR_MESHLETS: MESHLET_DTYPE, _ffi.BUF_REGULAR_MESHLET_BOUNDS: MESHLET_BOUNDS_DTYPE,
+    _ffi.BUF_REGULAR_MESHLET_COUNTS: np.dtype("<u4"), _ffi.BUF_TRANSITION_MESHLETS: MESHLET_DTYPE,
+    _ffi.BUF_TRANSITION_MESHLET_BOUNDS: MESHLET_BOUNDS_DTYPE, _ffi.BUF_TRANSITION_MESHLET_COUNTS: np.dtype("<u4"),
 }
 
 
@@ -199,6 +207,18 @@ class Context:
             slab_words = n * self.slab_words if count is None else count
         self._check(self._lib.hvx_extract_transition(self._handle, ptr, int(slab_words), descs, n), kind="transition")
         del keep
+
+    def build_meshlets(self, n, kind=0):
+        """63-index meshlets + bounds for chunks [0, n) of the last extraction (PV/src/terrain_meshlet.rs)."""
+        self._check(self._lib.hvx_build_meshlets(self._handle, kind, n), kind="transition" if kind else "regular")
+
+    def read_meshlets(self, chunk, kind=0):
+        """Host copy of one chunk's (descriptors, bounds) after build_meshlets."""
+        base = _ffi.BUF_TRANSITION_MESHLETS if kind else _ffi.BUF_REGULAR_MESHLETS
+        max_indices = self.max_transition_indices if kind else self.max_indices
+        stride = (max_indices + 62) // 63
+        count = int(self.read(base + 2, chunk, 1)[0])
+        return self.read(base, chunk * stride, count), self.read(base + 1, chunk * stride, count)
 
     def read_meshes(self, kind=0, first=0, n=None, vertices_out=None, indices_out=None):
         """Packed host copy of chunks [first, first+n): (vertices, indices, ranges)."""

@@ -102,6 +102,12 @@ uint64_t arena_bytes(const hvx_config& c, int id) {
         case HVX_BUF_TRANSITION_CELLS: return tr && dbg ? n * tcells(c.edge) * sizeof(hvx_cell_record) : 0;
         case HVX_BUF_TRANSITION_OFFSETS: return tr && dbg ? n * tcells(c.edge) * sizeof(hvx_cell_offset) : 0;
         case HVX_BUF_TRANSITION_BLOCKS: return tr && dbg ? n * (tcells(c.edge) / 256) * sizeof(hvx_scan_block) : 0;
+        case HVX_BUF_REGULAR_MESHLETS: return n * ((c.max_indices + 62ull) / 63) * sizeof(hvx_meshlet);
+        case HVX_BUF_REGULAR_MESHLET_BOUNDS: return n * ((c.max_indices + 62ull) / 63) * sizeof(hvx_meshlet_bounds);
+        case HVX_BUF_REGULAR_MESHLET_COUNTS: return n * 4;
+        case HVX_BUF_TRANSITION_MESHLETS: return tr ? n * ((c.max_transition_indices + 62ull) / 63) * sizeof(hvx_meshlet) : 0;
+        case HVX_BUF_TRANSITION_MESHLET_BOUNDS: return tr ? n * ((c.max_transition_indices + 62ull) / 63) * sizeof(hvx_meshlet_bounds) : 0;
+        case HVX_BUF_TRANSITION_MESHLET_COUNTS: return tr ? n * 4 : 0;
         default: return 0;
     }
 }
@@ -363,7 +369,7 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_work, 4))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_packed, c.max_chunks))) return bail(rc);
-    for (int id = HVX_BUF_REGULAR_VERTICES; id < HVX_BUF_COUNT; ++id)
+    for (int id = HVX_BUF_REGULAR_VERTICES; id <= HVX_BUF_TRANSITION_BLOCKS; ++id)  // meshlet arenas stay lazy
         if (arena_bytes(c, id) != 0 && (rc = ensure_buffer(ctx, id))) return bail(rc);
     if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaStreamSynchronize"));
     *out = ctx;
@@ -463,6 +469,38 @@ int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t words, 
     p.work_counter = ctx->d_work + 1;
     cudaError_t e = launch_transition(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_transition");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (kind != 0 && kind != 1) return fail(ctx, HVX_E_INVALID_ARGUMENT, "kind must be 0 (regular) or 1 (transition)");
+    if (n > ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
+    if (kind == 1 && ctx->cfg.max_transition_vertices == 0)
+        return fail(ctx, HVX_E_INVALID_CAPACITY, "Transvoxel transition capacities must be nonzero (vertices=0, indices=0)");
+    if (n == 0) return HVX_OK;
+    DeviceGuard guard(ctx->device);
+    const int mid = kind ? HVX_BUF_TRANSITION_MESHLETS : HVX_BUF_REGULAR_MESHLETS;
+    int rc;
+    for (int id = mid; id < mid + 3; ++id)
+        if ((rc = ensure_buffer(ctx, id))) return rc;
+    MeshletParams p{};
+    p.n_chunks = n;
+    p.transition = static_cast<uint32_t>(kind);
+    p.max_vertices = kind ? ctx->cfg.max_transition_vertices : ctx->cfg.max_vertices;
+    p.max_indices = kind ? ctx->cfg.max_transition_indices : ctx->cfg.max_indices;
+    p.max_meshlets = (p.max_indices + 62u) / 63u;
+    p.vertices = static_cast<hvx_vertex*>(ctx->buf[kind ? HVX_BUF_TRANSITION_VERTICES : HVX_BUF_REGULAR_VERTICES]);
+    p.indices = static_cast<uint32_t*>(ctx->buf[kind ? HVX_BUF_TRANSITION_INDICES : HVX_BUF_REGULAR_INDICES]);
+    p.regular_counters = static_cast<hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
+    p.transition_counters = static_cast<hvx_transition_counters*>(ctx->buf[HVX_BUF_TRANSITION_COUNTERS]);
+    p.descs = ctx->d_descs;
+    p.meshlets = static_cast<hvx_meshlet*>(ctx->buf[mid]);
+    p.bounds = static_cast<hvx_meshlet_bounds*>(ctx->buf[mid + 1]);
+    p.meshlet_counts = static_cast<uint32_t*>(ctx->buf[mid + 2]);
+    cudaError_t e = launch_meshlets(p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_meshlets");
     ctx->launches += 1;
     return HVX_OK;
 }

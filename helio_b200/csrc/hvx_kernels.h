@@ -59,6 +59,21 @@ struct FillParams {
     uint32_t* out;
 };
 
+struct MeshletParams {
+    uint32_t n_chunks;
+    uint32_t transition;                  // 0 regular, 1 transition
+    uint32_t max_vertices, max_indices;   // per-chunk slot capacity of the source arenas
+    uint32_t max_meshlets;                // ceil(max_indices / 63)
+    const hvx_vertex* vertices;
+    const uint32_t* indices;
+    const hvx_emission_counters* regular_counters;
+    const hvx_transition_counters* transition_counters;
+    const ChunkDesc* descs;
+    hvx_meshlet* meshlets;                // [n][max_meshlets]
+    hvx_meshlet_bounds* bounds;           // [n][max_meshlets]
+    uint32_t* meshlet_counts;             // [n]
+};
+
 struct DeviceInfo {
     int sm_count;
     int max_smem_optin;
@@ -69,6 +84,7 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
 cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_samples(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
 cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,
                         const hvx_range* packed_ranges, uint32_t n, hvx_vertex* out_vertices,

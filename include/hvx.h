@@ -108,6 +108,21 @@ typedef struct {
     uint32_t vertex_count, index_count, first_vertex, first_index;
 } hvx_scan_block;
 
+/* PV/src/extraction.rs:81-92 GpuTerrainMeshlet (32 B) and PV/src/terrain_meshlet.rs:10-20
+ * GpuTerrainMeshletBounds (48 B): fixed 63-index meshlets over a chunk's mesh. */
+typedef struct {
+    uint32_t first_index, index_count, first_vertex, vertex_count;
+    uint32_t bounds_offset, generation_low, generation_high, _pad; /* _pad: 0 regular, 1 transition */
+} hvx_meshlet;
+
+typedef struct {
+    float center[3], radius;
+    float cone_apex[3], cone_cutoff;
+    float cone_axis[3], _pad;
+} hvx_meshlet_bounds;
+
+#define HVX_MESHLET_INDICES 63u /* TERRAIN_MESHLET_BUILD_INDICES, PV/src/terrain_meshlet.rs:7-8 */
+
 /* Where chunk k's mesh lives in the ctx arenas (elements, not bytes).  Slots are
  * fixed-stride (k * max_vertices, k * max_indices), like the reference's per-slot
  * banked arenas (PV/src/surface_publish.wgsl:126-220); index values are chunk-local. */
@@ -193,6 +208,14 @@ int hvx_classify_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t sample_
 int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t slab_words,
                            const hvx_chunk_desc* descs, uint32_t n);
 
+/* ---- meshlets (the step after extraction in the reference's pass) -------------------- */
+/* build_regular / build_transition (PV/src/terrain_meshlet_build.wgsl:205-261; CPU twin
+ * build_terrain_meshlets, PV/src/terrain_meshlet.rs:83-155) for chunks [0, n) of the last
+ * extraction of that kind: fixed 63-index partition, unique-vertex count, AABB-centre bounding
+ * sphere, normal cone.  Chunk k's meshlets start at k * ceil(max_indices / 63); chunks that
+ * overflowed publish none.  kind 0 = regular, 1 = transition. */
+int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n);
+
 /* ---- outputs ------------------------------------------------------------------------ */
 typedef enum {
     HVX_BUF_SAMPLES = 0,             /* u32  [max_chunks][(edge+2)^3]          (lazy) */
@@ -212,7 +235,13 @@ typedef enum {
     HVX_BUF_TRANSITION_CELLS = 14,    /* [max_chunks][6*edge^2] (debug) cells_buffer() */
     HVX_BUF_TRANSITION_OFFSETS = 15,
     HVX_BUF_TRANSITION_BLOCKS = 16,   /* [max_chunks][6*edge^2/256] */
-    HVX_BUF_COUNT = 17
+    HVX_BUF_REGULAR_MESHLETS = 17,         /* hvx_meshlet        [max_chunks][ceil(max_indices/63)]  (lazy) */
+    HVX_BUF_REGULAR_MESHLET_BOUNDS = 18,   /* hvx_meshlet_bounds [max_chunks][ceil(max_indices/63)]  (lazy) */
+    HVX_BUF_REGULAR_MESHLET_COUNTS = 19,   /* u32 [max_chunks] */
+    HVX_BUF_TRANSITION_MESHLETS = 20,
+    HVX_BUF_TRANSITION_MESHLET_BOUNDS = 21,
+    HVX_BUF_TRANSITION_MESHLET_COUNTS = 22,
+    HVX_BUF_COUNT = 23
 } hvx_buffer_id;
 
 /* Device pointer / size of a ctx arena (allocating it if lazy); NULL / 0 if unavailable. */

@@ -877,3 +877,116 @@ int64_t hvxo_batch_regular(int kind, int edge, uint32_t lod, const int64_t* page
     }
     return (int64_t)n * edge * edge * edge;
 }
+
+/* ------------------------------------------------------------------------- */
+/* Meshlet build: PV/src/terrain_meshlet.rs:83-249              */
+
+static inline float m_dot(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void m_sub(const float a[3], const float b[3], float o[3]) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static inline void m_cross(const float a[3], const float b[3], float o[3]) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+/* normalize (:309-312): magnitude > f32::EPSILON, scale by magnitude.recip() */
+static inline int m_normalize(const float v[3], float o[3]) {
+    float magnitude = sqrtf(m_dot(v, v));
+    if (!(magnitude > 1.1920929e-7f)) return 0;
+    float inv = 1.0f / magnitude;
+    o[0] = v[0] * inv; o[1] = v[1] * inv; o[2] = v[2] * inv;
+    return 1;
+}
+static int m_triangle_normal(const hvxo_vertex* v, const uint32_t* tri, float n[3]) {
+    float ab[3], ac[3], c[3];
+    m_sub(v[tri[1]].position, v[tri[0]].position, ab);
+    m_sub(v[tri[2]].position, v[tri[0]].position, ac);
+    m_cross(ab, ac, c);
+    return m_normalize(c, n);
+}
+
+/* compute_bounds (:184-249) for one chunk of <= 63 indices */
+static void meshlet_bounds(const hvxo_vertex* v, const uint32_t* idx, uint32_t n, hvxo_meshlet_bounds* out) {
+    float mn[3], mx[3];
+    for (int a = 0; a < 3; ++a) mn[a] = mx[a] = v[idx[0]].position[a];
+    for (uint32_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fminf(mn[a], v[idx[i]].position[a]);
+            mx[a] = fmaxf(mx[a], v[idx[i]].position[a]);
+        }
+    float center[3];
+    for (int a = 0; a < 3; ++a) center[a] = (mn[a] + mx[a]) * 0.5f;
+    float radius = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) {
+        float d[3];
+        m_sub(v[idx[i]].position, center, d);
+        radius = fmaxf(radius, sqrtf(m_dot(d, d)));
+    }
+    memset(out, 0, sizeof *out);
+    for (int a = 0; a < 3; ++a) { out->center[a] = center[a]; out->cone_apex[a] = center[a]; }
+    out->radius = radius;
+    out->cone_cutoff = 1.0f; /* disabled_bounds (:251-260) until proven otherwise */
+    float sum[3] = {0.0f, 0.0f, 0.0f}, axis[3];
+    for (uint32_t t = 0; t + 2 < n; t += 3) {
+        float nrm[3];
+        if (m_triangle_normal(v, idx + t, nrm))
+            for (int a = 0; a < 3; ++a) sum[a] = sum[a] + nrm[a];
+    }
+    if (!m_normalize(sum, axis)) return;
+    float min_dot = 1.0f;
+    for (uint32_t t = 0; t + 2 < n; t += 3) {
+        float nrm[3];
+        if (m_triangle_normal(v, idx + t, nrm)) min_dot = fminf(min_dot, m_dot(nrm, axis));
+    }
+    if (min_dot <= 0.1f) return;
+    float apex_distance = 0.0f;
+    for (uint32_t t = 0; t + 2 < n; t += 3) {
+        float nrm[3], ca[3];
+        if (!m_triangle_normal(v, idx + t, nrm)) continue;
+        float denominator = m_dot(axis, nrm);
+        if (denominator > 0.0f) {
+            m_sub(center, v[idx[t]].position, ca);
+            apex_distance = fmaxf(apex_distance, m_dot(ca, nrm) / denominator);
+        }
+    }
+    for (int a = 0; a < 3; ++a) {
+        out->cone_apex[a] = center[a] - axis[a] * apex_distance;
+        out->cone_axis[a] = axis[a];
+    }
+    out->cone_cutoff = fminf(sqrtf(fmaxf(1.0f - min_dot * min_dot, 0.0f)) + 1.0e-4f, 1.0f);
+}
+
+int hvxo_build_meshlets(const hvxo_vertex* vertices, uint32_t vertex_count, const uint32_t* indices,
+                        uint32_t index_count, uint32_t first_index, uint32_t first_vertex, uint32_t first_bounds,
+                        uint64_t generation, uint32_t flags, hvxo_meshlet* meshlets, hvxo_meshlet_bounds* bounds,
+                        uint32_t capacity) {
+    if (index_count % 3 != 0) return -1;                                   /* IncompleteTriangle */
+    for (uint32_t i = 0; i < vertex_count; ++i)
+        for (int a = 0; a < 3; ++a)
+            if (!isfinite(vertices[i].position[a])) return -3;              /* NonFinitePosition */
+    for (uint32_t i = 0; i < index_count; ++i)
+        if (indices[i] >= vertex_count) return -2;                          /* IndexOutOfBounds */
+    uint32_t count = (index_count + 62) / 63;
+    if (count > capacity) return -4;
+    for (uint32_t m = 0; m < count; ++m) {
+        const uint32_t* chunk = indices + 63 * m;
+        uint32_t n = index_count - 63 * m < 63 ? index_count - 63 * m : 63;
+        uint32_t unique = 0;                                                /* unique_index_count (:171-182) */
+        for (uint32_t i = 0; i < n; ++i) {
+            int seen = 0;
+            for (uint32_t j = 0; j < i; ++j)
+                if (chunk[j] == chunk[i]) { seen = 1; break; }
+            unique += !seen;
+        }
+        hvxo_meshlet* d = &meshlets[m];
+        d->first_index = first_index + 63 * m;
+        d->index_count = n;
+        d->first_vertex = first_vertex;
+        d->vertex_count = unique;
+        d->bounds_offset = first_bounds + m;
+        d->generation_low = (uint32_t)generation;
+        d->generation_high = (uint32_t)(generation >> 32);
+        d->_pad = flags;
+        meshlet_bounds(vertices, chunk, n, &bounds[m]);
+    }
+    return (int)count;
+}

@@ -153,6 +153,22 @@ int64_t hvxo_batch_regular(int kind, int edge, uint32_t lod, const int64_t* page
 int hvxo_batch_fill(int kind, int edge, uint32_t lod, const int64_t* page_xyz, uint32_t n, int threads, uint32_t* out);
 int hvxo_max_threads(void);
 
+/* PV/src/extraction.rs:81-92 GpuTerrainMeshlet and PV/src/terrain_meshlet.rs:10-20 GpuTerrainMeshletBounds. */
+typedef struct {
+    uint32_t first_index, index_count, first_vertex, vertex_count, bounds_offset, generation_low, generation_high, _pad;
+} hvxo_meshlet;
+typedef struct {
+    float center[3], radius, cone_apex[3], cone_cutoff, cone_axis[3], _pad;
+} hvxo_meshlet_bounds;
+
+/* build_terrain_meshlets (PV/src/terrain_meshlet.rs:83-155): fixed 63-index partition, AABB-centre
+ * bounding sphere, normal cone.  Returns the meshlet count (<= capacity) or a negative error:
+ * -1 IncompleteTriangle, -2 IndexOutOfBounds, -3 NonFinitePosition, -4 capacity. */
+int hvxo_build_meshlets(const hvxo_vertex* vertices, uint32_t vertex_count, const uint32_t* indices,
+                        uint32_t index_count, uint32_t first_index, uint32_t first_vertex, uint32_t first_bounds,
+                        uint64_t generation, uint32_t flags, hvxo_meshlet* meshlets, hvxo_meshlet_bounds* bounds,
+                        uint32_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

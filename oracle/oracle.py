@@ -25,6 +25,10 @@ FIELD_NAMES = {
     "terrain_fbm": FIELD_TERRAIN_FBM, "dense_random": FIELD_DENSE_RANDOM,
 }
 
+MESHLET_DTYPE = np.dtype([(n, "<u4") for n in ("first_index", "index_count", "first_vertex", "vertex_count",
+                                                 "bounds_offset", "generation_low", "generation_high", "_pad")])
+MESHLET_BOUNDS_DTYPE = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("cone_apex", "<f4", 3), ("cone_cutoff", "<f4"),
+                                 ("cone_axis", "<f4", 3), ("_pad", "<f4")])
 VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("material", "<u4"), ("normal", "<f4", 3), ("flags", "<u4")])
 assert VERTEX_DTYPE.itemsize == 32
 
@@ -79,6 +83,8 @@ def lib():
         L.hvxo_batch_regular.restype = C.c_int64
         L.hvxo_batch_regular.argtypes = [C.c_int, C.c_int, C.c_uint32, i64p, C.c_uint32, C.c_int, u32p, C.c_int,
                                          C.POINTER(C.c_uint64)]
+        L.hvxo_build_meshlets.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                          C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.hvxo_batch_fill.argtypes = [C.c_int, C.c_int, C.c_uint32, i64p, C.c_uint32, C.c_int, u32p]
         L.hvxo_case_topology.argtypes = [C.c_int, C.c_uint32, u32p, u32p, u32p, u32p, C.POINTER(C.c_uint16),
                                          C.POINTER(C.c_uint8)]
@@ -218,6 +224,22 @@ def extract_transition_face_analytic(kind: int, page_xyz, lod: int, face: int, e
     if rc:
         raise ValueError(f"analytic face failed: {rc}")
     return verts[:nv.value].copy(), idx[:ni.value].copy()
+
+
+def build_meshlets(vertices: np.ndarray, indices: np.ndarray, first_index=0, first_vertex=0, first_bounds=0,
+                   generation=1, flags=0):
+    """build_terrain_meshlets: (descriptors, bounds); raises ValueError with the reference's error kind."""
+    vertices = np.ascontiguousarray(vertices, dtype=VERTEX_DTYPE)
+    indices = np.ascontiguousarray(indices, dtype=np.uint32)
+    cap = (indices.size + 62) // 63 + 1
+    meshlets = np.zeros(cap, dtype=MESHLET_DTYPE)
+    bounds = np.zeros(cap, dtype=MESHLET_BOUNDS_DTYPE)
+    rc = lib().hvxo_build_meshlets(vertices.ctypes.data_as(C.c_void_p), vertices.size, _u32p(indices), indices.size,
+                                   first_index, first_vertex, first_bounds, generation, flags,
+                                   meshlets.ctypes.data_as(C.c_void_p), bounds.ctypes.data_as(C.c_void_p), cap)
+    if rc < 0:
+        raise ValueError({-1: "IncompleteTriangle", -2: "IndexOutOfBounds", -3: "NonFinitePosition", -4: "capacity"}[rc])
+    return meshlets[:rc], bounds[:rc]
 
 
 def max_threads() -> int:
