@@ -13,18 +13,21 @@
 //   * one CTA per SM pulls chunks from an atomic queue and walks each chunk front to back in z.
 //     x-fastest cell order == walk order, so vertex/index placement is a running prefix inside
 //     the CTA: order preserving by construction, no cross-CTA scan on the data path.
-//   * a PRODUCER warp streams sample layers ((E+2)^2 words, contiguous, 16-byte aligned) from HBM
-//     into a shared-memory ring with cp.async.bulk (TMA 1-D, SASS UBLKCP): full[slot] mbarriers
-//     carry the byte count, empty[slot] mbarriers hand slots back.  It runs up to R-4 layers
-//     ahead, across chunk boundaries.  Every sample is read from HBM exactly once.
-//   * CONSUMER warps never meet at a CTA barrier while the chunk is empty: each warp turns its
-//     share of a landed layer into solid bits (one ballot per 32 samples), two warps per cell
-//     layer derive the 64-cell active masks of its rows with shifts and AND/OR (8 corner signs =
-//     8 shifted copies of 4 bit rows) and publish a verdict through an mbarrier; everybody else
-//     just reads the verdict two layers later and releases the oldest ring slot.
-//   * layers that do contain surface cells are batched (up to EB consecutive layers) and emitted
-//     collectively: popc ranks -> warp-shuffle scan -> ordered compaction -> one thread per
-//     VERTEX reading its 14 samples from the shared-memory bricks (no HBM re-read).
+//   * a PRODUCER warp streams SLABS of two sample layers (2*(E+2)^2 words, contiguous, 16-byte
+//     aligned) from HBM into a shared-memory ring with cp.async.bulk (TMA 1-D, SASS UBLKCP):
+//     full[slot] mbarriers carry the byte count, empty[slot] mbarriers hand slots back.  It runs
+//     ahead across chunk boundaries.  Every sample is read from HBM exactly once.
+//   * CONSUMER warps never meet at a CTA barrier while the chunk is empty.  Iteration j (slab j):
+//     every warp turns its 1/NW of the slab into solid bits (all loads first, then one ballot per
+//     32 samples); a rotating group of warps classifies step j-1 (two cell layers) -- a cell row's
+//     8 corner signs are 8 shifted copies of 4 bit rows, so one thread gets the 64-cell active
+//     mask of a row with funnel shifts and AND/OR -- and publishes a verdict through an mbarrier;
+//     everybody reads the verdict of step j-2 (ready for a whole iteration) and releases the
+//     oldest ring slot.
+//   * steps that do contain surface cells are batched (up to EBS consecutive steps) and emitted
+//     collectively: quarter-row popc ranks -> warp-shuffle scan -> ordered compaction -> one
+//     thread per active CELL (case from the bricks, counts, second scan, indices) -> one thread
+//     per VERTEX reading its 14 samples from the shared-memory bricks (no HBM re-read).
 //   * no single-address atomics: the reference's 5 atomicAdd per cell become one counter record
 //     written once per chunk.
 #include <cstdlib>
@@ -144,13 +147,6 @@ __device__ __forceinline__ RowCorners load_row_corners(const uint32_t* __restric
     row_window<C>(bits1, base1, y + 1, rc.a01, rc.b01);
     row_window<C>(bits1, base1, y + 2, rc.a11, rc.b11);
     return rc;
-}
-
-__device__ __forceinline__ uint32_t case_at(const RowCorners& rc, int x) {
-    return static_cast<uint32_t>((rc.a00 >> x) & 1) | static_cast<uint32_t>((rc.b00 >> x) & 1) << 1 |
-           static_cast<uint32_t>((rc.a10 >> x) & 1) << 2 | static_cast<uint32_t>((rc.b10 >> x) & 1) << 3 |
-           static_cast<uint32_t>((rc.a01 >> x) & 1) << 4 | static_cast<uint32_t>((rc.b01 >> x) & 1) << 5 |
-           static_cast<uint32_t>((rc.a11 >> x) & 1) << 6 | static_cast<uint32_t>((rc.b11 >> x) & 1) << 7;
 }
 
 // Exclusive scan over the values of the first `nws` consumer warps (other threads pass 0 and only
@@ -556,6 +552,7 @@ __global__ void __launch_bounds__(C::NT_ALL, C::E == 32 ? 2 : 1) regular_extract
             const uint32_t vi = stc0 + static_cast<uint32_t>(st - 1);
             sm.active[vi & (C::BR - 1)][r] = act;
             const bool any_row = __any_sync(0xffffffffu, act != 0);
+            __syncwarp();  // every lane's active-mask store is ordered before lane 0's releasing arrive
             if (lane == 0) {
                 sm.verdict_flag[vi & (C::BR - 1)][p2_sub] = any_row ? 1u : 0u;
                 mbar_arrive(&sm.verdict_bar[vi & (C::BR - 1)]);
