@@ -1,5 +1,6 @@
-run() { HVX_DEBUG_FLAGS=$1 HVX_REGULAR_VARIANT=$2 timeout 120 python bench.py --steps 5 --warmup 2 --no-e2e --no-cpu --workload $3 2>/dev/null | tail -1 | python -c "import sys,json
+# A/B of regular-kernel variants: usage  bash tools/run_ab.sh "0 10" "terrain empty surface"
+run() { HVX_REGULAR_VARIANT=$1 timeout 180 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --workload $2 2>/dev/null | tail -1 | python -c "import sys,json
 try:
-    d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('flags $1 variant $2 $3', round(d['ms_per_step'],4), round(d['roofline']['achieved']), round(d['roofline']['frac'],3))
-except Exception as e: print('flags $1 variant $2 $3 FAILED')"; }
-for f in 0 1; do for v in 2; do for w in terrain empty surface; do run $f $v $w; done; done; done
+    d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('variant $1 $2', round(d['ms_per_step'],4), round(d['roofline']['achieved']), round(d['roofline']['frac'],3))
+except Exception as e: print('variant $1 $2 FAILED')"; }
+for v in ${1:-0 10}; do for w in ${2:-terrain empty surface}; do run $v $w; done; done
