@@ -1152,6 +1152,9 @@ struct DecoupledCfg {
     static constexpr int NT_ALL = (FW + C::NW + 1) * 32;       // front + emission + producer
     static constexpr int FB = (C::FULL + FW - 1) / FW;         // ballot blocks per front warp per slab
     static constexpr int PB = FB % 17 == 0 ? 17 : 18;          // loads in flight per batch
+    // cells per tile: a typical surface cell has 4 vertices, so 30 cells fill four 32-lane vertex
+    // passes (~120 vertices); 32 cells would spill a handful of vertices into a fifth
+    static constexpr int TC = 30;
     static_assert(C::STEP_ROWS == CW * 32, "one classifying lane per cell row");
     static_assert(C::FULL % FW == 0 && FB % PB == 0, "front warps split the slab's ballot blocks evenly");
 };
@@ -1194,13 +1197,13 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 const uint32_t id = atomicAdd(p.work_counter, 1u);
                 sm.chunk_ids[k & 3] = id;
                 if (id >= p.n_chunks) {
-                    mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     mbar_arrive(&sm.full_bar[slot]);
                     break;
                 }
                 const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words;
                 for (int j = 0; j < C::NSLAB; ++j) {
-                    mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     mbar_arrive_expect_tx(&sm.full_bar[slot], C::SLAB_BYTES);
                     bulk_g2s(&sm.ring[slot][0], src + static_cast<size_t>(j) * C::SLAB_WORDS, C::SLAB_BYTES,
                              &sm.full_bar[slot]);
@@ -1222,7 +1225,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         for (uint32_t kc = 0;; ++kc) {
             uint64_t dirty = 0;
             for (int j = 0; j < C::NSLAB; ++j) {
-                mbar_wait(&sm.full_bar[slot], round & 1u);
+                mbar_wait_parked(&sm.full_bar[slot], round & 1u);
                 if (j == 0) {
                     const uint32_t chunk = sm.chunk_ids[kc & 3];
                     if (chunk >= p.n_chunks) return;
@@ -1331,8 +1334,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         auto process_tile = [&](int st, int rs, uint32_t t, uint32_t ntiles, uint32_t n_cells, const uint32_t (&cum)[CW]) {
             const uint32_t seq = tile_seq + t;
             const bool first = chunk_tiles + t == 0;
-            const uint32_t r = 32u * t + static_cast<uint32_t>(lane);
-            const bool valid = r < n_cells;
+            const uint32_t r = D::TC * t + static_cast<uint32_t>(lane);
+            const bool valid = lane < D::TC && r < n_cells;
             uint32_t rec = 0, packed = 0, info = 0;
             if (valid) {
                 // locate: front warp -> row (largest row whose first rank <= mine) -> k-th set bit
@@ -1373,6 +1376,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 rec = static_cast<uint32_t>(x) | (row << 8) | (c << 16);
                 packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
             }
+            __syncwarp();
             uint32_t incl = packed;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -1382,19 +1386,19 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
             const uint32_t tot_v = total & 0xffffu, tot_i = total >> 16;
             const uint32_t vo = (incl - packed) & 0xffffu, io = (incl - packed) >> 16;
-            // chained prefix: wait for the previous tile's inclusive totals, publish ours
-            uint32_t base_lo = 0, base_hi = 0;
+            // chained prefix: wait for the previous tile's inclusive totals, publish ours.  Every lane
+            // polls the same word (a broadcast read), so the warp never splits around the spin.
+            uint64_t base = 0;
+            if (!first) {
+                const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 63u];
+                const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
+                uint64_t got;
+                do {
+                    got = *prev;
+                } while ((got >> 44) != want);
+                base = got & ((1ull << 44) - 1ull);
+            }
             if (lane == 0) {
-                uint64_t base = 0;
-                if (!first) {
-                    const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 63u];
-                    const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
-                    uint64_t got;
-                    do {
-                        got = *prev;
-                    } while ((got >> 44) != want);
-                    base = got & ((1ull << 44) - 1ull);
-                }
                 const uint64_t mine = (base + static_cast<uint64_t>(tot_v) + (static_cast<uint64_t>(tot_i) << 22)) |
                                       (static_cast<uint64_t>(seq & 0xfffffu) << 44);
                 if (t + 1 == ntiles) {  // totals so far; later steps overwrite, ordered along the chain
@@ -1402,13 +1406,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     __threadfence_block();
                 }
                 *const_cast<volatile uint64_t*>(&sm.tile_prefix[seq & 63u]) = mine;
-                base_lo = static_cast<uint32_t>(base);
-                base_hi = static_cast<uint32_t>(base >> 32);
             }
-            base_lo = __shfl_sync(0xffffffffu, base_lo, 0);
-            base_hi = __shfl_sync(0xffffffffu, base_hi, 0);
+            __syncwarp();
             if (!do_emit) return;
-            const uint64_t base = static_cast<uint64_t>(base_lo) | (static_cast<uint64_t>(base_hi) << 32);
             const uint32_t v_base = static_cast<uint32_t>(base & FIELD), i_base = static_cast<uint32_t>((base >> 22) & FIELD);
             if (valid) {
                 const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
@@ -1446,7 +1446,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
 
         for (int j = 0; j < C::NSLAB; ++j) {
             if (j == 0) {
-                mbar_wait(&sm.full_bar[slot], round & 1u);
+                mbar_wait_parked(&sm.full_bar[slot], round & 1u);
                 chunk = sm.chunk_ids[kc & 3];
                 if (chunk >= p.n_chunks) return;
                 const ChunkDesc desc = p.descs[chunk];
@@ -1455,7 +1455,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
                 out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
             }
-            mbar_wait(&sm.ready_bar[slot], round & 1u);
+            mbar_wait_parked(&sm.ready_bar[slot], round & 1u);
             if (j >= 1) {
                 uint32_t cum[CW];
                 uint32_t n_cells = 0;
@@ -1465,7 +1465,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     cum[i] = n_cells;
                 }
                 if (n_cells != 0) {
-                    const uint32_t ntiles = (n_cells + 31u) >> 5;
+                    const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
                     if (*const_cast<volatile uint32_t*>(&sm.tile_ctr[slot]) < ntiles) {
                         // the z gradient of the step's upper layer reads the first layer of slab j+1
                         if (j + 1 < C::NSLAB) {
