@@ -682,44 +682,88 @@ __global__ void __launch_bounds__(C::NT_ALL, C::E == 32 ? 2 : 1) regular_extract
 }
 
 
-// =============================================================================================
-// Second-generation kernel: WARP-AUTONOMOUS emission.  Streaming, P1 and classification are as
-// above, but nothing ever meets at a CTA-wide barrier:
-//   * the classifying warps also publish, per step, every row's first cell rank (popc + warp
-//     scan) and their totals, so "the r-th active cell of the step" can be located by anybody;
-//   * the step's active cells are cut into TILES of 32 consecutive ranks; tile q of the CTA's
-//     running tile sequence belongs to consumer warp q % NW, which does everything for it alone:
-//     locate (binary search over row ranks + k-th-set-bit select), case from the bricks, warp
-//     scan of (vertices | indices), indices, then one lane per vertex through a warp-private
-//     owner map;
-//   * order-preserving placement across tiles is a chained prefix in shared memory (decoupled
-//     look-back with depth 1): tile q spins on tile q-1's inclusive (vertices, indices) total,
-//     a single 64-bit word tagged with q, and publishes its own before it starts writing;
-//   * a warp hands a slab back on empty[slot] once ITS tiles of the step are done; the mbarrier
-//     completes when every warp has.  Warp skew is bounded by the slab ring (RS) -- the per-step
-//     records live in rings of BRW >= RS - 2 entries.
-// =============================================================================================
+// Same vertex, restated for the decoupled kernel with fewer instructions and no data-dependent
+// branches; every float it produces has the same bits as emit_regular_vertex:
+//   * densities are converted with the 2^23 trick: (w & 0xffff) ^ 0x4B008000 is the float
+//     8421376 + d exactly, so differences of two biased values are the exact integer differences
+//     (what fsub(float(d1), float(d0)) gives), and one exact subtraction recovers d itself;
+//   * an edge runs along one axis from corner c0 to c1 = c0 + one bit (checked over the whole table),
+//     so mix(P0, P1, t) is P0 + 1*t on that axis and P0 + 0*t = P0 on the others;
+//   * the one-sided gradient on the +face becomes "load the centre instead of the +1 neighbour and
+//     scale by 1 instead of 0.5".
+// wl[d] is the ring word offset of sample layer (first layer of the step + d).
 template <class C>
-struct SmemW {
-    static constexpr int BRW = C::RS - 2 <= 4 ? 4 : 8;  // per-step record ring depth
-    static_assert(C::RS - 2 <= BRW, "per-step rings must cover the slab ring's warp skew");
-    alignas(128) uint32_t ring[C::RS][C::SLAB_WORDS];
-    alignas(8) uint64_t full_bar[C::RS];
-    uint64_t empty_bar[C::RS];
-    uint64_t bits_bar[BRW];
-    uint64_t verdict_bar[BRW];
-    uint64_t active[BRW][C::STEP_ROWS];    // active-cell bits per cell row of a step
-    uint64_t tile_prefix[64];              // chained tile totals: vertices | indices<<22 | tag<<44
-    uint32_t bits[BRW][C::BW];             // solid bit of every sample of a slab, flat x-fastest order
-    uint32_t wtot[BRW][C::PWS];            // active cells per classifying warp of a step
-    uint32_t wlayer[C::NW][8];             // per warp: ring word offset of sample layer z0 + d
-    uint32_t chunk_ids[4];
-    uint16_t rowrank[BRW][C::STEP_ROWS];   // first cell rank of a row, relative to its classifying warp
-    uint16_t case_info[256];
-    alignas(16) uint8_t class_index[16 * 16];
-    uint8_t vertex_edge[256 * 12];
-    uint8_t owner[C::NW][384];             // per warp: tile vertex -> lane (cell) that owns it
-};
+__device__ __forceinline__ void emit_regular_vertex_fast(const uint32_t* __restrict__ ring, const uint32_t* __restrict__ wl,
+                                                         int x, int y, int zl, int z, uint32_t code, uint32_t transition_mask,
+                                                         hvx_vertex* dst) {
+    constexpr int S = C::S;
+    constexpr float BIAS = 8421376.0f;  // 2^23 + 2^15
+    auto biased = [](uint32_t w) { return __uint_as_float((w & 0xffffu) ^ 0x4B008000u); };
+    const int c0 = code >> 4, axis = (code >> 4) ^ (code & 15);  // axis: 1 = x, 2 = y, 4 = z
+    const int ax = x + 1 + (c0 & 1), ay = y + 1 + ((c0 >> 1) & 1), ea = zl + 1 + ((c0 >> 2) & 1);
+    const int bx = ax + (axis & 1), by = ay + ((axis >> 1) & 1), eb = ea + (axis >> 2);
+    const int az = z - zl + ea, bz = z - zl + eb;  // absolute sample-layer indices
+    auto endpoint = [&](int xi, int yi, int e, int zi, uint32_t& w, float& m, float g[3]) {
+        const bool hx = xi >= C::E + 1, hy = yi >= C::E + 1, hz = zi >= C::E + 1;
+        const int off = yi * S + xi;
+        const uint32_t* l0 = ring + wl[e] + off;
+        const uint32_t* lm = ring + wl[e - 1] + off;
+        const uint32_t* lp = ring + wl[hz ? e : e + 1] + off;
+        w = l0[0];
+        m = biased(w);
+        const float xm = biased(l0[-1]), ym = biased(l0[-S]), zm = biased(lm[0]);
+        const float xp = biased(l0[hx ? 0 : 1]), yp = biased(l0[hy ? 0 : S]), zp = biased(lp[0]);
+        g[0] = fmul(fsub(xp, xm), hx ? 1.0f : 0.5f);
+        g[1] = fmul(fsub(yp, ym), hy ? 1.0f : 0.5f);
+        g[2] = fmul(fsub(zp, zm), hz ? 1.0f : 0.5f);
+    };
+    uint32_t wa, wb;
+    float ma, mb, ga[3], gb[3];
+    endpoint(ax, ay, ea, az, wa, ma, ga);
+    endpoint(bx, by, eb, bz, wb, mb, gb);
+    const float d0 = fsub(ma, BIAS), d1 = fsub(mb, BIAS);
+    const float t = edge_parameter(d0, d1);
+    float p[3], n[3];
+    const float fx = static_cast<float>(ax - 1), fy = static_cast<float>(ay - 1), fz = static_cast<float>(az - 1);
+    p[0] = (axis & 1) ? fadd(fx, t) : fx;
+    p[1] = (axis & 2) ? fadd(fy, t) : fy;
+    p[2] = (axis & 4) ? fadd(fz, t) : fz;
+    const float gx = fmix(ga[0], gb[0], t), gy = fmix(ga[1], gb[1], t), gz = fmix(ga[2], gb[2], t);
+    const float s = fadd(fadd(fmul(gx, gx), fmul(gy, gy)), fmul(gz, gz));
+    const bool sound = s > 1.0e-12f;
+    const float inv = fdiv(1.0f, fsqrt(sound ? s : 1.0f));
+    n[0] = sound ? fmul(gx, inv) : 0.0f;
+    n[1] = sound ? fmul(gy, inv) : 1.0f;
+    n[2] = sound ? fmul(gz, inv) : 0.0f;
+    // Transvoxel secondary position on faces that own a transition mesh
+    // (PV/tests/gpu_transvoxel_emission.rs:346-400, thresholds 1 and E-1)
+    if (transition_mask != 0) {
+        const float hi = static_cast<float>(C::E - 1);
+        uint32_t near = 0;
+        near |= p[0] < 1.0f ? 1u : 0u;
+        near |= p[0] > hi ? 2u : 0u;
+        near |= p[1] < 1.0f ? 4u : 0u;
+        near |= p[1] > hi ? 8u : 0u;
+        near |= p[2] < 1.0f ? 16u : 0u;
+        near |= p[2] > hi ? 32u : 0u;
+        if (near != 0 && (near & ~transition_mask) == 0) {
+            float off[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                off[a] = 0.0f;
+                if (near & (1u << (2 * a))) off[a] = fmul(fsub(1.0f, p[a]), 0.25f);
+                else if (near & (2u << (2 * a))) off[a] = fmul(fsub(hi, p[a]), 0.25f);
+            }
+            const float nc = fadd(fadd(fmul(off[0], n[0]), fmul(off[1], n[1])), fmul(off[2], n[2]));
+#pragma unroll
+            for (int a = 0; a < 3; ++a) p[a] = fsub(fadd(p[a], off[a]), fmul(n[a], nc));
+        }
+    }
+    const uint32_t material = d0 <= 0.0f ? cw_material(wa) : cw_material(wb);
+    float4* out = reinterpret_cast<float4*>(dst);
+    out[0] = make_float4(p[0], p[1], p[2], __uint_as_float(material));
+    out[1] = make_float4(n[0], n[1], n[2], __uint_as_float(0u));
+}
 
 // position of the k-th (0-based) set bit of w; k < popc(w)
 __device__ __forceinline__ int select_bit32(uint32_t w, uint32_t k) {
@@ -736,381 +780,8 @@ __device__ __forceinline__ int select_bit32(uint32_t w, uint32_t k) {
     return pos;
 }
 
-template <class C>
-__global__ void __launch_bounds__(C::NT_ALL, C::E == 32 ? 2 : 1) regular_extract_auton_kernel(const RegularParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    using SM = SmemW<C>;
-    SM& sm = *reinterpret_cast<SM*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int E = C::E, S = C::S, RS = C::RS, NW = C::NW, LW = C::LAYER_WORDS, BRW = SM::BRW, PWS = C::PWS;
-    constexpr uint64_t ROWMASK = E == 64 ? ~0ull : 0xffffffffull;
-    constexpr uint64_t FIELD = (1ull << 22) - 1ull;
-    const size_t chunk_words = static_cast<size_t>(S) * S * S;
-
-    for (int i = tid; i < 256; i += C::NT_ALL) sm.case_info[i] = HVX_REGULAR_CASE_INFO[i];
-    for (int i = tid; i < 256 * 12; i += C::NT_ALL) sm.vertex_edge[i] = HVX_REGULAR_VERTEX_EDGE[i / 12][i % 12];
-    for (int i = tid; i < 256; i += C::NT_ALL) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
-    for (int i = tid; i < BRW * C::BW; i += C::NT_ALL) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. zero padding
-    for (int i = tid; i < 64; i += C::NT_ALL) sm.tile_prefix[i] = ~0ull;                    // no tile has this tag yet
-    if (tid == 0) {
-        for (int i = 0; i < RS; ++i) {
-            mbar_init(&sm.full_bar[i], 1);
-            mbar_init(&sm.empty_bar[i], NW);
-        }
-        for (int i = 0; i < BRW; ++i) {
-            mbar_init(&sm.bits_bar[i], NW);
-            mbar_init(&sm.verdict_bar[i], PWS);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    // ---- PRODUCER warp (identical protocol to the first-generation kernel) --------------------
-    if (warp == NW) {
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t round = 0;
-            for (uint32_t k = 0;; ++k) {
-                const uint32_t id = atomicAdd(p.work_counter, 1u);
-                sm.chunk_ids[k & 3] = id;
-                if (id >= p.n_chunks) {
-                    mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
-                    mbar_arrive(&sm.full_bar[slot]);
-                    break;
-                }
-                const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words;
-                for (int j = 0; j < C::NSLAB; ++j) {
-                    mbar_wait(&sm.empty_bar[slot], (round & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(&sm.full_bar[slot], C::SLAB_BYTES);
-                    bulk_g2s(&sm.ring[slot][0], src + static_cast<size_t>(j) * C::SLAB_WORDS, C::SLAB_BYTES,
-                             &sm.full_bar[slot]);
-                    if (++slot == RS) {
-                        slot = 0;
-                        ++round;
-                    }
-                }
-            }
-        }
-        return;
-    }
-
-    // ---- CONSUMER warps ----------------------------------------------------------------------
-    const uint32_t* const ring_flat = &sm.ring[0][0];
-    uint32_t* const wl = sm.wlayer[warp];
-    uint8_t* const ow = sm.owner[warp];
-    int slot = 0;
-    uint32_t round = 0;
-    int rel_slot = 0;
-    uint32_t sc = 0, stc = 0;
-    uint32_t tile_seq = 0;   // tiles issued by this CTA so far (every warp counts identically)
-    int rot = 0;             // tile_seq % NW
-    const int p2_group = warp / PWS, p2_sub = warp % PWS;
-    const bool do_emit = p.mode == MODE_EXTRACT;
-
-    for (uint32_t kc = 0;; ++kc) {
-        uint32_t chunk = 0;
-        uint64_t dirty = 0;
-        uint32_t tmask = 0;
-        hvx_vertex* out_v = nullptr;
-        uint32_t* out_i = nullptr;
-        uint32_t chunk_tiles = 0, active_cells = 0;
-        uint32_t last_v = 0, last_i = 0;   // inclusive totals after this warp's latest tile of the chunk
-        int released = 0;
-        const uint32_t sc0 = sc, stc0 = stc;
-
-        auto release_through = [&](int last_slab) {
-            while (released <= last_slab) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty_bar[rel_slot]);
-                if (++rel_slot == RS) rel_slot = 0;
-                ++released;
-            }
-        };
-
-        // ---- P2: classify step st; publish active masks, row ranks and the warp's cell total ----
-        auto classify_step = [&](int st) {
-            if (p2_group != st % C::PG) return;
-            const uint32_t s1 = sc0 + static_cast<uint32_t>(st - 1), s2 = s1 + 1;
-            mbar_wait(&sm.bits_bar[s1 & (BRW - 1)], (s1 / BRW) & 1u);
-            mbar_wait(&sm.bits_bar[s2 & (BRW - 1)], (s2 / BRW) & 1u);
-            const int r = p2_sub * 32 + lane, zl = r / E, y = r % E, z = 2 * st - 2 + zl;
-            const uint32_t* bp0 = zl == 0 ? sm.bits[s1 & (BRW - 1)] : sm.bits[s2 & (BRW - 1)];
-            const int base0 = zl == 0 ? LW : 0;
-            const uint32_t* bp1 = sm.bits[s2 & (BRW - 1)];
-            const int base1 = zl == 0 ? 0 : LW;
-            const RowCorners rc = load_row_corners<C>(bp0, base0, bp1, base1, y);
-            const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
-            const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
-            uint64_t act = any & ~all & ROWMASK;
-            if (dirty != ~0ull) {
-                const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
-                uint64_t dirty_x = 0;
-#pragma unroll
-                for (int mx = 0; mx < 4; ++mx)
-                    if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
-                act &= dirty_x;
-            }
-            const uint32_t vi = stc0 + static_cast<uint32_t>(st - 1), ri = vi & (BRW - 1);
-            const uint32_t cnt = static_cast<uint32_t>(__popcll(act));
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
-            }
-            sm.active[ri][r] = act;
-            sm.rowrank[ri][r] = static_cast<uint16_t>(incl - cnt);
-            if (lane == 31) sm.wtot[ri][p2_sub] = incl;
-            __syncwarp();  // every lane's stores are ordered before lane 0's releasing arrive
-            if (lane == 0) mbar_arrive(&sm.verdict_bar[ri]);
-        };
-
-        // ---- one tile: 32 consecutive active cells of step st, handled by this warp alone --------
-        auto process_tile = [&](int st, uint32_t ri, uint32_t t, uint32_t n_cells, const uint32_t (&cum)[PWS]) {
-            const uint32_t seq = tile_seq + t;
-            const bool first = chunk_tiles + t == 0;
-            const uint32_t r = 32u * t + static_cast<uint32_t>(lane);
-            const bool valid = r < n_cells;
-            uint32_t rec = 0, packed = 0, info = 0;
-            if (valid) {
-                // locate: classifying warp -> row (largest row whose first rank <= mine) -> bit
-                uint32_t g = 0, rr = r;
-#pragma unroll
-                for (int i = 0; i + 1 < PWS; ++i)
-                    if (r >= cum[i]) {
-                        g = i + 1;
-                        rr = r - cum[i];
-                    }
-                const uint16_t* rk = sm.rowrank[ri] + 32u * g;
-                uint32_t i = 0;
-#pragma unroll
-                for (uint32_t b = 16; b != 0; b >>= 1)
-                    if (rk[i + b] <= rr) i += b;
-                uint32_t k = rr - rk[i];
-                const uint32_t row = 32u * g + i;
-                const uint64_t m = sm.active[ri][row];
-                uint32_t w = static_cast<uint32_t>(m);
-                int x = 0;
-                if (E == 64) {
-                    const uint32_t c = __popc(w);
-                    if (k >= c) {
-                        k -= c;
-                        w = static_cast<uint32_t>(m >> 32);
-                        x = 32;
-                    }
-                }
-                x += select_bit32(w, k);
-                const int zl = row / E, y = row % E;
-                const uint32_t* l0 = ring_flat + wl[zl + 1] + (y + 1) * S + (x + 1);
-                const uint32_t* l1 = ring_flat + wl[zl + 2] + (y + 1) * S + (x + 1);
-                const uint32_t c = (cw_solid(l0[0]) ? 1u : 0u) | (cw_solid(l0[1]) ? 2u : 0u) | (cw_solid(l0[S]) ? 4u : 0u) |
-                                   (cw_solid(l0[S + 1]) ? 8u : 0u) | (cw_solid(l1[0]) ? 16u : 0u) |
-                                   (cw_solid(l1[1]) ? 32u : 0u) | (cw_solid(l1[S]) ? 64u : 0u) |
-                                   (cw_solid(l1[S + 1]) ? 128u : 0u);
-                info = sm.case_info[c];
-                rec = static_cast<uint32_t>(x) | (row << 8) | (c << 16);
-                packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
-            }
-            uint32_t incl = packed;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t tot_v = total & 0xffffu, tot_i = total >> 16;
-            const uint32_t vo = (incl - packed) & 0xffffu, io = (incl - packed) >> 16;
-            // chained prefix: wait for the previous tile's inclusive totals, publish ours
-            uint32_t base_lo = 0, base_hi = 0;
-            if (lane == 0) {
-                uint64_t base = 0;
-                if (!first) {
-                    const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 63u];
-                    const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
-                    uint64_t got;
-                    do {
-                        got = *prev;
-                    } while ((got >> 44) != want);
-                    base = got & ((1ull << 44) - 1ull);
-                }
-                const uint64_t mine = base + static_cast<uint64_t>(tot_v) + (static_cast<uint64_t>(tot_i) << 22);
-                *const_cast<volatile uint64_t*>(&sm.tile_prefix[seq & 63u]) =
-                    mine | (static_cast<uint64_t>(seq & 0xfffffu) << 44);
-                base_lo = static_cast<uint32_t>(base);
-                base_hi = static_cast<uint32_t>(base >> 32);
-            }
-            base_lo = __shfl_sync(0xffffffffu, base_lo, 0);
-            base_hi = __shfl_sync(0xffffffffu, base_hi, 0);
-            const uint64_t base = static_cast<uint64_t>(base_lo) | (static_cast<uint64_t>(base_hi) << 32);
-            const uint32_t v_base = static_cast<uint32_t>(base & FIELD), i_base = static_cast<uint32_t>((base >> 22) & FIELD);
-            last_v = v_base + tot_v;
-            last_i = i_base + tot_i;
-            if (!do_emit) return;
-            if (valid) {
-                const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
-                for (uint32_t k = 0; k < nv; ++k) ow[vo + k] = static_cast<uint8_t>(lane);
-                const uint32_t first_vertex = v_base + vo, dst = i_base + io;
-                const uint4 row4 = *reinterpret_cast<const uint4*>(&sm.class_index[cls * 16]);
-                const uint32_t words[4] = {row4.x, row4.y, row4.z, row4.w};
-                if (dst + ni <= p.max_indices) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 15; ++j)
-                        if (j < ni) out_i[dst + j] = first_vertex + ((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
-                } else {
-                    for (uint32_t j = 0; j < ni; ++j)
-                        if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + ((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
-                }
-            }
-            __syncwarp();
-            auto layer_words = [&](int d) -> int { return static_cast<int>(wl[d]); };
-            const int z0 = 2 * st - 2;
-            for (uint32_t v0 = 0; v0 < tot_v; v0 += 32u) {
-                const uint32_t v = v0 + static_cast<uint32_t>(lane);
-                const bool on = v < tot_v;
-                const uint32_t o = on ? ow[v] : 0u;
-                const uint32_t cr = __shfl_sync(0xffffffffu, rec, o);
-                const uint32_t cvo = __shfl_sync(0xffffffffu, vo, o);
-                if (on && v_base + v < p.max_vertices) {
-                    const int x = cr & 63, rw = (cr >> 8) & 255, c = cr >> 16;
-                    const int zl = rw / E, y = rw % E;
-                    const uint32_t code = sm.vertex_edge[c * 12 + (v - cvo)];
-                    emit_regular_vertex<C>(ring_flat, layer_words, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
-                }
-            }
-            __syncwarp();  // the owner map is reused by this warp's next tile
-        };
-
-        // ---- P3: consume the verdict of step st; emit this warp's tiles; hand slab st-1 back ------
-        auto emit_step = [&](int st) {
-            const uint32_t vi = stc0 + static_cast<uint32_t>(st - 1), ri = vi & (BRW - 1);
-            mbar_wait(&sm.verdict_bar[ri], (vi / BRW) & 1u);
-            uint32_t cum[PWS];
-            uint32_t n_cells = 0;
-#pragma unroll
-            for (int i = 0; i < PWS; ++i) {
-                n_cells += sm.wtot[ri][i];
-                cum[i] = n_cells;
-            }
-            if (n_cells != 0) {
-                const uint32_t ntiles = (n_cells + 31u) >> 5;
-                uint32_t t = static_cast<uint32_t>(warp >= rot ? warp - rot : warp + NW - rot);
-                if (t < ntiles) {
-                    // ring word offsets of sample layers z0 .. z0+4: slab st-1 is the oldest not handed back
-                    __syncwarp();
-                    if (lane < 6) {
-                        int s2 = rel_slot + (lane >> 1);
-                        if (s2 >= RS) s2 -= RS;
-                        wl[lane] = static_cast<uint32_t>(s2 * C::SLAB_WORDS + (lane & 1) * LW);
-                    }
-                    __syncwarp();
-                    for (; t < ntiles; t += NW) process_tile(st, ri, t, n_cells, cum);
-                }
-                tile_seq += ntiles;
-                chunk_tiles += ntiles;
-                rot = static_cast<int>((static_cast<uint32_t>(rot) + ntiles) % NW);
-                active_cells += n_cells;
-            }
-            release_through(st - 1);
-        };
-
-        bool stop = false;
-        for (int j = 0; j < C::NSLAB; ++j) {
-            mbar_wait(&sm.full_bar[slot], round & 1u);
-            if (j == 0) {
-                chunk = sm.chunk_ids[kc & 3];
-                if (chunk >= p.n_chunks) {
-                    stop = true;
-                    break;
-                }
-                const ChunkDesc desc = p.descs[chunk];
-                dirty = desc.dirty_microbricks;
-                tmask = desc.transition_mask & 0x3fu;
-                out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
-                out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
-            }
-            if (p.mode == MODE_STREAM_ONLY) {
-                release_through(j);
-            } else {
-                {
-                    const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
-                    uint32_t* dst = sm.bits[sc & (BRW - 1)] + warp;
-                    short dens[C::BPW];
-#pragma unroll
-                    for (int k = 0; k < C::BPW; ++k) {
-                        const bool in_range = k * NW + NW <= C::FULL || warp < C::FULL - k * NW;
-                        dens[k] = in_range ? src[64 * NW * k] : short(1);
-                    }
-#pragma unroll
-                    for (int k = 0; k < C::BPW; ++k) {
-                        const uint32_t b = __ballot_sync(0xffffffffu, dens[k] <= 0);
-                        if (lane == 0 && (k * NW + NW <= C::FULL || warp < C::FULL - k * NW)) dst[NW * k] = b;
-                    }
-                    if (C::TAIL != 0 && warp == NW - 1) {
-                        const short* tail = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * C::FULL);
-                        const short d = lane < C::TAIL ? tail[2 * lane] : short(1);
-                        const uint32_t b = __ballot_sync(0xffffffffu, d <= 0);
-                        if (lane == 0) sm.bits[sc & (BRW - 1)][C::FULL] = b;
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.bits_bar[sc & (BRW - 1)]);
-                }
-                if (p.mode == MODE_BITS_ONLY) {
-                    release_through(j);
-                } else {
-                    if (j >= 2) classify_step(j - 1);
-                    if (j >= 3) emit_step(j - 2);
-                }
-            }
-            ++sc;
-            if (++slot == RS) {
-                slot = 0;
-                ++round;
-            }
-        }
-        if (stop) break;
-        if (p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY) {
-            classify_step(C::NSLAB - 1);
-            emit_step(C::NSLAB - 2);
-            emit_step(C::NSLAB - 1);
-            release_through(C::NSLAB - 1);
-            stc += C::NSLAB - 1;
-        }
-
-        // ---- chunk epilogue: written by the owner of the chunk's last tile (it holds the totals) ----
-        const int last_owner = chunk_tiles == 0 ? 0 : (rot == 0 ? NW - 1 : rot - 1);
-        if (warp == last_owner && lane == 0) {
-            const uint32_t v_tot = chunk_tiles == 0 ? 0u : last_v, i_tot = chunk_tiles == 0 ? 0u : last_i;
-            const uint32_t vo = v_tot > p.max_vertices ? 1u : 0u, io = i_tot > p.max_indices ? 1u : 0u;
-            const bool ok = !(vo | io) && do_emit;
-            hvx_emission_counters ec;
-            ec.required_vertices = v_tot;
-            ec.required_indices = i_tot;
-            ec.emitted_vertices = ok ? v_tot : 0u;
-            ec.emitted_indices = ok ? i_tot : 0u;
-            ec.vertex_overflow = vo;
-            ec.index_overflow = io;
-            ec.completed = 1u;
-            ec._pad = 0u;
-            p.counters[chunk] = ec;
-            hvx_classify_counters cc;
-            cc.visited_cells = static_cast<uint32_t>(__popcll(dirty)) * (C::QW * C::QW * C::QW);
-            cc.active_cells = active_cells;
-            cc.vertices = v_tot;
-            cc.triangles = i_tot / 3u;
-            p.classify[chunk] = cc;
-            hvx_range rg;
-            rg.first_vertex = chunk * p.max_vertices;
-            rg.vertex_count = ok ? v_tot : 0u;
-            rg.first_index = chunk * p.max_indices;
-            rg.index_count = ok ? i_tot : 0u;
-            p.ranges[chunk] = rg;
-        }
-    }
-}
-
-
 // =============================================================================================
-// Third-generation kernel: DECOUPLED front end / emission.
+// Second-generation kernel (the default): DECOUPLED front end / emission.
 //   * PWS FRONT warps do all per-slab work (sign bits of the slab, classification of step j =
 //     cell layers 2j-2, 2j-1, row ranks) and publish a per-step record in the ring slot of slab j,
 //     signalled on ready[slot].  They sync only among themselves (one named barrier per slab).
@@ -1426,7 +1097,6 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 }
             }
             __syncwarp();
-            auto layer_words = [&](int d) -> int { return static_cast<int>(wl[d]); };
             const int z0 = 2 * st - 2;
             for (uint32_t v0 = 0; v0 < tot_v; v0 += 32u) {
                 const uint32_t v = v0 + static_cast<uint32_t>(lane);
@@ -1438,7 +1108,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     const int x = cr & 63, rw = (cr >> 8) & 255, c = cr >> 16;
                     const int zl = rw / E, y = rw % E;
                     const uint32_t code = sm.vertex_edge[c * 12 + (v - cvo)];
-                    emit_regular_vertex<C>(ring_flat, layer_words, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
+                    emit_regular_vertex_fast<C>(ring_flat, wl, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
                 }
             }
             __syncwarp();  // the owner map is reused by this warp's next tile
@@ -1547,10 +1217,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
 
 template <class C, int GEN>
 cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
-    const size_t smem = GEN == 2 ? sizeof(SmemD<C>) : GEN == 1 ? sizeof(SmemW<C>) : sizeof(Smem<C>);
+    const size_t smem = GEN == 2 ? sizeof(SmemD<C>) : sizeof(Smem<C>);
     const int threads = GEN == 2 ? DecoupledCfg<C>::NT_ALL : C::NT_ALL;
-    auto* kernel = GEN == 2 ? regular_extract_decoupled_kernel<C>
-                            : GEN == 1 ? regular_extract_auton_kernel<C> : regular_extract_kernel<C>;
+    auto* kernel = GEN == 2 ? regular_extract_decoupled_kernel<C> : regular_extract_kernel<C>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
     int ctas_per_sm = 1;
@@ -1565,8 +1234,9 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
 
 using Cfg64 = Cfg<64, 2, 6, 16>;
 using Cfg32 = Cfg<32, 2, 10, 8>;
+using Cfg32D = Cfg<32, 1, 10, 6>;  // decoupled kernel at edge 32: 4 front + 6 emission + 1 producer warps, 2 CTAs / SM
 
-// Tuning variants (HVX_REGULAR_VARIANT=<n>, default 0); all produce identical output.
+// HVX_REGULAR_VARIANT=1 selects the first-generation kernel (identical output); default: decoupled.
 int variant_from_env() {
     const char* v = getenv("HVX_REGULAR_VARIANT");
     return v ? atoi(v) : 0;
@@ -1575,8 +1245,7 @@ int variant_from_env() {
 }  // namespace
 
 size_t regular_smem_bytes(int edge) {
-    return edge == 64 ? max(max(sizeof(Smem<Cfg64>), sizeof(SmemW<Cfg64>)), sizeof(SmemD<Cfg64>))
-                      : max(max(sizeof(Smem<Cfg32>), sizeof(SmemW<Cfg32>)), sizeof(SmemD<Cfg<32, 1, 10, 6>>));
+    return edge == 64 ? max(sizeof(Smem<Cfg64>), sizeof(SmemD<Cfg64>)) : max(sizeof(Smem<Cfg32>), sizeof(SmemD<Cfg32D>));
 }
 
 cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
@@ -1584,21 +1253,9 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     // debug records (per-cell words, offsets, scan blocks) only exist in the first-generation kernel
-    const int variant = p.cells != nullptr ? 0 : variant_from_env();
-    if (edge == 64) {
-        switch (variant) {
-            case 10: return launch_cfg<Cfg64, 1>(p, dev, stream);
-            case 20: return launch_cfg<Cfg64, 2>(p, dev, stream);
-            default: return launch_cfg<Cfg64, 0>(p, dev, stream);
-        }
-    }
-    if (edge == 32) {
-        switch (variant) {
-            case 10: return launch_cfg<Cfg32, 1>(p, dev, stream);
-            case 20: return launch_cfg<Cfg<32, 1, 10, 6>, 2>(p, dev, stream);
-            default: return launch_cfg<Cfg32, 0>(p, dev, stream);
-        }
-    }
+    const bool first_gen = p.cells != nullptr || variant_from_env() == 1;
+    if (edge == 64) return first_gen ? launch_cfg<Cfg64, 0>(p, dev, stream) : launch_cfg<Cfg64, 2>(p, dev, stream);
+    if (edge == 32) return first_gen ? launch_cfg<Cfg32, 0>(p, dev, stream) : launch_cfg<Cfg32D, 2>(p, dev, stream);
     return cudaErrorInvalidValue;
 }
 
