@@ -781,35 +781,56 @@ __device__ __forceinline__ int select_bit32(uint32_t w, uint32_t k) {
 }
 
 // =============================================================================================
-// Second-generation kernel (the default): DECOUPLED front end / emission.
-//   * PWS FRONT warps do all per-slab work (sign bits of the slab, classification of step j =
-//     cell layers 2j-2, 2j-1, row ranks) and publish a per-step record in the ring slot of slab j,
-//     signalled on ready[slot].  They sync only among themselves (one named barrier per slab).
-//   * NW EMISSION warps walk the steps in order, wait on ready[slot], and pull TILES of 32
-//     consecutive active cells from the step's counter (dynamic, so a warp that is still busy
-//     with an older tile never holds up a newer one).  A tile is handled by one warp alone, as in
-//     the warp-autonomous kernel; placement is the same chained prefix.  A warp arrives on
-//     empty[slot of slab j-1] when it leaves step j, so the slab ring itself is the run-ahead
-//     window: the front end classifies up to RS-3 steps ahead of the slowest emission warp and
-//     several steps' tiles are in flight at once.
+// Second-generation kernel (the default): DECOUPLED front end / emission with a work queue.
+//   * FW FRONT warps do all per-slab work.  Every front warp turns its share of slab j into sign
+//     bits; after one named barrier CW of them classify step j (cell layers 2j-2, 2j-1; one lane per
+//     cell row) and store the row masks and row ranks in the ring slot of slab j (rec_bar[slot]).
+//   * one SCHEDULER lane turns step records into work: a step WITH surface cells becomes an entry of
+//     a 16-deep work queue (q_bar[i] signals it); a step WITHOUT is finished on the spot.  It runs
+//     beside the front warps, so their per-slab loop has no serial section.
+//   * NW EMISSION warps sleep on the queue (a parked mbarrier wait costs no issue slots while the
+//     chunk is empty), walk its entries in order and pull TILES of TC consecutive active cells from
+//     the entry's counter.  A tile is handled by one warp alone: locate the cells (binary search
+//     over row ranks + k-th-set-bit select), cases from the bricks, warp scan of (vertices |
+//     indices), indices, then one lane per vertex through a warp-private owner map.  Placement
+//     across tiles is a chained prefix in shared memory: tile q polls tile q-1's inclusive totals
+//     (one 64-bit word tagged with q) and publishes its own before it starts writing.
+//   * slab s is handed back to the producer after THREE arrivals on empty[s]: "step s-1 done",
+//     "step s done", "step s+1 done" (the steps whose emission window contains it).  The scheduler
+//     makes them for empty and non-existent steps, the warp that finishes the last tile of a step
+//     makes them for that step.  The slab ring is therefore the run-ahead window: the front end
+//     classifies up to RS-2 slabs ahead of the oldest unfinished step and several steps' tiles are in
+//     flight at once.  q_free[i] (one arrival per emission warp) keeps the scheduler from reusing a
+//     queue entry somebody has not read yet.
 //   * chunk totals travel with the chain: whoever handles the last tile of a step stores the
-//     inclusive totals in chunk_total[] before publishing, emission warp 0 writes the counters.
+//     inclusive totals in chunk_total[] before publishing; a CHUNK_END queue entry tells one
+//     emission warp to wait for the final value and write the chunk's counter records.
 // =============================================================================================
+enum : uint32_t { QK_STEP = 0, QK_CHUNK_END = 1, QK_EXIT = 2 };
+
 template <class C>
 struct SmemD {
+    static constexpr int NQ = 16;
     alignas(128) uint32_t ring[C::RS][C::SLAB_WORDS];
+    // queue entry: [0] slot | st<<4 | tmask<<12 | chunk parity<<18 | first-of-chunk<<20 | parity of full[slot+1]<<21 |
+    // kind<<30, [1] chunk, [2] active cells, [3] first tile seq, [4..6] cumulative cells of front warps 0..2;
+    // CHUNK_END: [2] chunk's active cells, [3] last tile seq, [4],[5] dirty mask, [7] chunk has tiles
+    alignas(16) uint32_t queue[NQ][8];
     alignas(8) uint64_t full_bar[C::RS];
     uint64_t empty_bar[C::RS];
-    uint64_t ready_bar[C::RS];
+    uint64_t rec_bar[C::RS];               // step record of slab j complete (CW arrivals)
+    uint64_t q_bar[NQ];
+    uint64_t q_free[NQ];
     uint64_t active[C::RS][C::STEP_ROWS];  // per step (ring slot of its newest slab): active-cell bits per row
-    uint64_t tile_prefix[64];              // chained tile totals: vertices | indices<<22 | tag<<44
+    uint64_t tile_prefix[32];              // chained tile totals: vertices | indices<<22 | tag<<44
     uint64_t chunk_total[4];               // totals after the last tile of the newest finished step, same packing
     uint32_t bits[3][C::BW];               // solid bits of the last three slabs (front warps only)
-    uint32_t wtot[C::RS][C::PWS];          // active cells per front warp
-    uint32_t tile_ctr[C::RS];              // next tile of the step
+    uint32_t q_ctr[NQ];                    // next tile of the entry
+    uint32_t q_done[NQ];                   // finished tiles of the entry
+    uint32_t wtot[C::RS][C::PWS];          // active cells per classifying warp
     uint32_t wlayer[C::NW][8];             // per emission warp: ring word offset of sample layer z0 + d
     uint32_t chunk_ids[4];
-    uint16_t rowrank[C::RS][C::STEP_ROWS]; // first cell rank of a row, relative to its front warp
+    uint16_t rowrank[C::RS][C::STEP_ROWS]; // first cell rank of a row, relative to its classifying warp
     uint16_t case_info[256];
     alignas(16) uint8_t class_index[16 * 16];
     uint8_t vertex_edge[256 * 12];
@@ -820,7 +841,7 @@ template <class C>
 struct DecoupledCfg {
     static constexpr int CW = C::PWS;                          // classifying front warps (one lane per cell row)
     static constexpr int FW = 2 * C::PWS;                      // front warps; all of them turn slabs into sign bits
-    static constexpr int NT_ALL = (FW + C::NW + 1) * 32;       // front + emission + producer
+    static constexpr int NT_ALL = (FW + C::NW + 2) * 32;       // front + emission + producer + scheduler
     static constexpr int FB = (C::FULL + FW - 1) / FW;         // ballot blocks per front warp per slab
     static constexpr int PB = FB % 17 == 0 ? 17 : 18;          // loads in flight per batch
     // cells per tile: a typical surface cell has 4 vertices, so 30 cells fill four 32-lane vertex
@@ -828,6 +849,7 @@ struct DecoupledCfg {
     static constexpr int TC = 30;
     static_assert(C::STEP_ROWS == CW * 32, "one classifying lane per cell row");
     static_assert(C::FULL % FW == 0 && FB % PB == 0, "front warps split the slab's ballot blocks evenly");
+    static_assert(CW <= 4 && C::RS <= 15 && C::NSLAB <= 255, "queue entry packing");
 };
 
 template <class C>
@@ -838,7 +860,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     using D = DecoupledCfg<C>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int E = C::E, S = C::S, RS = C::RS, NW = C::NW, LW = C::LAYER_WORDS, FW = D::FW, CW = D::CW;
+    constexpr int E = C::E, S = C::S, RS = C::RS, NW = C::NW, LW = C::LAYER_WORDS, FW = D::FW, CW = D::CW, NQ = SM::NQ;
     constexpr uint64_t ROWMASK = E == 64 ? ~0ull : 0xffffffffull;
     constexpr uint64_t FIELD = (1ull << 22) - 1ull;
     const size_t chunk_words = static_cast<size_t>(S) * S * S;
@@ -847,13 +869,17 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     for (int i = tid; i < 256 * 12; i += D::NT_ALL) sm.vertex_edge[i] = HVX_REGULAR_VERTEX_EDGE[i / 12][i % 12];
     for (int i = tid; i < 256; i += D::NT_ALL) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
     for (int i = tid; i < 3 * C::BW; i += D::NT_ALL) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. zero padding
-    for (int i = tid; i < 64; i += D::NT_ALL) sm.tile_prefix[i] = ~0ull;                  // no tile has this tag yet
+    if (tid < 32) sm.tile_prefix[tid] = ~0ull;                                            // no tile has this tag yet
     if (tid < 4) sm.chunk_total[tid] = ~0ull;
     if (tid == 0) {
         for (int i = 0; i < RS; ++i) {
             mbar_init(&sm.full_bar[i], 1);
-            mbar_init(&sm.empty_bar[i], NW);
-            mbar_init(&sm.ready_bar[i], CW);
+            mbar_init(&sm.empty_bar[i], 3);
+            mbar_init(&sm.rec_bar[i], CW);
+        }
+        for (int i = 0; i < NQ; ++i) {
+            mbar_init(&sm.q_bar[i], 1);
+            mbar_init(&sm.q_free[i], NW);
         }
         mbar_fence_init();
     }
@@ -888,7 +914,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         return;
     }
 
-    // ---- FRONT warps: slab -> sign bits -> step record ------------------------------------------
+    // ---- FRONT warps: slab -> sign bits -> step record --------------------------------
     if (warp < FW) {
         int slot = 0;
         uint32_t round = 0;
@@ -935,45 +961,118 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(FW * 32) : "memory");  // the slab's bits are complete
                 if (warp < CW) {
-                uint32_t incl = 0, cnt = 0;
-                uint64_t act = 0;
-                const int r = warp * 32 + lane;
-                if (classify) {
-                    // step j = cell layers 2j-2, 2j-1: sample layers 2j-1 (slab j-1), 2j, 2j+1 (slab j)
-                    const int zl = r / E, y = r % E, z = 2 * j - 2 + zl;
-                    const uint32_t* bp0 = zl == 0 ? sm.bits[bprev] : sm.bits[bcur];
-                    const int base0 = zl == 0 ? LW : 0;
-                    const uint32_t* bp1 = sm.bits[bcur];
-                    const int base1 = zl == 0 ? 0 : LW;
-                    const RowCorners rc = load_row_corners<C>(bp0, base0, bp1, base1, y);
-                    const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
-                    const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
-                    act = any & ~all & ROWMASK;
-                    if (dirty != ~0ull) {
-                        const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
-                        uint64_t dirty_x = 0;
+                    uint32_t incl = 0;
+                    if (classify) {
+                        // step j = cell layers 2j-2, 2j-1: sample layers 2j-1 (slab j-1), 2j, 2j+1 (slab j)
+                        const int r = warp * 32 + lane, zl = r / E, y = r % E, z = 2 * j - 2 + zl;
+                        const uint32_t* bp0 = zl == 0 ? sm.bits[bprev] : sm.bits[bcur];
+                        const int base0 = zl == 0 ? LW : 0;
+                        const uint32_t* bp1 = sm.bits[bcur];
+                        const int base1 = zl == 0 ? 0 : LW;
+                        const RowCorners rc = load_row_corners<C>(bp0, base0, bp1, base1, y);
+                        const uint64_t any = rc.a00 | rc.b00 | rc.a10 | rc.b10 | rc.a01 | rc.b01 | rc.a11 | rc.b11;
+                        const uint64_t all = rc.a00 & rc.b00 & rc.a10 & rc.b10 & rc.a01 & rc.b01 & rc.a11 & rc.b11;
+                        uint64_t act = any & ~all & ROWMASK;
+                        if (dirty != ~0ull) {
+                            const uint32_t nib = static_cast<uint32_t>(dirty >> (4 * ((y / C::QW) + 4 * (z / C::QW)))) & 15u;
+                            uint64_t dirty_x = 0;
 #pragma unroll
-                        for (int mx = 0; mx < 4; ++mx)
-                            if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
-                        act &= dirty_x;
-                    }
-                    cnt = static_cast<uint32_t>(__popcll(act));
-                    incl = cnt;
+                            for (int mx = 0; mx < 4; ++mx)
+                                if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
+                            act &= dirty_x;
+                        }
+                        const uint32_t cnt = static_cast<uint32_t>(__popcll(act));
+                        incl = cnt;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += up;
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += up;
+                        }
+                        sm.active[slot][r] = act;
+                        sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
                     }
-                    sm.active[slot][r] = act;
-                    sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
-                }
-                if (lane == 31) sm.wtot[slot][warp] = incl;
-                if (tid == 0) sm.tile_ctr[slot] = 0u;
-                __syncwarp();  // every lane's stores are ordered before lane 0's releasing arrive
-                if (lane == 0) mbar_arrive(&sm.ready_bar[slot]);
+                    if (lane == 31) sm.wtot[slot][warp] = incl;
+                    __syncwarp();  // every lane's stores are ordered before lane 0's releasing arrive
+                    if (lane == 0) mbar_arrive(&sm.rec_bar[slot]);
                 }
                 bprev = bcur;
                 bcur = bcur == 2 ? 0 : bcur + 1;
+                if (++slot == RS) {
+                    slot = 0;
+                    ++round;
+                }
+            }
+        }
+    }
+
+    // ---- SCHEDULER warp: step records -> work queue / slab hand-back (one lane, off everybody's critical path) ----
+    if (warp == FW + NW + 1) {
+        if (lane != 0) return;
+        int slot = 0;
+        uint32_t round = 0;
+        uint32_t q_tail = 0, tile_total = 0;
+        auto publish = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6,
+                           uint32_t w7) {
+            const uint32_t qi = q_tail & (NQ - 1);
+            if (q_tail >= NQ) mbar_wait(&sm.q_free[qi], ((q_tail / NQ) - 1u) & 1u);  // every emission warp has left its last use
+            *reinterpret_cast<uint4*>(&sm.queue[qi][0]) = make_uint4(w0, w1, w2, w3);
+            *reinterpret_cast<uint4*>(&sm.queue[qi][4]) = make_uint4(w4, w5, w6, w7);
+            sm.q_ctr[qi] = 0u;
+            sm.q_done[qi] = 0u;
+            mbar_arrive(&sm.q_bar[qi]);  // release: the entry is visible to whoever sees the phase flip
+            ++q_tail;
+        };
+        for (uint32_t kc = 0;; ++kc) {
+            mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+            const uint32_t chunk = sm.chunk_ids[kc & 3];
+            if (chunk >= p.n_chunks) {
+                publish(QK_EXIT << 30, 0, 0, 0, 0, 0, 0, 0);
+                return;
+            }
+            const ChunkDesc desc = p.descs[chunk];
+            const uint64_t dirty = desc.dirty_microbricks;
+            const uint32_t tmask = desc.transition_mask & 0x3fu;
+            const uint32_t chunk_first_tile = tile_total;
+            uint32_t chunk_cells = 0;
+            bool prev_empty = false;
+            for (int j = 0; j < C::NSLAB; ++j) {
+                mbar_wait_parked(&sm.rec_bar[slot], round & 1u);
+                const int prev_slot = slot == 0 ? RS - 1 : slot - 1;
+                if (j == 0) {
+                    // slab 0 has no steps -1 and 0: make their arrivals; slab 1 gets "step 0 done" next round
+                    mbar_arrive(&sm.empty_bar[slot]);
+                    mbar_arrive(&sm.empty_bar[slot]);
+                    prev_empty = true;
+                } else {
+                    if (prev_empty) mbar_arrive(&sm.empty_bar[slot]);  // "step j-1 done" for slab j, now that it is current
+                    uint32_t cum[4] = {0, 0, 0, 0};
+                    uint32_t n = 0;
+#pragma unroll
+                    for (int i = 0; i < CW; ++i) {
+                        n += sm.wtot[slot][i];
+                        cum[i] = n;
+                    }
+                    if (n == 0) {
+                        mbar_arrive(&sm.empty_bar[slot]);       // "step j done" for slab j
+                        mbar_arrive(&sm.empty_bar[prev_slot]);  // "step j done" for slab j-1
+                        prev_empty = true;
+                    } else {
+                        const uint32_t next_parity = (slot + 1 == RS ? round + 1u : round) & 1u;
+                        const uint32_t w0 = static_cast<uint32_t>(slot) | (static_cast<uint32_t>(j) << 4) | (tmask << 12) |
+                                            ((kc & 3u) << 18) | ((tile_total == chunk_first_tile ? 1u : 0u) << 20) |
+                                            (next_parity << 21) | (QK_STEP << 30);
+                        publish(w0, chunk, n, tile_total, cum[0], cum[1], cum[2], 0u);
+                        tile_total += (n + D::TC - 1u) / D::TC;
+                        chunk_cells += n;
+                        prev_empty = false;
+                    }
+                }
+                if (j == C::NSLAB - 1) {
+                    mbar_arrive(&sm.empty_bar[slot]);  // the last slab has no step NSLAB
+                    publish((QK_CHUNK_END << 30) | ((kc & 3u) << 18), chunk, chunk_cells, tile_total - 1u,
+                            static_cast<uint32_t>(dirty), static_cast<uint32_t>(dirty >> 32), 0u,
+                            tile_total != chunk_first_tile ? 1u : 0u);
+                }
                 if (++slot == RS) {
                     slot = 0;
                     ++round;
@@ -987,237 +1086,211 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     const uint32_t* const ring_flat = &sm.ring[0][0];
     uint32_t* const wl = sm.wlayer[ew];
     uint8_t* const ow = sm.owner[ew];
-    int slot = 0;
-    uint32_t round = 0;
-    int rel_slot = 0;
-    uint32_t tile_seq = 0;   // tiles issued by this CTA before the current step (every warp counts identically)
     const bool do_emit = p.mode == MODE_EXTRACT;
 
-    for (uint32_t kc = 0;; ++kc) {
-        uint32_t chunk = 0;
-        uint64_t dirty = 0;
-        uint32_t tmask = 0;
-        hvx_vertex* out_v = nullptr;
-        uint32_t* out_i = nullptr;
-        uint32_t chunk_tiles = 0, active_cells = 0;
-
-        // ---- one tile: 32 consecutive active cells of step st (record in ring slot rs) -------------
-        auto process_tile = [&](int st, int rs, uint32_t t, uint32_t ntiles, uint32_t n_cells, const uint32_t (&cum)[CW]) {
-            const uint32_t seq = tile_seq + t;
-            const bool first = chunk_tiles + t == 0;
-            const uint32_t r = D::TC * t + static_cast<uint32_t>(lane);
-            const bool valid = lane < D::TC && r < n_cells;
-            uint32_t rec = 0, packed = 0, info = 0;
-            if (valid) {
-                // locate: front warp -> row (largest row whose first rank <= mine) -> k-th set bit
-                uint32_t g = 0, rr = r;
-#pragma unroll
-                for (int i = 0; i + 1 < CW; ++i)
-                    if (r >= cum[i]) {
-                        g = i + 1;
-                        rr = r - cum[i];
-                    }
-                const uint16_t* rk = sm.rowrank[rs] + 32u * g;
-                uint32_t i = 0;
-#pragma unroll
-                for (uint32_t b = 16; b != 0; b >>= 1)
-                    if (rk[i + b] <= rr) i += b;
-                uint32_t k = rr - rk[i];
-                const uint32_t row = 32u * g + i;
-                const uint64_t m = sm.active[rs][row];
-                uint32_t w = static_cast<uint32_t>(m);
-                int x = 0;
-                if (E == 64) {
-                    const uint32_t c = __popc(w);
-                    if (k >= c) {
-                        k -= c;
-                        w = static_cast<uint32_t>(m >> 32);
-                        x = 32;
-                    }
+    for (uint32_t k = 0;; ++k) {
+        const uint32_t qi = k & (NQ - 1);
+        mbar_wait_parked(&sm.q_bar[qi], (k / NQ) & 1u);
+        const uint4 e0 = *reinterpret_cast<const uint4*>(&sm.queue[qi][0]);
+        const uint4 e1 = *reinterpret_cast<const uint4*>(&sm.queue[qi][4]);
+        const uint32_t kind = e0.x >> 30;
+        if (kind == QK_EXIT) return;
+        const uint32_t chunk = e0.y, kcpar = (e0.x >> 18) & 3u;
+        if (kind == QK_CHUNK_END) {
+            // ---- chunk epilogue: one warp waits for the chain's final totals and writes the records ----
+            if (static_cast<int>(k % NW) == ew && lane == 0) {
+                uint32_t v_tot = 0, i_tot = 0;
+                if (e1.w != 0u) {
+                    const volatile uint64_t* tot = &sm.chunk_total[kcpar];
+                    const uint64_t want = static_cast<uint64_t>(e0.w & 0xfffffu);
+                    uint64_t got;
+                    do {
+                        got = *tot;
+                    } while ((got >> 44) != want);
+                    v_tot = static_cast<uint32_t>(got & FIELD);
+                    i_tot = static_cast<uint32_t>((got >> 22) & FIELD);
                 }
-                x += select_bit32(w, k);
-                const int zl = row / E, y = row % E;
-                const uint32_t* l0 = ring_flat + wl[zl + 1] + (y + 1) * S + (x + 1);
-                const uint32_t* l1 = ring_flat + wl[zl + 2] + (y + 1) * S + (x + 1);
-                const uint32_t c = (cw_solid(l0[0]) ? 1u : 0u) | (cw_solid(l0[1]) ? 2u : 0u) | (cw_solid(l0[S]) ? 4u : 0u) |
-                                   (cw_solid(l0[S + 1]) ? 8u : 0u) | (cw_solid(l1[0]) ? 16u : 0u) |
-                                   (cw_solid(l1[1]) ? 32u : 0u) | (cw_solid(l1[S]) ? 64u : 0u) |
-                                   (cw_solid(l1[S + 1]) ? 128u : 0u);
-                info = sm.case_info[c];
-                rec = static_cast<uint32_t>(x) | (row << 8) | (c << 16);
-                packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
+                const uint64_t dirty = static_cast<uint64_t>(e1.x) | (static_cast<uint64_t>(e1.y) << 32);
+                const uint32_t vo = v_tot > p.max_vertices ? 1u : 0u, io = i_tot > p.max_indices ? 1u : 0u;
+                const bool ok = !(vo | io) && do_emit;
+                hvx_emission_counters ec;
+                ec.required_vertices = v_tot;
+                ec.required_indices = i_tot;
+                ec.emitted_vertices = ok ? v_tot : 0u;
+                ec.emitted_indices = ok ? i_tot : 0u;
+                ec.vertex_overflow = vo;
+                ec.index_overflow = io;
+                ec.completed = 1u;
+                ec._pad = 0u;
+                p.counters[chunk] = ec;
+                hvx_classify_counters cc;
+                cc.visited_cells = static_cast<uint32_t>(__popcll(dirty)) * (C::QW * C::QW * C::QW);
+                cc.active_cells = e0.z;
+                cc.vertices = v_tot;
+                cc.triangles = i_tot / 3u;
+                p.classify[chunk] = cc;
+                hvx_range rg;
+                rg.first_vertex = chunk * p.max_vertices;
+                rg.vertex_count = ok ? v_tot : 0u;
+                rg.first_index = chunk * p.max_indices;
+                rg.index_count = ok ? i_tot : 0u;
+                p.ranges[chunk] = rg;
             }
-            __syncwarp();
-            uint32_t incl = packed;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t tot_v = total & 0xffffu, tot_i = total >> 16;
-            const uint32_t vo = (incl - packed) & 0xffffu, io = (incl - packed) >> 16;
-            // chained prefix: wait for the previous tile's inclusive totals, publish ours.  Every lane
-            // polls the same word (a broadcast read), so the warp never splits around the spin.
-            uint64_t base = 0;
-            if (!first) {
-                const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 63u];
-                const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
-                uint64_t got;
-                do {
-                    got = *prev;
-                } while ((got >> 44) != want);
-                base = got & ((1ull << 44) - 1ull);
-            }
-            if (lane == 0) {
-                const uint64_t mine = (base + static_cast<uint64_t>(tot_v) + (static_cast<uint64_t>(tot_i) << 22)) |
-                                      (static_cast<uint64_t>(seq & 0xfffffu) << 44);
-                if (t + 1 == ntiles) {  // totals so far; later steps overwrite, ordered along the chain
-                    *const_cast<volatile uint64_t*>(&sm.chunk_total[kc & 3]) = mine;
-                    __threadfence_block();
-                }
-                *const_cast<volatile uint64_t*>(&sm.tile_prefix[seq & 63u]) = mine;
-            }
-            __syncwarp();
-            if (!do_emit) return;
-            const uint32_t v_base = static_cast<uint32_t>(base & FIELD), i_base = static_cast<uint32_t>((base >> 22) & FIELD);
-            if (valid) {
-                const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
-                for (uint32_t k = 0; k < nv; ++k) ow[vo + k] = static_cast<uint8_t>(lane);
-                const uint32_t first_vertex = v_base + vo, dst = i_base + io;
-                const uint4 row4 = *reinterpret_cast<const uint4*>(&sm.class_index[cls * 16]);
-                const uint32_t words[4] = {row4.x, row4.y, row4.z, row4.w};
-                if (dst + ni <= p.max_indices) {
-#pragma unroll
-                    for (uint32_t j = 0; j < 15; ++j)
-                        if (j < ni) out_i[dst + j] = first_vertex + ((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
-                } else {
-                    for (uint32_t j = 0; j < ni; ++j)
-                        if (dst + j < p.max_indices) out_i[dst + j] = first_vertex + ((words[j >> 2] >> (8 * (j & 3))) & 0xffu);
-                }
-            }
-            __syncwarp();
-            const int z0 = 2 * st - 2;
-            for (uint32_t v0 = 0; v0 < tot_v; v0 += 32u) {
-                const uint32_t v = v0 + static_cast<uint32_t>(lane);
-                const bool on = v < tot_v;
-                const uint32_t o = on ? ow[v] : 0u;
-                const uint32_t cr = __shfl_sync(0xffffffffu, rec, o);
-                const uint32_t cvo = __shfl_sync(0xffffffffu, vo, o);
-                if (on && v_base + v < p.max_vertices) {
-                    const int x = cr & 63, rw = (cr >> 8) & 255, c = cr >> 16;
-                    const int zl = rw / E, y = rw % E;
-                    const uint32_t code = sm.vertex_edge[c * 12 + (v - cvo)];
-                    emit_regular_vertex_fast<C>(ring_flat, wl, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
-                }
-            }
-            __syncwarp();  // the owner map is reused by this warp's next tile
-        };
-
-        for (int j = 0; j < C::NSLAB; ++j) {
-            if (j == 0) {
-                mbar_wait_parked(&sm.full_bar[slot], round & 1u);
-                chunk = sm.chunk_ids[kc & 3];
-                if (chunk >= p.n_chunks) return;
-                const ChunkDesc desc = p.descs[chunk];
-                dirty = desc.dirty_microbricks;
-                tmask = desc.transition_mask & 0x3fu;
-                out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
-                out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
-            }
-            mbar_wait_parked(&sm.ready_bar[slot], round & 1u);
-            if (j >= 1) {
-                uint32_t cum[CW];
-                uint32_t n_cells = 0;
-#pragma unroll
-                for (int i = 0; i < CW; ++i) {
-                    n_cells += sm.wtot[slot][i];
-                    cum[i] = n_cells;
-                }
-                if (n_cells != 0) {
-                    const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
-                    if (*const_cast<volatile uint32_t*>(&sm.tile_ctr[slot]) < ntiles) {
-                        // the z gradient of the step's upper layer reads the first layer of slab j+1
-                        if (j + 1 < C::NSLAB) {
-                            const bool wrap = slot + 1 == RS;
-                            mbar_wait(&sm.full_bar[wrap ? 0 : slot + 1], (wrap ? round + 1u : round) & 1u);
-                        }
-                        // ring word offsets of sample layers z0 .. z0+4: slab j-1 is the oldest this warp still holds
-                        __syncwarp();
-                        if (lane < 6) {
-                            int s2 = rel_slot + (lane >> 1);
-                            if (s2 >= RS) s2 -= RS;
-                            wl[lane] = static_cast<uint32_t>(s2 * C::SLAB_WORDS + (lane & 1) * LW);
-                        }
-                        __syncwarp();
-                        for (;;) {
-                            uint32_t t = 0;
-                            if (lane == 0) t = atomicAdd(&sm.tile_ctr[slot], 1u);
-                            t = __shfl_sync(0xffffffffu, t, 0);
-                            if (t >= ntiles) break;
-                            process_tile(j, slot, t, ntiles, n_cells, cum);
-                        }
-                    }
-                    tile_seq += ntiles;
-                    chunk_tiles += ntiles;
-                    active_cells += n_cells;
+        } else {
+            const int slot = e0.x & 15u, st = (e0.x >> 4) & 255u;
+            const uint32_t tmask = (e0.x >> 12) & 63u, first_of_chunk = (e0.x >> 20) & 1u, next_parity = (e0.x >> 21) & 1u;
+            const uint32_t n_cells = e0.z, tile_base = e0.w;
+            const uint32_t cum[3] = {e1.x, e1.y, e1.z};
+            const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
+            if (*const_cast<volatile uint32_t*>(&sm.q_ctr[qi]) < ntiles) {
+                const int slot_m = slot == 0 ? RS - 1 : slot - 1, slot_p = slot + 1 == RS ? 0 : slot + 1;
+                // the z gradient of the step's upper layer reads the first layer of slab st+1
+                if (st + 1 < C::NSLAB) mbar_wait(&sm.full_bar[slot_p], next_parity);
+                // ring word offsets of sample layers z0 .. z0+4 (slabs st-1, st, st+1)
+                __syncwarp();
+                if (lane < 6) {
+                    const int s2 = lane < 2 ? slot_m : lane < 4 ? slot : slot_p;
+                    wl[lane] = static_cast<uint32_t>(s2 * C::SLAB_WORDS + (lane & 1) * LW);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.empty_bar[rel_slot]);  // slab j-1
-                if (++rel_slot == RS) rel_slot = 0;
+                hvx_vertex* const out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
+                uint32_t* const out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
+                const int z0 = 2 * st - 2;
+                for (;;) {
+                    uint32_t t = 0;
+                    if (lane == 0) t = atomicAdd(&sm.q_ctr[qi], 1u);
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    if (t >= ntiles) break;
+                    // ---- one tile: TC consecutive active cells of the step ---------------------------
+                    const uint32_t seq = tile_base + t;
+                    const bool first = first_of_chunk != 0u && t == 0u;
+                    const uint32_t r = D::TC * t + static_cast<uint32_t>(lane);
+                    const bool valid = lane < D::TC && r < n_cells;
+                    uint32_t rec = 0, packed = 0, info = 0;
+                    if (valid) {
+                        // locate: classifying warp -> row (largest row whose first rank <= mine) -> k-th set bit
+                        uint32_t g = 0, rr = r;
+#pragma unroll
+                        for (int i = 0; i + 1 < CW; ++i)
+                            if (r >= cum[i]) {
+                                g = i + 1;
+                                rr = r - cum[i];
+                            }
+                        const uint16_t* rk = sm.rowrank[slot] + 32u * g;
+                        uint32_t i = 0;
+#pragma unroll
+                        for (uint32_t b = 16; b != 0; b >>= 1)
+                            if (rk[i + b] <= rr) i += b;
+                        uint32_t kk = rr - rk[i];
+                        const uint32_t row = 32u * g + i;
+                        const uint64_t m = sm.active[slot][row];
+                        uint32_t w = static_cast<uint32_t>(m);
+                        int x = 0;
+                        if (E == 64) {
+                            const uint32_t c = __popc(w);
+                            if (kk >= c) {
+                                kk -= c;
+                                w = static_cast<uint32_t>(m >> 32);
+                                x = 32;
+                            }
+                        }
+                        x += select_bit32(w, kk);
+                        const int zl = row / E, y = row % E;
+                        const uint32_t* l0 = ring_flat + wl[zl + 1] + (y + 1) * S + (x + 1);
+                        const uint32_t* l1 = ring_flat + wl[zl + 2] + (y + 1) * S + (x + 1);
+                        const uint32_t c = (cw_solid(l0[0]) ? 1u : 0u) | (cw_solid(l0[1]) ? 2u : 0u) |
+                                           (cw_solid(l0[S]) ? 4u : 0u) | (cw_solid(l0[S + 1]) ? 8u : 0u) |
+                                           (cw_solid(l1[0]) ? 16u : 0u) | (cw_solid(l1[1]) ? 32u : 0u) |
+                                           (cw_solid(l1[S]) ? 64u : 0u) | (cw_solid(l1[S + 1]) ? 128u : 0u);
+                        info = sm.case_info[c];
+                        rec = static_cast<uint32_t>(x) | (row << 8) | (c << 16);
+                        packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
+                    }
+                    __syncwarp();
+                    uint32_t incl = packed;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += up;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    const uint32_t tot_v = total & 0xffffu, tot_i = total >> 16;
+                    const uint32_t vo = (incl - packed) & 0xffffu, io = (incl - packed) >> 16;
+                    // chained prefix: wait for the previous tile's inclusive totals, publish ours.  Every
+                    // lane polls the same word (a broadcast read), so the warp never splits around the spin.
+                    uint64_t base = 0;
+                    if (!first) {
+                        const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 31u];
+                        const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
+                        uint64_t got;
+                        do {
+                            got = *prev;
+                        } while ((got >> 44) != want);
+                        base = got & ((1ull << 44) - 1ull);
+                    }
+                    if (lane == 0) {
+                        const uint64_t mine = (base + static_cast<uint64_t>(tot_v) + (static_cast<uint64_t>(tot_i) << 22)) |
+                                              (static_cast<uint64_t>(seq & 0xfffffu) << 44);
+                        if (t + 1 == ntiles) {  // totals so far; later steps overwrite, ordered along the chain
+                            *const_cast<volatile uint64_t*>(&sm.chunk_total[kcpar]) = mine;
+                            __threadfence_block();
+                        }
+                        *const_cast<volatile uint64_t*>(&sm.tile_prefix[seq & 31u]) = mine;
+                    }
+                    __syncwarp();
+                    if (do_emit) {
+                        const uint32_t v_base = static_cast<uint32_t>(base & FIELD);
+                        const uint32_t i_base = static_cast<uint32_t>((base >> 22) & FIELD);
+                        if (valid) {
+                            const uint32_t nv = info & 15u, ni = 3u * ((info >> 4) & 15u), cls = info >> 8;
+                            for (uint32_t q = 0; q < nv; ++q) ow[vo + q] = static_cast<uint8_t>(lane);
+                            const uint32_t first_vertex = v_base + vo, dst = i_base + io;
+                            const uint4 row4 = *reinterpret_cast<const uint4*>(&sm.class_index[cls * 16]);
+                            const uint32_t words[4] = {row4.x, row4.y, row4.z, row4.w};
+                            if (dst + ni <= p.max_indices) {
+#pragma unroll
+                                for (uint32_t q = 0; q < 15; ++q)
+                                    if (q < ni) out_i[dst + q] = first_vertex + ((words[q >> 2] >> (8 * (q & 3))) & 0xffu);
+                            } else {
+                                for (uint32_t q = 0; q < ni; ++q)
+                                    if (dst + q < p.max_indices)
+                                        out_i[dst + q] = first_vertex + ((words[q >> 2] >> (8 * (q & 3))) & 0xffu);
+                            }
+                        }
+                        __syncwarp();
+                        for (uint32_t v0 = 0; v0 < tot_v; v0 += 32u) {
+                            const uint32_t v = v0 + static_cast<uint32_t>(lane);
+                            const bool on = v < tot_v;
+                            const uint32_t o = on ? ow[v] : 0u;
+                            const uint32_t cr = __shfl_sync(0xffffffffu, rec, o);
+                            const uint32_t cvo = __shfl_sync(0xffffffffu, vo, o);
+                            if (on && v_base + v < p.max_vertices) {
+                                const int x = cr & 63, rw = (cr >> 8) & 255, c = cr >> 16;
+                                const int zl = rw / E, y = rw % E;
+                                const uint32_t code = sm.vertex_edge[c * 12 + (v - cvo)];
+                                emit_regular_vertex_fast<C>(ring_flat, wl, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
+                            }
+                        }
+                    }
+                    __syncwarp();  // every ring read of the tile is done; the owner map is free again
+                    if (lane == 0 && atomicAdd(&sm.q_done[qi], 1u) + 1u == ntiles) {
+                        // last tile of the step: "step st done" for slabs st-1, st, st+1
+                        mbar_arrive(&sm.empty_bar[slot_m]);
+                        mbar_arrive(&sm.empty_bar[slot]);
+                        if (st + 1 < C::NSLAB) mbar_arrive(&sm.empty_bar[slot_p]);
+                    }
+                }
             }
-            if (++slot == RS) {
-                slot = 0;
-                ++round;
-            }
-        }
-        // ---- chunk epilogue (emission warp 0): totals arrive with the chain ------------------------
-        if (ew == 0 && lane == 0) {
-            uint32_t v_tot = 0, i_tot = 0;
-            if (chunk_tiles != 0) {
-                const volatile uint64_t* tot = &sm.chunk_total[kc & 3];
-                const uint64_t want = static_cast<uint64_t>((tile_seq - 1u) & 0xfffffu);
-                uint64_t got;
-                do {
-                    got = *tot;
-                } while ((got >> 44) != want);
-                v_tot = static_cast<uint32_t>(got & FIELD);
-                i_tot = static_cast<uint32_t>((got >> 22) & FIELD);
-            }
-            const uint32_t vo = v_tot > p.max_vertices ? 1u : 0u, io = i_tot > p.max_indices ? 1u : 0u;
-            const bool ok = !(vo | io) && do_emit;
-            hvx_emission_counters ec;
-            ec.required_vertices = v_tot;
-            ec.required_indices = i_tot;
-            ec.emitted_vertices = ok ? v_tot : 0u;
-            ec.emitted_indices = ok ? i_tot : 0u;
-            ec.vertex_overflow = vo;
-            ec.index_overflow = io;
-            ec.completed = 1u;
-            ec._pad = 0u;
-            p.counters[chunk] = ec;
-            hvx_classify_counters cc;
-            cc.visited_cells = static_cast<uint32_t>(__popcll(dirty)) * (C::QW * C::QW * C::QW);
-            cc.active_cells = active_cells;
-            cc.vertices = v_tot;
-            cc.triangles = i_tot / 3u;
-            p.classify[chunk] = cc;
-            hvx_range rg;
-            rg.first_vertex = chunk * p.max_vertices;
-            rg.vertex_count = ok ? v_tot : 0u;
-            rg.first_index = chunk * p.max_indices;
-            rg.index_count = ok ? i_tot : 0u;
-            p.ranges[chunk] = rg;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty_bar[rel_slot]);  // the chunk's last slab
-        if (++rel_slot == RS) rel_slot = 0;
+        if (lane == 0) mbar_arrive(&sm.q_free[qi]);
     }
 }
 
 template <class C, int GEN>
 cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
     const size_t smem = GEN == 2 ? sizeof(SmemD<C>) : sizeof(Smem<C>);
+    static_assert(sizeof(SmemD<C>) <= 232448 && sizeof(Smem<C>) <= 232448, "shared memory budget (227 KB per CTA)");
     const int threads = GEN == 2 ? DecoupledCfg<C>::NT_ALL : C::NT_ALL;
     auto* kernel = GEN == 2 ? regular_extract_decoupled_kernel<C> : regular_extract_kernel<C>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
