@@ -833,8 +833,9 @@ struct SmemD {
     uint16_t rowrank[C::RS][C::STEP_ROWS]; // first cell rank of a row, relative to its classifying warp
     uint16_t case_info[256];
     alignas(16) uint8_t class_index[16 * 16];
-    uint8_t vertex_edge[256 * 12];
-    uint8_t owner[C::NW][384];             // per emission warp: tile vertex -> lane (cell) that owns it
+    uint16_t vertex_base[256];             // first entry of a case's run in vertex_packed
+    uint8_t vertex_packed[1536];           // edge codes (corner pair) of every case's vertices, back to back
+    uint8_t owner[C::NW][360];             // per emission warp: tile vertex -> lane (cell) that owns it (TC * 12)
 };
 
 template <class C>
@@ -847,6 +848,7 @@ struct DecoupledCfg {
     // cells per tile: a typical surface cell has 4 vertices, so 30 cells fill four 32-lane vertex
     // passes (~120 vertices); 32 cells would spill a handful of vertices into a fifth
     static constexpr int TC = 30;
+    static_assert(TC * 12 <= 360, "owner map size");
     static_assert(C::STEP_ROWS == CW * 32, "one classifying lane per cell row");
     static_assert(C::FULL % FW == 0 && FB % PB == 0, "front warps split the slab's ballot blocks evenly");
     static_assert(CW <= 4 && C::RS <= 15 && C::NSLAB <= 255, "queue entry packing");
@@ -866,7 +868,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     const size_t chunk_words = static_cast<size_t>(S) * S * S;
 
     for (int i = tid; i < 256; i += D::NT_ALL) sm.case_info[i] = HVX_REGULAR_CASE_INFO[i];
-    for (int i = tid; i < 256 * 12; i += D::NT_ALL) sm.vertex_edge[i] = HVX_REGULAR_VERTEX_EDGE[i / 12][i % 12];
+    for (int i = tid; i < 256; i += D::NT_ALL) sm.vertex_base[i] = HVX_REGULAR_VERTEX_BASE[i];
+    for (int i = tid; i < 1536; i += D::NT_ALL) sm.vertex_packed[i] = HVX_REGULAR_VERTEX_PACKED[i];
     for (int i = tid; i < 256; i += D::NT_ALL) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
     for (int i = tid; i < 3 * C::BW; i += D::NT_ALL) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. zero padding
     if (tid < 32) sm.tile_prefix[tid] = ~0ull;                                            // no tile has this tag yet
@@ -1166,7 +1169,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     const bool first = first_of_chunk != 0u && t == 0u;
                     const uint32_t r = D::TC * t + static_cast<uint32_t>(lane);
                     const bool valid = lane < D::TC && r < n_cells;
-                    uint32_t rec = 0, packed = 0, info = 0;
+                    uint32_t rec = 0, packed = 0, info = 0, vbase = 0;
                     if (valid) {
                         // locate: classifying warp -> row (largest row whose first rank <= mine) -> k-th set bit
                         uint32_t g = 0, rr = r;
@@ -1203,6 +1206,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                            (cw_solid(l1[0]) ? 16u : 0u) | (cw_solid(l1[1]) ? 32u : 0u) |
                                            (cw_solid(l1[S]) ? 64u : 0u) | (cw_solid(l1[S + 1]) ? 128u : 0u);
                         info = sm.case_info[c];
+                        vbase = sm.vertex_base[c];
                         rec = static_cast<uint32_t>(x) | (row << 8) | (c << 16);
                         packed = (info & 15u) | ((3u * ((info >> 4) & 15u)) << 16);
                     }
@@ -1216,6 +1220,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
                     const uint32_t tot_v = total & 0xffffu, tot_i = total >> 16;
                     const uint32_t vo = (incl - packed) & 0xffffu, io = (incl - packed) >> 16;
+                    const uint32_t vo_vb = vo | (vbase << 9);  // what a vertex lane needs from its cell: first vertex, code run
                     // chained prefix: wait for the previous tile's inclusive totals, publish ours.  Every
                     // lane polls the same word (a broadcast read), so the warp never splits around the spin.
                     uint64_t base = 0;
@@ -1263,11 +1268,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             const bool on = v < tot_v;
                             const uint32_t o = on ? ow[v] : 0u;
                             const uint32_t cr = __shfl_sync(0xffffffffu, rec, o);
-                            const uint32_t cvo = __shfl_sync(0xffffffffu, vo, o);
+                            const uint32_t cvv = __shfl_sync(0xffffffffu, vo_vb, o);
                             if (on && v_base + v < p.max_vertices) {
-                                const int x = cr & 63, rw = (cr >> 8) & 255, c = cr >> 16;
+                                const int x = cr & 63, rw = (cr >> 8) & 255;
                                 const int zl = rw / E, y = rw % E;
-                                const uint32_t code = sm.vertex_edge[c * 12 + (v - cvo)];
+                                const uint32_t code = sm.vertex_packed[(cvv >> 9) + (v - (cvv & 511u))];
                                 emit_regular_vertex_fast<C>(ring_flat, wl, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
                             }
                         }
@@ -1307,7 +1312,8 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
 
 using Cfg64 = Cfg<64, 2, 6, 16>;
 using Cfg32 = Cfg<32, 2, 10, 8>;
-using Cfg32D = Cfg<32, 1, 10, 6>;  // decoupled kernel at edge 32: 4 front + 6 emission + 1 producer warps, 2 CTAs / SM
+using Cfg64D = Cfg<64, 1, 6, 20>;  // decoupled kernel at edge 64: 8 front + 20 emission + producer + scheduler warps
+using Cfg32D = Cfg<32, 1, 10, 8>;  // decoupled kernel at edge 32: 4 front + 8 emission + producer + scheduler warps, 2 CTAs / SM
 
 // HVX_REGULAR_VARIANT=1 selects the first-generation kernel (identical output); default: decoupled.
 int variant_from_env() {
@@ -1318,7 +1324,7 @@ int variant_from_env() {
 }  // namespace
 
 size_t regular_smem_bytes(int edge) {
-    return edge == 64 ? max(sizeof(Smem<Cfg64>), sizeof(SmemD<Cfg64>)) : max(sizeof(Smem<Cfg32>), sizeof(SmemD<Cfg32D>));
+    return edge == 64 ? max(sizeof(Smem<Cfg64>), sizeof(SmemD<Cfg64D>)) : max(sizeof(Smem<Cfg32>), sizeof(SmemD<Cfg32D>));
 }
 
 cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
@@ -1327,7 +1333,7 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     if (e != cudaSuccess) return e;
     // debug records (per-cell words, offsets, scan blocks) only exist in the first-generation kernel
     const bool first_gen = p.cells != nullptr || variant_from_env() == 1;
-    if (edge == 64) return first_gen ? launch_cfg<Cfg64, 0>(p, dev, stream) : launch_cfg<Cfg64, 2>(p, dev, stream);
+    if (edge == 64) return first_gen ? launch_cfg<Cfg64, 0>(p, dev, stream) : launch_cfg<Cfg64D, 2>(p, dev, stream);
     if (edge == 32) return first_gen ? launch_cfg<Cfg32, 0>(p, dev, stream) : launch_cfg<Cfg32D, 2>(p, dev, stream);
     return cudaErrorInvalidValue;
 }
