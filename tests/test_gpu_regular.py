@@ -223,3 +223,55 @@ def test_batch_of_mixed_chunks(edge):
     with pytest.raises(H.BatchCapacity):
         batch.extract_regular(np.zeros((n + 1) * (edge + 2) ** 3, dtype=np.uint32), n + 1)
     batch.close()
+
+
+@pytest.mark.parametrize("edge,n", [(64, 592), (32, 1184)])
+def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, n, monkeypatch):
+    """Race detector for the asynchronous (decoupled) kernel at a size where every SM walks several chunks.
+
+    A terrain batch (surface and empty chunks mixed, random transition masks, a few partially dirty
+    chunks) is extracted three times with the default kernel and once with the first-generation
+    kernel (CTA-wide barriers, HVX_REGULAR_VARIANT=1): counters, ranges and every mesh byte must be
+    identical, and a sample of chunks must equal the oracle.
+    """
+    rng = np.random.default_rng(7)
+    side = int(round(n ** 0.5)) + 1
+    pages = np.array([[x - side // 2, -1 if (x + z) % 3 else 0, z - side // 2] for z in range(side) for x in range(side)][:n],
+                     dtype=np.int64)
+    batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=49_152 if edge == 64 else 12_288,
+                                  max_indices=73_728 if edge == 64 else 18_432)
+    batch.fill_density(O.FIELD_TERRAIN_FBM, pages)
+    masks = [int(m) for m in rng.integers(0, 64, n)]
+    dirty = [ALL] * n
+    for i in range(0, n, 17):
+        dirty[i] = int(rng.integers(1, 1 << 62))
+    gens = [1000 + i for i in range(n)]
+
+    def run():
+        batch.extract_regular(None, n, generation=gens, transition_mask=masks, dirty_microbricks=dirty)
+        c, r = batch.counters(n).copy(), batch.ranges(n).copy()
+        v, i, packed = batch.ctx.read_meshes(0, 0, n)
+        return c, r, v.copy(), i.copy(), packed.copy()
+
+    first = run()
+    assert int(first[0]["vertex_overflow"].sum()) == 0 and int(first[0]["completed"].sum()) == n
+    assert int(first[0]["emitted_vertices"].astype(np.int64).sum()) > 100 * n
+    for _ in range(2):
+        again = run()
+        for a, b in zip(first, again):
+            assert a.tobytes() == b.tobytes()
+    monkeypatch.setenv("HVX_REGULAR_VARIANT", "1")
+    old = run()
+    monkeypatch.delenv("HVX_REGULAR_VARIANT")
+    for a, b in zip(first, old):
+        assert a.tobytes() == b.tobytes()
+    # a sample of chunks against the oracle (surface chunks included)
+    picks = [int(k) for k in np.argsort(-first[0]["emitted_vertices"].astype(np.int64))[:3]] + [0, n - 1]
+    for k in picks:
+        s = O.fixture_fill(O.FIELD_TERRAIN_FBM, [int(t) for t in pages[k]], edge=edge)
+        want = O.extract_regular(s, edge=edge, transition_mask=masks[k], dirty_microbricks=dirty[k], debug=False)
+        r = first[4][k]
+        assert r["vertex_count"] == len(want.vertices) and r["index_count"] == len(want.indices), k
+        assert_vertices_equal(first[2][r["first_vertex"]:r["first_vertex"] + r["vertex_count"]], want.vertices, f"chunk {k}")
+        assert np.array_equal(first[3][r["first_index"]:r["first_index"] + r["index_count"]], want.indices), k
+    batch.close()
