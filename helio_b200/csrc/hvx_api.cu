@@ -7,6 +7,7 @@
 // Ownership follows the reference: the ctx owns every device buffer, the caller borrows inputs
 // for the duration of the call, outputs are overwritten by the next dispatch.
 #include <cstdarg>
+#include <cstdint>
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
@@ -29,6 +30,12 @@ struct hvx_ctx {
     ChunkDesc* d_descs = nullptr;
     int64_t* d_pages = nullptr;
     uint8_t* d_lod = nullptr;
+    // fBm terrain fill: distinct (x, z, lod) columns of the batch and their shared height maps
+    uint32_t* d_col_index = nullptr;  // [max_chunks] chunk -> column
+    long long* d_col_xz = nullptr;    // [max_chunks][2]
+    uint8_t* d_col_lod = nullptr;     // [max_chunks]
+    float* d_heights = nullptr;       // [heights_cols][(E+2)^2], grown on demand
+    uint64_t heights_cols = 0;
     uint32_t* d_work = nullptr;       // [2] work counters (regular, transition)
     hvx_range* d_packed = nullptr;    // [max_chunks] packed placement for hvx_read_meshes
     void* pack_v = nullptr;           // staging for hvx_read_meshes
@@ -269,7 +276,62 @@ int run_fill(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t
                                   cudaMemcpyHostToDevice, ctx->stream));
     if (lod) HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_lod, lod, n, cudaMemcpyHostToDevice, ctx->stream));
     else HVX_CUDA(ctx, cudaMemsetAsync(ctx->d_lod, 0, n, ctx->stream));
-    FillParams p{kind, n, ctx->d_pages, ctx->d_lod, out};
+    FillParams p{kind, n, ctx->d_pages, ctx->d_lod, out, nullptr, nullptr};
+    if (kind == 16 && !slabs) {
+        // the fBm height depends only on (x, z): evaluate it once per distinct column of the batch
+        // (open-addressing hash on (x, z, lod); the batch is at most max_chunks long)
+        uint32_t table_size = 16;
+        while (table_size < 2u * n) table_size <<= 1;
+        std::vector<uint32_t> table(table_size, UINT32_MAX);
+        std::vector<uint32_t> col_index(n);
+        std::vector<long long> col_xz;
+        std::vector<uint8_t> col_lod;
+        col_xz.reserve(2ull * n);
+        col_lod.reserve(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint8_t l = lod ? lod[i] : 0;
+            const long long x = page_xyz[3 * i], z = page_xyz[3 * i + 2];
+            uint64_t h = static_cast<uint64_t>(x) * 0x9E3779B97F4A7C15ull ^ static_cast<uint64_t>(z) * 0xC2B2AE3D27D4EB4Full ^ l;
+            h ^= h >> 29;
+            uint32_t slot = static_cast<uint32_t>(h) & (table_size - 1);
+            for (;; slot = (slot + 1) & (table_size - 1)) {
+                const uint32_t c = table[slot];
+                if (c == UINT32_MAX) {
+                    table[slot] = static_cast<uint32_t>(col_lod.size());
+                    col_index[i] = table[slot];
+                    col_xz.push_back(x);
+                    col_xz.push_back(z);
+                    col_lod.push_back(l);
+                    break;
+                }
+                if (col_xz[2 * c] == x && col_xz[2 * c + 1] == z && col_lod[c] == l) {
+                    col_index[i] = c;
+                    break;
+                }
+            }
+        }
+        const uint64_t n_cols = col_lod.size(), s = ctx->cfg.edge + 2;
+        if (n_cols > ctx->heights_cols) {
+            if (ctx->d_heights) {
+                HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                cudaFree(ctx->d_heights);
+                ctx->allocated -= ctx->heights_cols * s * s * sizeof(float);
+                ctx->d_heights = nullptr;
+                ctx->heights_cols = 0;
+            }
+            if ((rc = small_alloc(ctx, &ctx->d_heights, n_cols * s * s))) return rc;
+            ctx->heights_cols = n_cols;
+        }
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_col_index, col_index.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_col_xz, col_xz.data(), col_xz.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_col_lod, col_lod.data(), n_cols, cudaMemcpyHostToDevice, ctx->stream));
+        cudaError_t eh = launch_terrain_heights(static_cast<int>(ctx->cfg.edge), ctx->d_col_xz, ctx->d_col_lod,
+                                                static_cast<uint32_t>(n_cols), ctx->d_heights, ctx->stream);
+        if (eh != cudaSuccess) return cuda_fail(ctx, eh, "launch_terrain_heights");
+        ctx->launches += 1;
+        p.heights = ctx->d_heights;
+        p.col_index = ctx->d_col_index;
+    }
     cudaError_t e = slabs ? launch_fill_slabs(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream)
                           : launch_fill_samples(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_fill");
@@ -367,6 +429,9 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((rc = small_alloc(ctx, &ctx->d_descs, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_col_index, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_col_xz, 2ull * c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_col_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_work, 4))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_packed, c.max_chunks))) return bail(rc);
     for (int id = HVX_BUF_REGULAR_VERTICES; id <= HVX_BUF_TRANSITION_BLOCKS; ++id)  // meshlet arenas stay lazy
@@ -385,6 +450,10 @@ void hvx_destroy(hvx_ctx* ctx) {
     cudaFree(ctx->d_descs);
     cudaFree(ctx->d_pages);
     cudaFree(ctx->d_lod);
+    cudaFree(ctx->d_col_index);
+    cudaFree(ctx->d_col_xz);
+    cudaFree(ctx->d_col_lod);
+    cudaFree(ctx->d_heights);
     cudaFree(ctx->d_work);
     cudaFree(ctx->d_packed);
     cudaFree(ctx->pack_v);

@@ -57,6 +57,10 @@ struct FillParams {
     const int64_t* page_xyz;  // [n][3] device
     const uint8_t* lod;       // [n] device
     uint32_t* out;
+    // fBm terrain only (kind 16, sample fill): shared height maps of the batch's distinct (x, z, lod)
+    // columns, heights[col][(E+2)][(E+2)], and each chunk's column; NULL = compute per chunk
+    const float* heights;
+    const uint32_t* col_index;
 };
 
 struct MeshletParams {
@@ -84,6 +88,8 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
 cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_samples(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_terrain_heights(int edge, const long long* col_xz, const uint8_t* col_lod, uint32_t n_cols, float* heights,
+                                   cudaStream_t stream);
 cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
 cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,
