@@ -6,11 +6,14 @@
 // (PV/src/transvoxel_transition.rs:189-270, 412-424, 504-559), including the *0.5 on gradients
 // that the WGSL omits, so results are bit-identical to the oracle.
 //
-// One CTA owns one chunk at a time (atomic queue) and walks its faces in index order, each face
-// v-major / u-fastest in steps of NT cells, so the running prefix inside the CTA reproduces the
-// reference's face-major order without any cross-CTA scan.  Layer 1 of a slab is read once,
-// coalesced (a warp's 9-sample patches cover three contiguous 65-word row segments); layers 0
-// and 2 are touched only around active cells for the outward gradient.  Slab rows are 4*(2E+3)
+// One CTA owns one chunk at a time (atomic queue) and walks its faces in index order.  A whole face
+// is classified at once: every thread owns a row segment of CPT consecutive cells (v-major /
+// u-fastest, the reference's face-local order), loads its 3 x (2 CPT + 1) layer-1 samples with all
+// loads in flight, and one block scan per face gives the ordered placement -- the running prefix
+// inside the CTA reproduces the reference's face-major order without any cross-CTA scan.  Vertices
+// are then emitted one thread per vertex (owner thread by binary search over the scanned prefix).
+// Layer 1 of a slab is read once, coalesced; layers 0 and 2 are touched only around active cells
+// for the outward gradient.  Slab rows are 4*(2E+3)
 // bytes, not 16-byte multiples, so this path uses plain vector-width-1 loads through L1 rather
 // than bulk copies.
 #include "hvx_device.cuh"
@@ -42,27 +45,21 @@ struct TCfg {
     static constexpr int W = 2 * E_ + 3;             // slab edge
     static constexpr int FACE_WORDS = W * W * 3;     // one face slab
     static constexpr int FACE_CELLS = E_ * E_;
-    static constexpr int STEPS = FACE_CELLS / NT_;   // NT consecutive cells (v-major) per step
-    static_assert(FACE_CELLS % NT_ == 0 && NT_ % 256 == 0, "steps must align with 256-cell scan blocks");
+    static constexpr int CPT = FACE_CELLS / NT_;     // consecutive cells (one row segment) per thread
+    static_assert(FACE_CELLS % NT_ == 0 && E_ % CPT == 0 && CPT <= 8 && 256 % CPT == 0, "a thread owns a row segment");
 };
 
 template <class C>
 struct TSmem {
-    uint32_t cell_rec[C::NT];        // case | u<<9 | v<<16   (u, v < 64)
-    uint32_t cell_off[C::NT];        // step-local exclusive vertex | index<<16
-    uint16_t owner[C::NT * 12];      // vertex -> cell slot | k<<10
-    uint32_t scan_sums[40], scan_prefix[40];
+    uint64_t thread_pre[C::NT + 1];  // exclusive prefix per thread: vertices | indices<<16 | active cells<<34
+    uint64_t scan_sums[40], scan_prefix[40];
+    uint32_t thread_nv[C::NT];       // vertex counts of a thread's CPT cells, 4 bits each
+    uint16_t cases[C::FACE_CELLS];   // 9-bit case of every cell of the face being processed
     uint32_t chunk_id;
     uint16_t case_info[512];
     uint8_t vertex_edge[512 * 12];
     uint8_t class_index[56 * 36];
 };
-
-// 9-bit case weights, PV/src/transvoxel.rs:20-22 (not row-major after sample 2)
-__device__ __forceinline__ uint32_t case_weight(int i) {
-    const uint32_t w[9] = {0x001, 0x002, 0x004, 0x080, 0x100, 0x008, 0x040, 0x020, 0x010};
-    return w[i];
-}
 
 template <class C>
 __device__ __forceinline__ void emit_transition_vertex(const uint32_t* __restrict__ slab, int face, int cu, int cv,
@@ -127,11 +124,13 @@ template <class C>
 __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const TransitionParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TSmem<C>& sm = *reinterpret_cast<TSmem<C>*>(smem_raw);
-    constexpr int E = C::E, W = C::W, NT = C::NT;
+    constexpr int E = C::E, W = C::W, NT = C::NT, CPT = C::CPT, NS = 2 * CPT + 1;
     const int tid = threadIdx.x;
     for (int i = tid; i < 512; i += NT) sm.case_info[i] = HVX_TRANSITION_CASE_INFO[i];
     for (int i = tid; i < 512 * 12; i += NT) sm.vertex_edge[i] = HVX_TRANSITION_VERTEX_EDGE[i / 12][i % 12];
     for (int i = tid; i < 56 * 36; i += NT) sm.class_index[i] = HVX_TRANSITION_CLASS_INDEX[i / 36][i % 36];
+    // this thread's CPT cells of a face: one row segment, u fastest (face-local linear order)
+    const int cell0 = tid * CPT, cv = cell0 / E, cu0 = cell0 % E;
 
     for (;;) {
         __syncthreads();
@@ -164,76 +163,113 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
                 continue;
             }
             const uint32_t* slab = chunk_slabs + static_cast<size_t>(face) * C::FACE_WORDS;
-            for (int step = 0; step < C::STEPS; ++step) {
-                const int cell = step * NT + tid;  // face-local linear, u fastest
-                const int cu = cell % E, cv = cell / E;
-                // ---- classify: 9 samples of layer 1 ------------------------------------------
-                uint32_t c = 0;
-                {
-                    const uint32_t* row = slab + W * W + (2 * cv + 1) * W + (2 * cu + 1);
+            // ---- classify the whole face: 3 rows x (2 CPT + 1) layer-1 samples per thread, all loads
+            //      in flight at once; a cell's 9 signs are 3-bit windows of the three row masks -----
+            uint32_t rows[3] = {0u, 0u, 0u};
+            {
+                const uint32_t* base = slab + W * W + (2 * cv + 1) * W + (2 * cu0 + 1);
+                uint32_t w[3][NS];
 #pragma unroll
-                    for (int i = 0; i < 9; ++i)
-                        if (cw_solid(__ldg(row + (i / 3) * W + (i % 3)))) c |= case_weight(i);
-                }
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) w[r][k] = __ldg(base + r * W + k);
+#pragma unroll
+                for (int r = 0; r < 3; ++r)
+#pragma unroll
+                    for (int k = 0; k < NS; ++k) rows[r] |= cw_solid(w[r][k]) ? (1u << k) : 0u;
+            }
+            uint32_t cases[CPT], nv_word = 0, tot_v = 0, tot_i = 0, tot_a = 0;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const uint32_t t0 = (rows[0] >> (2 * j)) & 7u, t1 = (rows[1] >> (2 * j)) & 7u, t2 = (rows[2] >> (2 * j)) & 7u;
+                // case weights 1,2,4 / 0x80,0x100,8 / 0x40,0x20,0x10 (PV/src/transvoxel.rs:20-22)
+                const uint32_t c = t0 | ((t1 & 3u) << 7) | ((t1 & 4u) << 1) | ((t2 & 1u) << 6) | ((t2 & 2u) << 4) | ((t2 & 4u) << 2);
+                cases[j] = c;
                 const uint32_t info = sm.case_info[c];
-                const uint32_t nv = info & 15u, nt = (info >> 4) & 15u, class_code = info >> 8;
-                uint32_t tot;
-                const uint32_t off = block_exclusive_scan<NT>(nv | ((3u * nt) << 16), sm.scan_sums, sm.scan_prefix, tot);
-                const uint32_t step_v = tot & 0xffffu, step_i = tot >> 16;
-                const uint32_t vo = off & 0xffffu, io = off >> 16;
-                const uint32_t n_act = __syncthreads_count(nv != 0);
-                active_cells += n_act;
-                sm.cell_rec[tid] = c | (cu << 9) | (cv << 16);
-                sm.cell_off[tid] = off;
-                for (uint32_t k = 0; k < nv; ++k) sm.owner[vo + k] = static_cast<uint16_t>(tid | (k << 10));
-                // ---- indices: per-case inverse flip then the global flip => raw order iff inverse
-                {
-                    const uint32_t first_vertex = v_base + vo, dst = i_base + io;
-                    const uint8_t* tri = &sm.class_index[(class_code & 0x7fu) * 36];
-                    const bool inverse = (class_code & 0x80u) != 0;
-                    for (uint32_t tr = 0; tr < nt; ++tr) {
-                        const uint32_t a = tri[3 * tr], b1 = tri[3 * tr + 1], c1 = tri[3 * tr + 2];
-                        const uint32_t second = inverse ? b1 : c1, third = inverse ? c1 : b1;
-                        const uint32_t d = dst + 3 * tr;
-                        if (d + 2 < p.max_indices) {
-                            out_i[d] = first_vertex + a;
-                            out_i[d + 1] = first_vertex + second;
-                            out_i[d + 2] = first_vertex + third;
+                const uint32_t nv = info & 15u, nt = (info >> 4) & 15u;
+                nv_word |= nv << (4 * j);
+                tot_v += nv;
+                tot_i += 3u * nt;
+                tot_a += nv != 0u ? 1u : 0u;
+                sm.cases[cell0 + j] = static_cast<uint16_t>(c);
+            }
+            sm.thread_nv[tid] = nv_word;
+            uint64_t face_tot;
+            const uint64_t mine = static_cast<uint64_t>(tot_v) | (static_cast<uint64_t>(tot_i) << 16) | (static_cast<uint64_t>(tot_a) << 34);
+            const uint64_t pre = block_exclusive_scan<NT>(mine, sm.scan_sums, sm.scan_prefix, face_tot);
+            sm.thread_pre[tid] = pre;
+            if (tid == 0) sm.thread_pre[NT] = face_tot;
+            const uint32_t face_v = static_cast<uint32_t>(face_tot & 0xffffu), face_i = static_cast<uint32_t>((face_tot >> 16) & 0x3ffffu);
+            active_cells += static_cast<uint32_t>(face_tot >> 34);
+            __syncthreads();
+            // ---- indices (+ debug records): each thread walks its own cells -------------------------
+            {
+                uint32_t vo = static_cast<uint32_t>(pre & 0xffffu), io = static_cast<uint32_t>((pre >> 16) & 0x3ffffu);
+                const uint64_t bpre = sm.thread_pre[(tid / (256 / CPT)) * (256 / CPT)];  // start of this cell's 256-cell scan block
+                const uint32_t bvo = static_cast<uint32_t>(bpre & 0xffffu), bio = static_cast<uint32_t>((bpre >> 16) & 0x3ffffu);
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const uint32_t info = sm.case_info[cases[j]];
+                    const uint32_t nv = info & 15u, nt = (info >> 4) & 15u, class_code = info >> 8;
+                    if (nt != 0u) {
+                        // per-case inverse flip then the global flip => raw order iff inverse
+                        const uint32_t first_vertex = v_base + vo, dst = i_base + io;
+                        const uint8_t* tri = &sm.class_index[(class_code & 0x7fu) * 36];
+                        const bool inverse = (class_code & 0x80u) != 0;
+                        for (uint32_t tr = 0; tr < nt; ++tr) {
+                            const uint32_t a = tri[3 * tr], b1 = tri[3 * tr + 1], c1 = tri[3 * tr + 2];
+                            const uint32_t second = inverse ? b1 : c1, third = inverse ? c1 : b1;
+                            const uint32_t d = dst + 3 * tr;
+                            if (d + 2 < p.max_indices) {
+                                out_i[d] = first_vertex + a;
+                                out_i[d + 1] = first_vertex + second;
+                                out_i[d + 2] = first_vertex + third;
+                            }
                         }
                     }
-                }
-                __syncthreads();
-                if (debug) {
-                    const size_t lin = cell_base + static_cast<size_t>(face) * C::FACE_CELLS + cell;
-                    *reinterpret_cast<uint4*>(&p.cells[lin]) =
-                        make_uint4(c | (class_code << 9) | (nv << 17) | (nt << 21) | 0x80000000u, glo, ghi, 0u);
-                    const uint32_t boff = sm.cell_off[(tid / 256) * 256];
-                    *reinterpret_cast<uint4*>(&p.offsets[lin]) =
-                        make_uint4(vo - (boff & 0xffffu), io - (boff >> 16), glo, ghi);
-                    if (tid % 256 == 0) {
-                        const uint32_t nxt = tid + 256 < NT ? sm.cell_off[tid + 256] : tot;
-                        hvx_scan_block blk;
-                        blk.vertex_count = (nxt & 0xffffu) - (boff & 0xffffu);
-                        blk.index_count = (nxt >> 16) - (boff >> 16);
-                        blk.first_vertex = v_base + (boff & 0xffffu);
-                        blk.first_index = i_base + (boff >> 16);
-                        p.blocks[block_base + (face * C::FACE_CELLS + cell) / 256] = blk;
+                    if (debug) {
+                        const size_t lin = cell_base + static_cast<size_t>(face) * C::FACE_CELLS + cell0 + j;
+                        *reinterpret_cast<uint4*>(&p.cells[lin]) =
+                            make_uint4(cases[j] | (class_code << 9) | (nv << 17) | (nt << 21) | 0x80000000u, glo, ghi, 0u);
+                        *reinterpret_cast<uint4*>(&p.offsets[lin]) = make_uint4(vo - bvo, io - bio, glo, ghi);
                     }
+                    vo += nv;
+                    io += 3u * nt;
                 }
-                // ---- vertices: one thread per vertex -------------------------------------------
-                for (uint32_t v = tid; v < step_v; v += NT) {
-                    const uint32_t o = sm.owner[v];
-                    const uint32_t slot = o & 1023u, k = o >> 10;
-                    const uint32_t cr = sm.cell_rec[slot];
-                    const uint32_t cc = cr & 511u;
-                    const int u2 = (cr >> 9) & 127, v2 = cr >> 16;
-                    if (v_base + v < p.max_vertices)
-                        emit_transition_vertex<C>(slab, face, u2, v2, sm.vertex_edge[cc * 12 + k], out_v + v_base + v);
+                if (debug && (cell0 % 256) == 0) {
+                    const uint64_t nxt = sm.thread_pre[tid + 256 / CPT];
+                    hvx_scan_block blk;
+                    blk.vertex_count = static_cast<uint32_t>(nxt & 0xffffu) - bvo;
+                    blk.index_count = static_cast<uint32_t>((nxt >> 16) & 0x3ffffu) - bio;
+                    blk.first_vertex = v_base + bvo;
+                    blk.first_index = i_base + bio;
+                    p.blocks[block_base + (face * C::FACE_CELLS + cell0) / 256] = blk;
                 }
-                v_base += step_v;
-                i_base += step_i;
-                __syncthreads();
             }
+            // ---- vertices: one thread per vertex; owner thread by binary search over the prefix,
+            //      owner cell by walking that thread's 4-bit vertex counts ---------------------------
+            for (uint32_t v = tid; v < face_v; v += NT) {
+                uint32_t lo = 0;
+#pragma unroll
+                for (uint32_t step = NT / 2; step != 0; step >>= 1)
+                    if (static_cast<uint32_t>(sm.thread_pre[lo + step] & 0xffffu) <= v) lo += step;
+                uint32_t k = v - static_cast<uint32_t>(sm.thread_pre[lo] & 0xffffu);
+                uint32_t nvw = sm.thread_nv[lo];
+                uint32_t j = 0;
+                while (k >= (nvw & 15u)) {
+                    k -= nvw & 15u;
+                    nvw >>= 4;
+                    ++j;
+                }
+                const uint32_t cell = lo * CPT + j;
+                const uint32_t cc = sm.cases[cell];
+                if (v_base + v < p.max_vertices)
+                    emit_transition_vertex<C>(slab, face, static_cast<int>(cell % E), static_cast<int>(cell / E),
+                                              sm.vertex_edge[cc * 12 + k], out_v + v_base + v);
+            }
+            v_base += face_v;
+            i_base += face_i;
+            __syncthreads();  // thread_pre / thread_nv / cases are rewritten by the next face
         }
         if (tid == 0) {
             const uint32_t vo = v_base > p.max_vertices ? 1u : 0u, io = i_base > p.max_indices ? 1u : 0u;
