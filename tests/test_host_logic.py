@@ -188,3 +188,28 @@ def test_partition_is_deterministic_balanced_and_lod_aware():
     assert H.chunk_cost(64, 0) == 4 * 66 ** 3 and H.chunk_cost(32, 0x3F) == 4 * 34 ** 3 + 6 * 12 * 67 * 67
     uniform = H.partition_chunks(np.full(4096, 7, dtype=np.uint64), 8)
     assert np.array_equal(np.bincount(uniform), np.full(8, 512)) and np.array_equal(uniform[:16], np.arange(16) % 8)
+
+
+def test_packed_vertex_table_is_the_row_table_without_its_unused_tails():
+    """The regular kernel reads edge codes from a packed copy (shared memory is scarce): same data."""
+    import re
+    from pathlib import Path
+    text = (Path(__file__).resolve().parent.parent / "helio_b200" / "csrc" / "transvoxel_tables.inc").read_text()
+
+    def table(name):
+        body = re.search(name + r"(?:\[\d+\])+\s*=\s*\{(.*?)\};", text, re.S).group(1)
+        return [int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", body)]
+
+    info, rows = table("HVX_REGULAR_CASE_INFO"), table("HVX_REGULAR_VERTEX_EDGE")
+    base, packed = table("HVX_REGULAR_VERTEX_BASE"), table("HVX_REGULAR_VERTEX_PACKED")
+    assert len(info) == 256 and len(rows) == 256 * 12 and len(base) == 256 and len(packed) == 1536
+    at = 0
+    for case in range(256):
+        nv = info[case] & 15
+        assert base[case] == at
+        assert packed[at:at + nv] == rows[case * 12:case * 12 + nv]
+        for code in packed[at:at + nv]:       # an edge joins corner c0 to c0 + one bit (what the vertex code relies on)
+            c0, c1 = code >> 4, code & 15
+            assert c1 > c0 and (c0 ^ c1) in (1, 2, 4) and c1 < 8
+        at += nv
+    assert at == 1536
