@@ -46,6 +46,9 @@ struct TCfg {
     static constexpr int FACE_WORDS = W * W * 3;     // one face slab
     static constexpr int FACE_CELLS = E_ * E_;
     static constexpr int CPT = FACE_CELLS / NT_;     // consecutive cells (one row segment) per thread
+    static constexpr int RW = 2 * E_ + 1;            // layer-1 samples a cell row touches (columns 1 .. 2E+1)
+    static constexpr int RW32 = (RW + 31) / 32;      // ... in 32-sample ballot words
+    static_assert(32 * CPT == 4 * E_, "a warp owns exactly four cell rows");
     static_assert(FACE_CELLS % NT_ == 0 && E_ % CPT == 0 && CPT <= 8 && 256 % CPT == 0, "a thread owns a row segment");
 };
 
@@ -54,6 +57,8 @@ struct TSmem {
     uint64_t thread_pre[C::NT + 1];  // exclusive prefix per thread: vertices | indices<<16 | active cells<<34
     uint64_t scan_sums[40], scan_prefix[40];
     uint32_t thread_nv[C::NT];       // vertex counts of a thread's CPT cells, 4 bits each
+    uint32_t thread_nt[C::NT];       // triangle counts, 4 bits each
+    uint32_t rowbits[C::NT / 32][9][C::RW32 + 1];  // per warp: solid bits of its 9 layer-1 sample rows
     uint16_t cases[C::FACE_CELLS];   // 9-bit case of every cell of the face being processed
     uint32_t chunk_id;
     uint16_t case_info[512];
@@ -130,7 +135,7 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
     for (int i = tid; i < 512 * 12; i += NT) sm.vertex_edge[i] = HVX_TRANSITION_VERTEX_EDGE[i / 12][i % 12];
     for (int i = tid; i < 56 * 36; i += NT) sm.class_index[i] = HVX_TRANSITION_CLASS_INDEX[i / 36][i % 36];
     // this thread's CPT cells of a face: one row segment, u fastest (face-local linear order)
-    const int cell0 = tid * CPT, cv = cell0 / E, cu0 = cell0 % E;
+    const int cell0 = tid * CPT;
 
     for (;;) {
         __syncthreads();
@@ -163,22 +168,40 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
                 continue;
             }
             const uint32_t* slab = chunk_slabs + static_cast<size_t>(face) * C::FACE_WORDS;
-            // ---- classify the whole face: 3 rows x (2 CPT + 1) layer-1 samples per thread, all loads
-            //      in flight at once; a cell's 9 signs are 3-bit windows of the three row masks -----
-            uint32_t rows[3] = {0u, 0u, 0u};
+            // ---- classify the whole face.  A warp owns four cell rows = nine layer-1 sample rows; it
+            //      loads them coalesced (lane = column, all loads in flight), one ballot per 32 samples
+            //      turns them into bit rows in shared memory, and a cell's 9 signs are 3-bit windows of
+            //      three bit rows ------------------------------------------------------------------
+            uint32_t rows[3];
             {
-                const uint32_t* base = slab + W * W + (2 * cv + 1) * W + (2 * cu0 + 1);
-                uint32_t w[3][NS];
+                const int warp = tid >> 5, lane = tid & 31;
+                const uint32_t* base = slab + W * W + (2 * (warp * 4) + 1) * W + 1;
+                uint32_t w[9][C::RW32];
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < 9; ++r)
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) w[r][k] = __ldg(base + r * W + k);
+                    for (int c = 0; c < C::RW32; ++c) {
+                        const int col = 32 * c + lane;
+                        w[r][c] = col < C::RW ? __ldg(base + r * W + col) : 0x7fffu;  // padding reads as air
+                    }
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+                for (int r = 0; r < 9; ++r)
 #pragma unroll
-                    for (int k = 0; k < NS; ++k) rows[r] |= cw_solid(w[r][k]) ? (1u << k) : 0u;
+                    for (int c = 0; c < C::RW32; ++c) {
+                        const uint32_t b = __ballot_sync(0xffffffffu, cw_solid(w[r][c]));
+                        if (lane == 0) sm.rowbits[warp][r][c] = b;
+                    }
+                if (lane < 9) sm.rowbits[warp][lane][C::RW32] = 0u;
+                __syncwarp();
+                const int lv = lane / (E / CPT), bit = 2 * CPT * (lane % (E / CPT));
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const uint32_t* rb = sm.rowbits[warp][2 * lv + r] + (bit >> 5);
+                    rows[r] = __funnelshift_r(rb[0], rb[1], bit & 31) & ((1u << NS) - 1u);
+                }
+                __syncwarp();
             }
-            uint32_t cases[CPT], nv_word = 0, tot_v = 0, tot_i = 0, tot_a = 0;
+            uint32_t cases[CPT], nv_word = 0, nt_word = 0, tot_v = 0, tot_i = 0, tot_a = 0;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const uint32_t t0 = (rows[0] >> (2 * j)) & 7u, t1 = (rows[1] >> (2 * j)) & 7u, t2 = (rows[2] >> (2 * j)) & 7u;
@@ -188,12 +211,14 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
                 const uint32_t info = sm.case_info[c];
                 const uint32_t nv = info & 15u, nt = (info >> 4) & 15u;
                 nv_word |= nv << (4 * j);
+                nt_word |= nt << (4 * j);
                 tot_v += nv;
                 tot_i += 3u * nt;
                 tot_a += nv != 0u ? 1u : 0u;
                 sm.cases[cell0 + j] = static_cast<uint16_t>(c);
             }
             sm.thread_nv[tid] = nv_word;
+            sm.thread_nt[tid] = nt_word;
             uint64_t face_tot;
             const uint64_t mine = static_cast<uint64_t>(tot_v) | (static_cast<uint64_t>(tot_i) << 16) | (static_cast<uint64_t>(tot_a) << 34);
             const uint64_t pre = block_exclusive_scan<NT>(mine, sm.scan_sums, sm.scan_prefix, face_tot);
@@ -202,8 +227,8 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
             const uint32_t face_v = static_cast<uint32_t>(face_tot & 0xffffu), face_i = static_cast<uint32_t>((face_tot >> 16) & 0x3ffffu);
             active_cells += static_cast<uint32_t>(face_tot >> 34);
             __syncthreads();
-            // ---- indices (+ debug records): each thread walks its own cells -------------------------
-            {
+            // ---- debug records: each thread walks its own cells --------------------------------------
+            if (debug) {
                 uint32_t vo = static_cast<uint32_t>(pre & 0xffffu), io = static_cast<uint32_t>((pre >> 16) & 0x3ffffu);
                 const uint64_t bpre = sm.thread_pre[(tid / (256 / CPT)) * (256 / CPT)];  // start of this cell's 256-cell scan block
                 const uint32_t bvo = static_cast<uint32_t>(bpre & 0xffffu), bio = static_cast<uint32_t>((bpre >> 16) & 0x3ffffu);
@@ -211,32 +236,14 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
                 for (int j = 0; j < CPT; ++j) {
                     const uint32_t info = sm.case_info[cases[j]];
                     const uint32_t nv = info & 15u, nt = (info >> 4) & 15u, class_code = info >> 8;
-                    if (nt != 0u) {
-                        // per-case inverse flip then the global flip => raw order iff inverse
-                        const uint32_t first_vertex = v_base + vo, dst = i_base + io;
-                        const uint8_t* tri = &sm.class_index[(class_code & 0x7fu) * 36];
-                        const bool inverse = (class_code & 0x80u) != 0;
-                        for (uint32_t tr = 0; tr < nt; ++tr) {
-                            const uint32_t a = tri[3 * tr], b1 = tri[3 * tr + 1], c1 = tri[3 * tr + 2];
-                            const uint32_t second = inverse ? b1 : c1, third = inverse ? c1 : b1;
-                            const uint32_t d = dst + 3 * tr;
-                            if (d + 2 < p.max_indices) {
-                                out_i[d] = first_vertex + a;
-                                out_i[d + 1] = first_vertex + second;
-                                out_i[d + 2] = first_vertex + third;
-                            }
-                        }
-                    }
-                    if (debug) {
-                        const size_t lin = cell_base + static_cast<size_t>(face) * C::FACE_CELLS + cell0 + j;
-                        *reinterpret_cast<uint4*>(&p.cells[lin]) =
-                            make_uint4(cases[j] | (class_code << 9) | (nv << 17) | (nt << 21) | 0x80000000u, glo, ghi, 0u);
-                        *reinterpret_cast<uint4*>(&p.offsets[lin]) = make_uint4(vo - bvo, io - bio, glo, ghi);
-                    }
+                    const size_t lin = cell_base + static_cast<size_t>(face) * C::FACE_CELLS + cell0 + j;
+                    *reinterpret_cast<uint4*>(&p.cells[lin]) =
+                        make_uint4(cases[j] | (class_code << 9) | (nv << 17) | (nt << 21) | 0x80000000u, glo, ghi, 0u);
+                    *reinterpret_cast<uint4*>(&p.offsets[lin]) = make_uint4(vo - bvo, io - bio, glo, ghi);
                     vo += nv;
                     io += 3u * nt;
                 }
-                if (debug && (cell0 % 256) == 0) {
+                if ((cell0 % 256) == 0) {
                     const uint64_t nxt = sm.thread_pre[tid + 256 / CPT];
                     hvx_scan_block blk;
                     blk.vertex_count = static_cast<uint32_t>(nxt & 0xffffu) - bvo;
@@ -244,6 +251,38 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
                     blk.first_vertex = v_base + bvo;
                     blk.first_index = i_base + bio;
                     p.blocks[block_base + (face * C::FACE_CELLS + cell0) / 256] = blk;
+                }
+            }
+            // ---- indices: one thread per TRIANGLE (owner thread by binary search over the index prefix,
+            //      owner cell by walking that thread's 4-bit counts) ------------------------------------
+            for (uint32_t tr = tid; 3u * tr < face_i; tr += NT) {
+                const uint32_t want = 3u * tr;
+                uint32_t lo = 0;
+#pragma unroll
+                for (uint32_t step = NT / 2; step != 0; step >>= 1)
+                    if (static_cast<uint32_t>((sm.thread_pre[lo + step] >> 16) & 0x3ffffu) <= want) lo += step;
+                const uint64_t tp = sm.thread_pre[lo];
+                uint32_t k = tr - static_cast<uint32_t>((tp >> 16) & 0x3ffffu) / 3u;  // triangle within the thread's cells
+                uint32_t first_vertex = v_base + static_cast<uint32_t>(tp & 0xffffu);
+                uint32_t ntw = sm.thread_nt[lo], nvw = sm.thread_nv[lo];
+                uint32_t j = 0;
+                while (k >= (ntw & 15u)) {
+                    k -= ntw & 15u;
+                    first_vertex += nvw & 15u;
+                    ntw >>= 4;
+                    nvw >>= 4;
+                    ++j;
+                }
+                const uint32_t class_code = sm.case_info[sm.cases[lo * CPT + j]] >> 8;
+                // per-case inverse flip then the global flip => raw order iff inverse
+                const uint8_t* tri = &sm.class_index[(class_code & 0x7fu) * 36 + 3u * k];
+                const uint32_t a = tri[0], b1 = tri[1], c1 = tri[2];
+                const bool inverse = (class_code & 0x80u) != 0;
+                const uint32_t d = i_base + want;
+                if (d + 2 < p.max_indices) {
+                    out_i[d] = first_vertex + a;
+                    out_i[d + 1] = first_vertex + (inverse ? b1 : c1);
+                    out_i[d + 2] = first_vertex + (inverse ? c1 : b1);
                 }
             }
             // ---- vertices: one thread per vertex; owner thread by binary search over the prefix,
