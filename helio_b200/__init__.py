@@ -6,7 +6,7 @@ extractor objects.  Importing the package does not load the library; creating an
 does, and fails loudly if it is missing -- there is no CPU fallback.
 """
 from . import _ffi
-from .context import (CELL_OFFSET_DTYPE, CELL_RECORD_DTYPE, CLASSIFY_COUNTERS_DTYPE, EMISSION_COUNTERS_DTYPE,
+from .context import (GATHER_COUNTERS_DTYPE, CELL_OFFSET_DTYPE, CELL_RECORD_DTYPE, CLASSIFY_COUNTERS_DTYPE, EMISSION_COUNTERS_DTYPE,
                       MESHLET_BOUNDS_DTYPE, MESHLET_DTYPE, RANGE_DTYPE, TERRAIN_MESHLET_BUILD_INDICES, SCAN_BLOCK_DTYPE, TRANSITION_COUNTERS_DTYPE, VERTEX_DTYPE, Context, make_descs)
 from .errors import (AddressError, BatchCapacity, CudaError, DeviceLimit, FinestLodHasNoFinerNeighbor, HvxError,
                      InvalidExtractionCapacity, SampleCount, TerrainLodTopologyError, TransitionDeviceLimit,
@@ -16,6 +16,8 @@ from .extractor import (EXTRACTION_SAMPLE_COUNT, TRANSITION_ALL_FACE_SLAB_SAMPLE
                         TRANSVOXEL_SCAN_WORKGROUP_SIZE, ChunkBatchExtractor, ResourceStats, TransvoxelGpuClassifier,
                         TransvoxelGpuExtractor, TransvoxelGpuExtractorConfig, TransvoxelGpuTransitionExtractor,
                         TransvoxelGpuTransitionExtractorConfig)
+from .gather import (GATHER_JOB_DTYPE, PAGE_TABLE_ENTRY_DTYPE, RESIDENCY_UNIFORM_DTYPE, GpuLookupKey, GpuSurfaceSampler,
+                     PageTable, PageTableError, gather_job, residency_uniform)
 from .lod import HorizonLodFixturePlan, TerrainLodTopology, TerrainLodTopologyStats, chunk_cost, partition_chunks
 from .types import (MAX_ADDRESSABLE_LOD, PAGE_EDGE, TRANSITION_FACE_MASK, CellWord, ExtractionFixtureKind,
                     GpuTransvoxelCell, GpuTransvoxelTransitionCell, PageKey, TransitionFace)

@@ -39,7 +39,7 @@ HVX_CFG_DEBUG_RECORDS = 1
  BUF_TRANSITION_INDICES, BUF_TRANSITION_COUNTERS, BUF_TRANSITION_RANGES, BUF_TRANSITION_CELLS,
  BUF_TRANSITION_OFFSETS, BUF_TRANSITION_BLOCKS, BUF_REGULAR_MESHLETS, BUF_REGULAR_MESHLET_BOUNDS,
  BUF_REGULAR_MESHLET_COUNTS, BUF_TRANSITION_MESHLETS, BUF_TRANSITION_MESHLET_BOUNDS,
- BUF_TRANSITION_MESHLET_COUNTS) = range(23)
+ BUF_TRANSITION_MESHLET_COUNTS, BUF_GATHER_COUNTERS, BUF_GATHER_INDIRECT) = range(25)
 
 
 class Config(C.Structure):
@@ -73,7 +73,7 @@ EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
     "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count",
     "hvx_fill_density", "hvx_fill_slabs", "hvx_extract_regular", "hvx_classify_regular", "hvx_extract_transition",
-    "hvx_build_meshlets", "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
+    "hvx_build_meshlets", "hvx_gather_surface", "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
     "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost",
 ]
 
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     L.hvx_classify_regular.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
     L.hvx_extract_transition.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
     L.hvx_build_meshlets.argtypes = [vp, C.c_int, C.c_uint32]
+    L.hvx_gather_surface.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint32]
     L.hvx_buffer.argtypes = [vp, C.c_int]
     L.hvx_buffer.restype = vp
     L.hvx_buffer_bytes.argtypes = [vp, C.c_int]

@@ -28,6 +28,8 @@ MESHLET_DTYPE = np.dtype([(n, "<u4") for n in ("first_index", "index_count", "fi
                                                  "bounds_offset", "generation_low", "generation_high", "_pad")])
 MESHLET_BOUNDS_DTYPE = np.dtype([("center", "<f4", 3), ("radius", "<f4"), ("cone_apex", "<f4", 3),
                                  ("cone_cutoff", "<f4"), ("cone_axis", "<f4", 3), ("_pad", "<f4")])
+GATHER_COUNTERS_DTYPE = np.dtype([(n, "<u4") for n in ("regular_samples", "transition_samples", "table_probes", "page_misses",
+                                                        "stale_targets", "completed")] + [("_pad", "<u4", 2)])
 TERRAIN_MESHLET_BUILD_INDICES = 63  # PV/src/terrain_meshlet.rs:7-8
 assert VERTEX_DTYPE.itemsize == 32 and EMISSION_COUNTERS_DTYPE.itemsize == 32 and MESHLET_BOUNDS_DTYPE.itemsize == 48
 assert TRANSITION_COUNTERS_DTYPE.itemsize == 48 and CLASSIFY_COUNTERS_DTYPE.itemsize == 16
@@ -45,6 +47,7 @@ _BUF_DTYPES = {
     _ffi.BUF_REGULAR_MESHLETS: MESHLET_DTYPE, _ffi.BUF_REGULAR_MESHLET_BOUNDS: MESHLET_BOUNDS_DTYPE,
     _ffi.BUF_REGULAR_MESHLET_COUNTS: np.dtype("<u4"), _ffi.BUF_TRANSITION_MESHLETS: MESHLET_DTYPE,
     _ffi.BUF_TRANSITION_MESHLET_BOUNDS: MESHLET_BOUNDS_DTYPE, _ffi.BUF_TRANSITION_MESHLET_COUNTS: np.dtype("<u4"),
+    _ffi.BUF_GATHER_COUNTERS: GATHER_COUNTERS_DTYPE, _ffi.BUF_GATHER_INDIRECT: np.dtype("<u4"),
 }
 
 
@@ -211,6 +214,19 @@ class Context:
     def build_meshlets(self, n, kind=0):
         """63-index meshlets + bounds for chunks [0, n) of the last extraction (PV/src/terrain_meshlet.rs)."""
         self._check(self._lib.hvx_build_meshlets(self._handle, kind, n), kind="transition" if kind else "regular")
+
+    def gather_surface(self, residency, table, atlas, jobs):
+        """hvx_gather_surface: halo blocks + transition slabs of ``jobs`` from the page atlas into the ctx arenas.
+
+        residency / table / jobs: numpy structured arrays (helio_b200.gather dtypes); atlas: numpy uint32
+        array or a torch tensor (host or device) of 32^3-word tiles in linear order."""
+        residency = np.ascontiguousarray(residency)
+        table = np.ascontiguousarray(table)
+        jobs = np.ascontiguousarray(jobs)
+        aptr, awords, keep = _input_pointer(atlas)
+        self._check(self._lib.hvx_gather_surface(self._handle, C.c_void_p(residency.ctypes.data), C.c_void_p(table.ctypes.data),
+                                                 aptr, awords, C.c_void_p(jobs.ctypes.data), len(jobs)))
+        del keep
 
     def read_meshlets(self, chunk, kind=0):
         """Host copy of one chunk's (descriptors, bounds) after build_meshlets."""

@@ -36,6 +36,8 @@ struct hvx_ctx {
     uint8_t* d_col_lod = nullptr;     // [max_chunks]
     float* d_heights = nullptr;       // [heights_cols][(E+2)^2], grown on demand
     uint64_t heights_cols = 0;
+    void* stage[3] = {nullptr, nullptr, nullptr};  // gather inputs staged from the host: table, atlas, jobs
+    uint64_t stage_bytes[3] = {0, 0, 0};
     uint32_t* d_work = nullptr;       // [2] work counters (regular, transition)
     hvx_range* d_packed = nullptr;    // [max_chunks] packed placement for hvx_read_meshes
     void* pack_v = nullptr;           // staging for hvx_read_meshes
@@ -115,6 +117,8 @@ uint64_t arena_bytes(const hvx_config& c, int id) {
         case HVX_BUF_TRANSITION_MESHLETS: return tr ? n * ((c.max_transition_indices + 62ull) / 63) * sizeof(hvx_meshlet) : 0;
         case HVX_BUF_TRANSITION_MESHLET_BOUNDS: return tr ? n * ((c.max_transition_indices + 62ull) / 63) * sizeof(hvx_meshlet_bounds) : 0;
         case HVX_BUF_TRANSITION_MESHLET_COUNTS: return tr ? n * 4 : 0;
+        case HVX_BUF_GATHER_COUNTERS: return c.edge == 32 ? n * sizeof(hvx_gather_counters) : 0;
+        case HVX_BUF_GATHER_INDIRECT: return c.edge == 32 ? n * 24 * 4ull : 0;
         default: return 0;
     }
 }
@@ -315,6 +319,7 @@ int run_fill(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t
             if (ctx->d_heights) {
                 HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 cudaFree(ctx->d_heights);
+    for (void* b : ctx->stage) cudaFree(b);
                 ctx->allocated -= ctx->heights_cols * s * s * sizeof(float);
                 ctx->d_heights = nullptr;
                 ctx->heights_cols = 0;
@@ -454,6 +459,7 @@ void hvx_destroy(hvx_ctx* ctx) {
     cudaFree(ctx->d_col_xz);
     cudaFree(ctx->d_col_lod);
     cudaFree(ctx->d_heights);
+    for (void* b : ctx->stage) cudaFree(b);
     cudaFree(ctx->d_work);
     cudaFree(ctx->d_packed);
     cudaFree(ctx->pack_v);
@@ -539,6 +545,91 @@ int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t words, 
     cudaError_t e = launch_transition(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_transition");
     ctx->launches += 1;
+    return HVX_OK;
+}
+
+// Gather inputs: a device pointer is used in place, a host pointer is staged (grow-only scratch).
+static int stage_input(hvx_ctx* ctx, int which, const void* ptr, uint64_t bytes, const void** out) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        attr.type = cudaMemoryTypeUnregistered;
+    }
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+        if (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device)
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "gather input lives on device %d, ctx is on device %d", attr.device, ctx->device);
+        *out = ptr;
+        return HVX_OK;
+    }
+    if (bytes > ctx->stage_bytes[which]) {
+        if (ctx->stage[which]) {
+            HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->stage[which]);
+            ctx->allocated -= ctx->stage_bytes[which];
+            ctx->stage[which] = nullptr;
+            ctx->stage_bytes[which] = 0;
+        }
+        cudaError_t e = cudaMalloc(&ctx->stage[which], bytes);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+        ctx->stage_bytes[which] = bytes;
+        ctx->allocated += bytes;
+    }
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->stage[which], ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = ctx->stage[which];
+    return HVX_OK;
+}
+
+int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_page_table_entry* table,
+                       const uint32_t* atlas, uint64_t atlas_words, const hvx_gather_job* jobs, uint32_t n) {
+    static_assert(sizeof(hvx_page_table_entry) == 48 && sizeof(hvx_residency) == 32 && sizeof(hvx_gather_job) == 64 &&
+                      sizeof(hvx_gather_counters) == 32, "gather POD layouts");
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (ctx->cfg.edge != 32) return fail(ctx, HVX_E_INVALID_ARGUMENT, "surface gather needs edge 32 (the residency page edge), ctx has %u", ctx->cfg.edge);
+    if (n > ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
+    if (n == 0) return HVX_OK;
+    if (!residency || !table || !atlas || !jobs) return fail(ctx, HVX_E_INVALID_ARGUMENT, "residency, table, atlas and jobs must be non-NULL");
+    const hvx_residency& r = *residency;
+    if ((r.table_mask & (r.table_mask + 1u)) != 0u) return fail(ctx, HVX_E_INVALID_ARGUMENT, "page table capacity must be a power of two (mask %#x)", r.table_mask);
+    if (r.max_probe == 0u || r.max_probe > r.table_mask + 1u) return fail(ctx, HVX_E_INVALID_ARGUMENT, "max_probe %u must be in [1, capacity %u]", r.max_probe, r.table_mask + 1u);
+    const uint64_t tiles = static_cast<uint64_t>(r.atlas_tiles_x) * r.atlas_tiles_y * r.atlas_tiles_z;
+    if (tiles == 0 || atlas_words != tiles * 32768ull || atlas_words > 0xffffffffull)
+        return fail(ctx, HVX_E_SAMPLE_COUNT, "atlas holds %llu words; %u x %u x %u tiles of 32^3 need %llu",
+                    static_cast<unsigned long long>(atlas_words), r.atlas_tiles_x, r.atlas_tiles_y, r.atlas_tiles_z,
+                    static_cast<unsigned long long>(tiles * 32768ull));
+    bool any_transition = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (jobs[i].transition_mask & ~0x3fu)
+            return fail(ctx, HVX_E_TRANSITION_MASK, "transition mask %#x uses bits outside the six page faces", jobs[i].transition_mask);
+        if (jobs[i].lod == 0 && jobs[i].transition_mask != 0)
+            return fail(ctx, HVX_E_FINEST_LOD, "LOD0 pages cannot own coarse-side transition faces");
+        if (jobs[i].lod > 24) return fail(ctx, HVX_E_ADDRESS, "lod %u is outside the addressable range", jobs[i].lod);
+        any_transition |= jobs[i].transition_mask != 0;
+    }
+    DeviceGuard guard(ctx->device);
+    int rc;
+    if ((rc = ensure_buffer(ctx, HVX_BUF_SAMPLES))) return rc;
+    if (any_transition && (rc = ensure_buffer(ctx, HVX_BUF_SLABS))) return rc;
+    if ((rc = ensure_buffer(ctx, HVX_BUF_GATHER_COUNTERS))) return rc;
+    if ((rc = ensure_buffer(ctx, HVX_BUF_GATHER_INDIRECT))) return rc;
+    const void *d_table = nullptr, *d_atlas = nullptr, *d_jobs = nullptr;
+    if ((rc = stage_input(ctx, 0, table, (static_cast<uint64_t>(r.table_mask) + 1) * sizeof(hvx_page_table_entry), &d_table))) return rc;
+    if ((rc = stage_input(ctx, 1, atlas, atlas_words * 4, &d_atlas))) return rc;
+    if ((rc = stage_input(ctx, 2, jobs, static_cast<uint64_t>(n) * sizeof(hvx_gather_job), &d_jobs))) return rc;
+    HVX_CUDA(ctx, cudaMemsetAsync(ctx->buf[HVX_BUF_GATHER_COUNTERS], 0, static_cast<size_t>(n) * sizeof(hvx_gather_counters), ctx->stream));
+    HVX_CUDA(ctx, cudaMemsetAsync(ctx->buf[HVX_BUF_GATHER_INDIRECT], 0, static_cast<size_t>(n) * 24 * 4, ctx->stream));
+    GatherParams p{};
+    p.n_jobs = n;
+    p.residency = r;
+    p.table = static_cast<const hvx_page_table_entry*>(d_table);
+    p.atlas = static_cast<const uint32_t*>(d_atlas);
+    p.jobs = static_cast<const hvx_gather_job*>(d_jobs);
+    p.samples = static_cast<uint32_t*>(ctx->buf[HVX_BUF_SAMPLES]);
+    p.slabs = static_cast<uint32_t*>(ctx->buf[HVX_BUF_SLABS]);
+    p.counters = static_cast<hvx_gather_counters*>(ctx->buf[HVX_BUF_GATHER_COUNTERS]);
+    p.indirect = static_cast<uint32_t*>(ctx->buf[HVX_BUF_GATHER_INDIRECT]);
+    cudaError_t e = launch_gather(p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_gather");
+    ctx->launches += 2;
     return HVX_OK;
 }
 

@@ -63,6 +63,18 @@ struct FillParams {
     const uint32_t* col_index;
 };
 
+struct GatherParams {
+    uint32_t n_jobs;
+    hvx_residency residency;
+    const hvx_page_table_entry* table;
+    const uint32_t* atlas;
+    const hvx_gather_job* jobs;
+    uint32_t* samples;                 // [n][34^3]
+    uint32_t* slabs;                   // [n][6*3*67^2]
+    hvx_gather_counters* counters;     // [n], zeroed before the launch
+    uint32_t* indirect;                // [n][24]
+};
+
 struct MeshletParams {
     uint32_t n_chunks;
     uint32_t transition;                  // 0 regular, 1 transition
@@ -91,6 +103,7 @@ cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& d
 cudaError_t launch_terrain_heights(int edge, const long long* col_xz, const uint8_t* col_lod, uint32_t n_cols, float* heights,
                                    cudaStream_t stream);
 cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_gather(const GatherParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
 cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,
                         const hvx_range* packed_ranges, uint32_t n, hvx_vertex* out_vertices,

@@ -73,7 +73,7 @@ class _Single:
         return self._ctx
 
     def resource_stats(self):
-        return ResourceStats(buffers=sum(1 for i in range(23) if self._ctx.buffer_bytes(i)),
+        return ResourceStats(buffers=sum(1 for i in range(25) if self._ctx.buffer_bytes(i)),
                              allocated_bytes=self._ctx.allocated_bytes)
 
     def resize(self, _width, _height):

@@ -216,6 +216,61 @@ int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t slab_wo
  * overflowed publish none.  kind 0 = regular, 1 = transition. */
 int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n);
 
+/* ---- surface gather (the step before extraction in the reference's pass) ---------- */
+/* GpuPageTableEntry (PV/src/table.rs:8-19): open-addressed page table of the residency atlas. */
+typedef struct {
+    uint32_t planet_id[4];
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod;
+    uint32_t slot;
+    uint32_t generation_low, generation_high;
+    uint32_t state;                    /* 0 empty, 1 occupied, 2 tombstone */
+} hvx_page_table_entry;
+
+/* GpuResidencyUniform (PV/src/table.rs:62-72). */
+typedef struct {
+    uint32_t table_mask, max_probe, resident_pages;
+    uint32_t atlas_tiles_x, atlas_tiles_y, atlas_tiles_z;
+    uint32_t publication_epoch_low, publication_epoch_high;
+} hvx_residency;
+
+/* GpuSurfaceGatherJob (PV/src/surface_sampling.rs:121-134). */
+typedef struct {
+    uint32_t planet_id[4];
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod;
+    uint32_t generation_low, generation_high;
+    uint32_t transition_mask;
+    uint32_t target_slot;
+    uint32_t residency_epoch_low, residency_epoch_high;
+    uint32_t _pad[2];
+} hvx_gather_job;
+
+/* GpuSurfaceGatherCounters (PV/src/surface_sampling.rs:171-181). */
+typedef struct {
+    uint32_t regular_samples, transition_samples, table_probes, page_misses;
+    uint32_t stale_targets, completed, _pad[2];
+} hvx_gather_counters;
+
+/* GpuSurfaceSampler::prepare + encode (PV/src/surface_sampling.rs:309-337; gather_regular,
+ * gather_transition, finalize_gather in PV/src/surface_gather.wgsl:200-264) for n jobs at once.
+ * Requires edge 32 (the residency page edge).  For job k it builds the 34^3 halo block into
+ * HVX_BUF_SAMPLES[k] and, for the faces in transition_mask (lod > 0), the six 67x67x3 fine-side slabs
+ * into HVX_BUF_SLABS[k] from the resident page atlas, looking pages up in the open-addressed table
+ * exactly like the reference (same hash, same probe sequence, missing page -> AIR 0x00007fff).
+ * Counters have the reference's values (table_probes counts one lookup per gathered sample);
+ * HVX_BUF_GATHER_INDIRECT[k] holds the eight DispatchIndirectArgs finalize_gather publishes.
+ * A job whose residency epoch does not match the uniform gathers nothing, like the shader.
+ *   table:  HOST or DEVICE, table_mask + 1 entries.
+ *   atlas:  HOST or DEVICE, R32Uint texels of the 3-D atlas in linear order, x fastest:
+ *           (32 tiles_x) x (32 tiles_y) x (32 tiles_z) words; page slot s occupies the 32^3 tile at
+ *           tile coordinates (s % tiles_x, (s / tiles_x) % tiles_y, s / (tiles_x tiles_y)).
+ *   jobs:   HOST, n entries.
+ * The gathered arenas are then extracted with hvx_extract_regular / hvx_extract_transition
+ * (samples = NULL), with no host round trip of the 480 KB per page. */
+int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_page_table_entry* table,
+                       const uint32_t* atlas, uint64_t atlas_words, const hvx_gather_job* jobs, uint32_t n);
+
 /* ---- outputs ------------------------------------------------------------------------ */
 typedef enum {
     HVX_BUF_SAMPLES = 0,             /* u32  [max_chunks][(edge+2)^3]          (lazy) */
@@ -241,7 +296,9 @@ typedef enum {
     HVX_BUF_TRANSITION_MESHLETS = 20,
     HVX_BUF_TRANSITION_MESHLET_BOUNDS = 21,
     HVX_BUF_TRANSITION_MESHLET_COUNTS = 22,
-    HVX_BUF_COUNT = 23
+    HVX_BUF_GATHER_COUNTERS = 23,          /* hvx_gather_counters [max_chunks]                 (lazy) */
+    HVX_BUF_GATHER_INDIRECT = 24,          /* u32 [max_chunks][8][3]  DispatchIndirectArgs     (lazy) */
+    HVX_BUF_COUNT = 25
 } hvx_buffer_id;
 
 /* Device pointer / size of a ctx arena (allocating it if lazy); NULL / 0 if unavailable. */

@@ -990,3 +990,132 @@ int hvxo_build_meshlets(const hvxo_vertex* vertices, uint32_t vertex_count, cons
     }
     return (int)count;
 }
+
+/* ================================================================================================
+ * Surface gather.  Follows PV/src/surface_gather.wgsl line by line: every gathered
+ * sample walks the open-addressed page table (lookup_page, :125-149), missing pages read as AIR and
+ * count a miss (:181-186), counters are the shader's atomics, finalize_gather (:236-264) publishes
+ * `completed` and the eight DispatchIndirectArgs.  i32 arithmetic wraps like WGSL's.
+ * ============================================================================================== */
+static uint32_t gather_mix_hash(uint32_t hash, uint32_t value) { /* table.rs:163-167, wgsl:102-105 */
+    uint32_t mixed = (hash ^ value) * 0x045d9f3bu;
+    return mixed ^ (mixed >> 16);
+}
+
+uint32_t hvxo_page_hash(const uint32_t planet_id[4], const int32_t relative_min[3], uint32_t lod) {
+    uint32_t hash = 0x811c9dc5u;
+    for (int i = 0; i < 4; ++i) hash = gather_mix_hash(hash, planet_id[i]);
+    for (int i = 0; i < 3; ++i) hash = gather_mix_hash(hash, (uint32_t)relative_min[i]);
+    return gather_mix_hash(hash, lod);
+}
+
+typedef struct {
+    uint32_t slot, generation_low, generation_high, probes, found;
+} gather_lookup;
+
+static gather_lookup gather_lookup_page(const hvxo_residency* res, const hvxo_page_table_entry* table,
+                                        const hvxo_gather_job* job, const int32_t rel[3], uint32_t lod) {
+    const uint32_t start = hvxo_page_hash(job->planet_id, rel, lod) & res->table_mask;
+    uint32_t probe = 0;
+    for (;;) {
+        if (probe >= res->max_probe) break;
+        const hvxo_page_table_entry* e = &table[(start + probe) & res->table_mask];
+        if (e->state == 0u) return (gather_lookup){0u, 0u, 0u, probe + 1u, 0u};
+        if (e->state == 1u && memcmp(e->planet_id, job->planet_id, 16) == 0 && memcmp(e->relative_lod0_cell_min, rel, 12) == 0 &&
+            e->lod == lod)
+            return (gather_lookup){e->slot, e->generation_low, e->generation_high, probe + 1u, 1u};
+        probe += 1u;
+    }
+    return (gather_lookup){0u, 0u, 0u, probe, 0u};
+}
+
+static int32_t wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+static int32_t wrap_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+static int32_t wrap_mul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+static int32_t gather_floor_div(int32_t value, int32_t divisor) { /* wgsl:151-157 */
+    int32_t q = value / divisor;
+    if (value % divisor < 0) q -= 1;
+    return q;
+}
+
+static uint32_t gather_sample(const hvxo_residency* res, const hvxo_page_table_entry* table, const uint32_t* atlas,
+                              const hvxo_gather_job* job, const int32_t pos[3], uint32_t lod, hvxo_gather_counters* c) {
+    const int32_t scale = (int32_t)(1u << lod), span = 32 * scale; /* wgsl:166-168 */
+    int32_t rel[3];
+    for (int a = 0; a < 3; ++a) {
+        const int32_t off = wrap_sub(pos[a], job->relative_lod0_cell_min[a]);
+        rel[a] = wrap_add(job->relative_lod0_cell_min[a], wrap_mul(gather_floor_div(off, span), span));
+    }
+    const gather_lookup l = gather_lookup_page(res, table, job, rel, lod);
+    c->table_probes += l.probes;
+    if (!l.found) {
+        c->page_misses += 1u;
+        return 0x00007fffu;
+    }
+    uint32_t local[3];
+    for (int a = 0; a < 3; ++a) local[a] = (uint32_t)(wrap_sub(pos[a], rel[a]) / scale);
+    const uint32_t tx = l.slot % res->atlas_tiles_x, ty = (l.slot / res->atlas_tiles_x) % res->atlas_tiles_y,
+                   tz = l.slot / (res->atlas_tiles_x * res->atlas_tiles_y); /* slot_origin, wgsl:159-164 */
+    const uint64_t row = (uint64_t)res->atlas_tiles_x * 32u, slice = row * res->atlas_tiles_y * 32u;
+    return atlas[(tx * 32u + local[0]) + (ty * 32u + local[1]) * row + (tz * 32u + local[2]) * slice];
+}
+
+void hvxo_gather_surface(const hvxo_residency* res, const hvxo_page_table_entry* table, const uint32_t* atlas,
+                         const hvxo_gather_job* job, uint32_t* regular, uint32_t* transition,
+                         hvxo_gather_counters* c, uint32_t* indirect) {
+    static const int32_t ORIGIN[6][3] = {{0, 0, 1}, {1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 1, 0}, {0, 0, 1}};
+    static const int32_t U[6][3] = {{0, 1, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 1}, {1, 0, 0}, {1, 0, 0}};
+    static const int32_t V[6][3] = {{0, 0, -1}, {0, 0, 1}, {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}};
+    static const int32_t OUT[6][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+    memset(c, 0, sizeof(*c));
+    const int epoch_ok = res->publication_epoch_low == job->residency_epoch_low &&
+                         res->publication_epoch_high == job->residency_epoch_high;
+    if (epoch_ok) {
+        /* gather_regular, wgsl:200-212 */
+        const int32_t scale = (int32_t)(1u << job->lod);
+        for (int32_t linear = 0; linear < 39304; ++linear) {
+            const int32_t x = linear % 34, y = (linear / 34) % 34, z = linear / (34 * 34);
+            const int32_t local[3] = {x - 1, y - 1, z - 1};
+            int32_t pos[3];
+            for (int a = 0; a < 3; ++a) pos[a] = wrap_add(job->relative_lod0_cell_min[a], wrap_mul(local[a], scale));
+            regular[linear] = gather_sample(res, table, atlas, job, pos, job->lod, c);
+            c->regular_samples += 1u;
+        }
+        /* gather_transition, wgsl:214-241 */
+        if (job->lod != 0u) {
+            const int32_t fine = (int32_t)(1u << (job->lod - 1u)), coarse_span = 32 * fine * 2;
+            for (int32_t linear = 0; linear < 80802; ++linear) {
+                const int32_t face = linear / 13467;
+                if ((job->transition_mask & (1u << face)) == 0u) continue;
+                const int32_t fl = linear % 13467, layer = fl / (67 * 67), ll = fl % (67 * 67), v = ll / 67, u = ll % 67;
+                int32_t pos[3];
+                for (int a = 0; a < 3; ++a)
+                    pos[a] = wrap_add(wrap_add(wrap_add(wrap_add(job->relative_lod0_cell_min[a], wrap_mul(ORIGIN[face][a], coarse_span)),
+                                                        wrap_mul(wrap_mul(U[face][a], u - 1), fine)),
+                                               wrap_mul(wrap_mul(V[face][a], v - 1), fine)),
+                                      wrap_mul(wrap_mul(OUT[face][a], layer - 1), fine));
+                transition[linear] = gather_sample(res, table, atlas, job, pos, job->lod - 1u, c);
+                c->transition_samples += 1u;
+            }
+        }
+    }
+    /* finalize_gather, wgsl:236-264 */
+    const gather_lookup target = gather_lookup_page(res, table, job, job->relative_lod0_cell_min, job->lod);
+    c->table_probes += target.probes;
+    const int current = target.found && target.slot == job->target_slot && target.generation_low == job->generation_low &&
+                        target.generation_high == job->generation_high;
+    if (!current || !epoch_ok) {
+        c->stale_targets = 1u;
+        return;
+    }
+    uint32_t faces = 0;
+    for (int f = 0; f < 6; ++f) faces += (job->transition_mask >> f) & 1u;
+    if (c->page_misses != 0u || c->regular_samples != 39304u || c->transition_samples != faces * 13467u) return;
+    c->completed = 1u;
+    static const uint32_t GROUPS[8] = {512u, 128u, 1u, 512u, 96u, 24u, 1u, 96u};
+    for (int i = 0; i < 8; ++i) {
+        indirect[3 * i] = GROUPS[i];
+        indirect[3 * i + 1] = 1u;
+        indirect[3 * i + 2] = 1u;
+    }
+}

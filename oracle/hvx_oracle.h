@@ -173,3 +173,32 @@ int hvxo_build_meshlets(const hvxo_vertex* vertices, uint32_t vertex_count, cons
 }
 #endif
 #endif
+
+/* ---- surface gather: literal restatement of PV/src/surface_gather.wgsl ------------- */
+typedef struct {
+    uint32_t planet_id[4];
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod, slot, generation_low, generation_high, state;
+} hvxo_page_table_entry; /* GpuPageTableEntry, PV/src/table.rs:8-19 */
+typedef struct {
+    uint32_t table_mask, max_probe, resident_pages, atlas_tiles_x, atlas_tiles_y, atlas_tiles_z;
+    uint32_t publication_epoch_low, publication_epoch_high;
+} hvxo_residency; /* GpuResidencyUniform, PV/src/table.rs:62-72 */
+typedef struct {
+    uint32_t planet_id[4];
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod, generation_low, generation_high, transition_mask, target_slot;
+    uint32_t residency_epoch_low, residency_epoch_high, _pad[2];
+} hvxo_gather_job; /* GpuSurfaceGatherJob, PV/src/surface_sampling.rs:121-134 */
+typedef struct {
+    uint32_t regular_samples, transition_samples, table_probes, page_misses, stale_targets, completed, _pad[2];
+} hvxo_gather_counters; /* GpuSurfaceGatherCounters, PV/src/surface_sampling.rs:171-181 */
+
+/* GpuLookupKey::hash (PV/src/table.rs:148-160) */
+uint32_t hvxo_page_hash(const uint32_t planet_id[4], const int32_t relative_min[3], uint32_t lod);
+/* gather_regular + gather_transition + finalize_gather for one job.  regular: 34^3 words,
+ * transition: 6*67*67*3 words (faces outside the mask are left untouched), indirect: 24 words
+ * (written only when the job completes).  One table walk per sample, exactly like the shader. */
+void hvxo_gather_surface(const hvxo_residency* residency, const hvxo_page_table_entry* table, const uint32_t* atlas,
+                         const hvxo_gather_job* job, uint32_t* regular, uint32_t* transition,
+                         hvxo_gather_counters* counters, uint32_t* indirect);

@@ -86,6 +86,10 @@ def lib():
         L.hvxo_build_meshlets.argtypes = [C.c_void_p, C.c_uint32, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
         L.hvxo_batch_fill.argtypes = [C.c_int, C.c_int, C.c_uint32, i64p, C.c_uint32, C.c_int, u32p]
+        L.hvxo_page_hash.restype = C.c_uint32
+        L.hvxo_page_hash.argtypes = [u32p, C.POINTER(C.c_int32), C.c_uint32]
+        L.hvxo_gather_surface.restype = None
+        L.hvxo_gather_surface.argtypes = [C.c_void_p, C.c_void_p, u32p, C.c_void_p, u32p, u32p, C.c_void_p, u32p]
         L.hvxo_case_topology.argtypes = [C.c_int, C.c_uint32, u32p, u32p, u32p, u32p, C.POINTER(C.c_uint16),
                                          C.POINTER(C.c_uint8)]
     return _LIB
@@ -265,3 +269,29 @@ def batch_regular(kind: int, pages: np.ndarray, edge: int, lod: int = 0, threads
     cells = lib().hvxo_batch_regular(kind, edge, lod, pages.ctypes.data_as(C.POINTER(C.c_int64)), pages.shape[0],
                                      1 if do_fill else 0, smp, threads, totals)
     return int(cells), [int(t) for t in totals]
+
+
+def gather_surface(residency: np.ndarray, table: np.ndarray, atlas: np.ndarray, job: np.ndarray):
+    """One job of the surface gather (hvxo_gather_surface): (regular[39304], transition[80802], counters, indirect[24]).
+
+    residency / table / job are the structured arrays of oracle/residency.py; slab words of faces outside
+    the job's mask keep the sentinel 0xFFFFFFFF."""
+    from . import residency as R
+    residency = np.ascontiguousarray(residency, dtype=R.RESIDENCY_DTYPE)
+    table = np.ascontiguousarray(table, dtype=R.ENTRY_DTYPE)
+    job = np.ascontiguousarray(job, dtype=R.JOB_DTYPE)
+    atlas = np.ascontiguousarray(atlas, dtype=np.uint32).reshape(-1)
+    regular = np.full(34 ** 3, 0xFFFFFFFF, dtype=np.uint32)
+    transition = np.full(6 * 3 * 67 * 67, 0xFFFFFFFF, dtype=np.uint32)
+    counters = np.zeros(1, dtype=R.COUNTERS_DTYPE)
+    indirect = np.zeros(24, dtype=np.uint32)
+    lib().hvxo_gather_surface(residency.ctypes.data_as(C.c_void_p), table.ctypes.data_as(C.c_void_p), _u32p(atlas),
+                              job.ctypes.data_as(C.c_void_p), _u32p(regular), _u32p(transition),
+                              counters.ctypes.data_as(C.c_void_p), _u32p(indirect))
+    return regular, transition, counters[0], indirect
+
+
+def page_hash(planet_id, relative_min, lod: int) -> int:
+    pid = np.ascontiguousarray(planet_id, dtype=np.uint32)
+    rel = np.ascontiguousarray(relative_min, dtype=np.int32)
+    return int(lib().hvxo_page_hash(_u32p(pid), rel.ctypes.data_as(C.POINTER(C.c_int32)), lod))
