@@ -65,17 +65,23 @@ def _input_pointer(array, expected_dtype=np.uint32):
     return C.c_void_p(arr.ctypes.data), arr.size, arr
 
 
+_DESC_DTYPE = np.dtype([("generation", "<u8"), ("dirty_microbricks", "<u8"), ("transition_mask", "<u4"), ("_pad", "<u4")])
+
+
 def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask=0):
     """ctypes array of ``hvx_chunk_desc``; scalar arguments broadcast, sequences are per chunk."""
-    descs = (_ffi.ChunkDesc * max(n, 1))()
+    arr = np.zeros(max(n, 1), dtype=_DESC_DTYPE)
 
-    def at(value, i):
-        return int(value[i]) if hasattr(value, "__len__") else int(value)
+    def column(value, mask):
+        if hasattr(value, "__len__"):
+            return np.array([int(v) & mask for v in value[:n]], dtype=np.uint64)
+        return np.uint64(int(value) & mask)
 
-    for i in range(n):
-        descs[i].generation = at(generation, i) & ((1 << 64) - 1)
-        descs[i].dirty_microbricks = at(dirty_microbricks, i) & ((1 << 64) - 1)
-        descs[i].transition_mask = at(transition_mask, i) & 0xFFFFFFFF
+    arr["generation"][:n] = column(generation, (1 << 64) - 1)
+    arr["dirty_microbricks"][:n] = column(dirty_microbricks, (1 << 64) - 1)
+    arr["transition_mask"][:n] = column(transition_mask, 0xFFFFFFFF)
+    descs = (_ffi.ChunkDesc * max(n, 1)).from_buffer(arr)
+    descs._keepalive = arr
     return descs
 
 

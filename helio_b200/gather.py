@@ -180,9 +180,9 @@ class GpuSurfaceSampler:
     def extract(self, dirty_microbricks=(1 << 64) - 1, transition=True) -> None:
         """Regular (and transition) extraction of the gathered jobs, straight from the arenas."""
         jobs, n = self._jobs, len(self._jobs)
-        generation = [int(j["generation_low"]) | (int(j["generation_high"]) << 32) for j in jobs]
-        masks = [int(j["transition_mask"]) for j in jobs]
+        generation = jobs["generation_low"].astype(np.uint64) | (jobs["generation_high"].astype(np.uint64) << np.uint64(32))
+        masks = jobs["transition_mask"]
         descs = make_descs(n, generation, dirty_microbricks, masks)
         self._ctx.extract_regular(None, descs, n)
-        if transition and any(masks) and self._ctx.max_transition_vertices:
+        if transition and masks.any() and self._ctx.max_transition_vertices:
             self._ctx.extract_transition(None, descs, n)

@@ -174,4 +174,41 @@ class TransvoxelGpuTransitionExtractor {
     uint64_t cells_;
 };
 
+/// Batched GpuSurfaceSampler (PV/src/surface_sampling.rs:184-350): halo blocks + transition slabs of n jobs
+/// from the resident page atlas into the context's sample arenas, then the extractors run on them.
+class GpuSurfaceSampler {
+   public:
+    GpuSurfaceSampler(int device, uint32_t max_jobs, TransvoxelGpuExtractorConfig regular = {},
+                      TransvoxelGpuTransitionExtractorConfig transition = {})
+        : ctx_(device, hvx_config{PAGE_EDGE, max_jobs, regular.max_vertices, regular.max_indices, transition.max_vertices,
+                                  transition.max_indices, 0u, 0}) {}
+    /// prepare + encode for n jobs.  table: table_mask + 1 entries; atlas: linear R32Uint texels (host or device).
+    void dispatch(const hvx_residency& residency, const hvx_page_table_entry* table, const uint32_t* atlas,
+                  uint64_t atlas_words, const hvx_gather_job* jobs, uint32_t n) {
+        ctx_.check(hvx_gather_surface(ctx_.get(), &residency, table, atlas, atlas_words, jobs, n));
+        jobs_.assign(jobs, jobs + n);
+    }
+    /// regular + transition extraction of the gathered jobs, straight from the arenas
+    void extract(uint64_t dirty_microbricks = ~0ull) {
+        std::vector<hvx_chunk_desc> d(jobs_.size());
+        bool any_faces = false;
+        for (size_t i = 0; i < jobs_.size(); ++i) {
+            d[i] = detail::desc(jobs_[i].generation_low | (static_cast<uint64_t>(jobs_[i].generation_high) << 32),
+                                dirty_microbricks, static_cast<uint8_t>(jobs_[i].transition_mask));
+            any_faces |= jobs_[i].transition_mask != 0;
+        }
+        const uint32_t n = static_cast<uint32_t>(d.size());
+        ctx_.check(hvx_extract_regular(ctx_.get(), nullptr, n * 39304ull, d.data(), n));
+        if (any_faces) ctx_.check(hvx_extract_transition(ctx_.get(), nullptr, n * 80802ull, d.data(), n));
+    }
+    std::vector<hvx_gather_counters> counters_buffer() const { return ctx_.read<hvx_gather_counters>(HVX_BUF_GATHER_COUNTERS, 0, jobs_.size()); }
+    std::vector<uint32_t> indirect_buffer() const { return ctx_.read<uint32_t>(HVX_BUF_GATHER_INDIRECT, 0, 24 * jobs_.size()); }
+    std::vector<hvx_emission_counters> regular_counters() const { return ctx_.read<hvx_emission_counters>(HVX_BUF_REGULAR_COUNTERS, 0, jobs_.size()); }
+    ResourceStats resource_stats() const { return ctx_.stats(); }
+
+   private:
+    detail::Ctx ctx_;
+    std::vector<hvx_gather_job> jobs_;
+};
+
 }  // namespace helio_voxel_cuda

@@ -31,6 +31,62 @@ pub struct hvx_chunk_desc {
 #[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
 pub struct hvx_range { pub first_vertex: u32, pub vertex_count: u32, pub first_index: u32, pub index_count: u32 }
 
+/// `GpuPageTableEntry` (PV/src/table.rs:8-19) -- bytemuck-castable from the reference's own type.
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_page_table_entry {
+    pub planet_id: [u32; 4],
+    pub relative_lod0_cell_min: [i32; 3],
+    pub lod: u32,
+    pub slot: u32,
+    pub generation_low: u32,
+    pub generation_high: u32,
+    pub state: u32,
+}
+
+/// `GpuResidencyUniform` (PV/src/table.rs:62-72).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_residency {
+    pub table_mask: u32,
+    pub max_probe: u32,
+    pub resident_pages: u32,
+    pub atlas_tiles_x: u32,
+    pub atlas_tiles_y: u32,
+    pub atlas_tiles_z: u32,
+    pub publication_epoch_low: u32,
+    pub publication_epoch_high: u32,
+}
+
+/// `GpuSurfaceGatherJob` (PV/src/surface_sampling.rs:121-134).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_gather_job {
+    pub planet_id: [u32; 4],
+    pub relative_lod0_cell_min: [i32; 3],
+    pub lod: u32,
+    pub generation_low: u32,
+    pub generation_high: u32,
+    pub transition_mask: u32,
+    pub target_slot: u32,
+    pub residency_epoch_low: u32,
+    pub residency_epoch_high: u32,
+    pub _pad: [u32; 2],
+}
+
+/// `GpuSurfaceGatherCounters` (PV/src/surface_sampling.rs:171-181).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_gather_counters {
+    pub regular_samples: u32,
+    pub transition_samples: u32,
+    pub table_probes: u32,
+    pub page_misses: u32,
+    pub stale_targets: u32,
+    pub completed: u32,
+    pub _pad: [u32; 2],
+}
+
 pub const HVX_OK: c_int = 0;
 pub const HVX_E_SAMPLE_COUNT: c_int = -1;
 pub const HVX_E_INVALID_CAPACITY: c_int = -2;
@@ -62,6 +118,9 @@ extern "C" {
     pub fn hvx_extract_regular(ctx: *mut hvx_ctx, samples: *const u32, sample_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
     pub fn hvx_classify_regular(ctx: *mut hvx_ctx, samples: *const u32, sample_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
     pub fn hvx_extract_transition(ctx: *mut hvx_ctx, slabs: *const u32, slab_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
+    pub fn hvx_build_meshlets(ctx: *mut hvx_ctx, kind: c_int, n: u32) -> c_int;
+    pub fn hvx_gather_surface(ctx: *mut hvx_ctx, residency: *const hvx_residency, table: *const hvx_page_table_entry,
+                              atlas: *const u32, atlas_words: u64, jobs: *const hvx_gather_job, n: u32) -> c_int;
     pub fn hvx_buffer(ctx: *mut hvx_ctx, buffer_id: c_int) -> *mut c_void;
     pub fn hvx_buffer_bytes(ctx: *mut hvx_ctx, buffer_id: c_int) -> u64;
     pub fn hvx_read(ctx: *mut hvx_ctx, buffer_id: c_int, byte_offset: u64, bytes: u64, host_dst: *mut c_void) -> c_int;

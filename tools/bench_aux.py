@@ -6,6 +6,7 @@
   lod_transition   config 2: coarse pages with all six transition faces, regular + transition kernels
   dirty_edit       config 4: 256 resident 64^3 chunks re-extracted per frame with dirty-microbrick masks
   fill             K1 density fill GB/s per field kind
+  gather           SURVEY 8f-1: halo blocks gathered from a resident page atlas, alone and followed by extraction
 
 Prints one JSON object per line; CUDA events on the ctx stream, inputs resident in HBM.
 """
@@ -135,6 +136,49 @@ def main():
     out.append({"case": "dirty_edit_256x64^3_per_frame", "ms_p50": float(np.percentile(t, 50)), "ms_p95": float(np.percentile(t, 95)),
                 "ms_p99": float(np.percentile(t, 99)), "frames": len(t), "full_reextract": r_full})
     b.close()
+    # ---- surface gather from a resident page atlas, then extraction of the gathered blocks ----
+    side, ys = 32, [-2, -1, 0, 1]
+    xs = np.arange(-side // 2, side // 2)
+    pages = grid(side, ys)                                          # page index = (iz * len(ys) + iy) * side + ix
+    n_pages = len(pages)
+    blocks = torch.empty(n_pages * 34 ** 3, dtype=torch.int32, device="cuda")
+    fillb = H.ChunkBatchExtractor(0, edge=32, max_chunks=n_pages, max_vertices=8, max_indices=8)
+    fillb.ctx.set_stream(stream.cuda_stream)
+    fillb.fill_density(16, pages, out_ptr=blocks.data_ptr())        # 34^3 fBm blocks; their interiors are the resident pages
+    fillb.ctx.synchronize()
+    fillb.close()
+    tiles = (side, side, len(ys))                                   # tile (tx, ty, tz) = (ix, iz, iy)
+    interior = blocks.view(side, len(ys), side, 34, 34, 34)[:, :, :, 1:33, 1:33, 1:33]   # [iz][iy][ix][cz][cy][cx]
+    atlas = torch.empty((tiles[2] * 32, tiles[1] * 32, tiles[0] * 32), dtype=torch.int32, device="cuda")
+    atlas.view(tiles[2], 32, tiles[1], 32, tiles[0], 32).copy_(interior.permute(1, 3, 0, 4, 2, 5))
+    del blocks, interior
+    planet = (0x5A5A5A5A,) * 4
+    table = H.PageTable(8192, 64)
+    slot_of = {}
+    for iy, y in enumerate(ys):
+        for iz, z in enumerate(xs):
+            for ix, x in enumerate(xs):
+                slot = ix + tiles[0] * (iz + tiles[1] * iy)
+                slot_of[(int(x), int(y), int(z))] = slot
+                table.insert(H.GpuLookupKey(planet, (int(x) * 32, int(y) * 32, int(z) * 32), 0), slot, 5)
+    inner = [k for k in slot_of if xs[0] < k[0] < xs[-1] and xs[0] < k[2] < xs[-1] and k[1] in (-1, 0)]
+    jobs = np.concatenate([H.gather_job(planet, (x * 32, y * 32, z * 32), 0, 5, 0, slot_of[(x, y, z)], 9) for (x, y, z) in inner])
+    nj = len(jobs)
+    res = H.residency_uniform(table, tiles, n_pages, 9)
+    gctx = H.Context(0, edge=32, max_chunks=nj, max_vertices=12288, max_indices=18432)
+    gctx.set_stream(stream.cuda_stream)
+    sampler = H.GpuSurfaceSampler(gctx)
+    r_g = timed(stream, lambda: sampler.dispatch(res, table, atlas, jobs), 2, 10)
+    c = sampler.counters_buffer()
+    r_ge = timed(stream, lambda: (sampler.dispatch(res, table, atlas, jobs), sampler.extract()), 2, 10)
+    ec = gctx.read(H._ffi.BUF_REGULAR_COUNTERS, 0, nj)
+    out.append({"case": f"gather_{nj}x34^3_from_{n_pages}_resident_pages", **r_g, "jobs_per_s": nj / (r_g["ms_median"] * 1e-3),
+                "GBps_read_plus_write": 2 * nj * 34 ** 3 * 4 / (r_g["ms_median"] * 1e-3) / 1e9,
+                "completed": int(c["completed"].sum()), "page_misses": int(c["page_misses"].sum()),
+                "note": "every call also stages the 384 KB page table and the job array from the host"})
+    out.append({"case": f"gather_then_extract_{nj}x32^3", **r_ge, "pages_per_s": nj / (r_ge["ms_median"] * 1e-3),
+                "vertices": int(ec["emitted_vertices"].astype(np.int64).sum())})
+    gctx.close()
     for o in out:
         print(json.dumps(o))
 
