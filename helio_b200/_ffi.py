@@ -33,6 +33,8 @@ HVX_E_TOPOLOGY_MISSING_PARENT = -27
 HVX_E_TOPOLOGY_COVERAGE = -28
 
 HVX_CFG_DEBUG_RECORDS = 1
+(PUB_REGULAR_VERTICES, PUB_REGULAR_INDICES, PUB_TRANSITION_VERTICES, PUB_TRANSITION_INDICES, PUB_STATES, PUB_REGULAR_DRAWS,
+ PUB_TRANSITION_DRAWS, PUB_FEEDBACK) = range(8)
 
 (BUF_SAMPLES, BUF_SLABS, BUF_REGULAR_VERTICES, BUF_REGULAR_INDICES, BUF_REGULAR_COUNTERS, BUF_REGULAR_CLASSIFY,
  BUF_REGULAR_RANGES, BUF_REGULAR_CELLS, BUF_REGULAR_OFFSETS, BUF_REGULAR_BLOCKS, BUF_TRANSITION_VERTICES,
@@ -73,7 +75,9 @@ EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
     "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count",
     "hvx_fill_density", "hvx_fill_slabs", "hvx_extract_regular", "hvx_classify_regular", "hvx_extract_transition",
-    "hvx_build_meshlets", "hvx_gather_surface", "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
+    "hvx_build_meshlets", "hvx_gather_surface", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
+    "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
+    "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
     "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost",
 ]
 
@@ -117,6 +121,17 @@ def load() -> C.CDLL:
     L.hvx_extract_transition.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
     L.hvx_build_meshlets.argtypes = [vp, C.c_int, C.c_uint32]
     L.hvx_gather_surface.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint32]
+    L.hvx_publisher_create.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+    L.hvx_publisher_destroy.argtypes = [vp]
+    L.hvx_publisher_destroy.restype = None
+    L.hvx_publish_surfaces.argtypes = [vp, vp, vp, vp, C.c_uint32]
+    L.hvx_refresh_visibility.argtypes = [vp, vp]
+    L.hvx_publisher_buffer.argtypes = [vp, C.c_int]
+    L.hvx_publisher_buffer.restype = vp
+    L.hvx_publisher_buffer_bytes.argtypes = [vp, C.c_int]
+    L.hvx_publisher_buffer_bytes.restype = C.c_uint64
+    L.hvx_publisher_read.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
+    L.hvx_publisher_write.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
     L.hvx_buffer.argtypes = [vp, C.c_int]
     L.hvx_buffer.restype = vp
     L.hvx_buffer_bytes.argtypes = [vp, C.c_int]

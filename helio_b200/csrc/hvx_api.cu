@@ -548,8 +548,8 @@ int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t words, 
     return HVX_OK;
 }
 
-// Gather inputs: a device pointer is used in place, a host pointer is staged (grow-only scratch).
-static int stage_input(hvx_ctx* ctx, int which, const void* ptr, uint64_t bytes, const void** out) {
+// Batched inputs: a device pointer is used in place, a host pointer is staged (grow-only scratch).
+static int stage_to(hvx_ctx* ctx, void** slot, uint64_t* cap, const void* ptr, uint64_t bytes, const void** out) {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
         cudaGetLastError();
@@ -557,26 +557,29 @@ static int stage_input(hvx_ctx* ctx, int which, const void* ptr, uint64_t bytes,
     }
     if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
         if (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device)
-            return fail(ctx, HVX_E_INVALID_ARGUMENT, "gather input lives on device %d, ctx is on device %d", attr.device, ctx->device);
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "input lives on device %d, ctx is on device %d", attr.device, ctx->device);
         *out = ptr;
         return HVX_OK;
     }
-    if (bytes > ctx->stage_bytes[which]) {
-        if (ctx->stage[which]) {
+    if (bytes > *cap) {
+        if (*slot) {
             HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->stage[which]);
-            ctx->allocated -= ctx->stage_bytes[which];
-            ctx->stage[which] = nullptr;
-            ctx->stage_bytes[which] = 0;
+            cudaFree(*slot);
+            ctx->allocated -= *cap;
+            *slot = nullptr;
+            *cap = 0;
         }
-        cudaError_t e = cudaMalloc(&ctx->stage[which], bytes);
+        cudaError_t e = cudaMalloc(slot, bytes);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
-        ctx->stage_bytes[which] = bytes;
+        *cap = bytes;
         ctx->allocated += bytes;
     }
-    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->stage[which], ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    *out = ctx->stage[which];
+    HVX_CUDA(ctx, cudaMemcpyAsync(*slot, ptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = *slot;
     return HVX_OK;
+}
+static int stage_input(hvx_ctx* ctx, int which, const void* ptr, uint64_t bytes, const void** out) {
+    return stage_to(ctx, &ctx->stage[which], &ctx->stage_bytes[which], ptr, bytes, out);
 }
 
 int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_page_table_entry* table,
@@ -630,6 +633,178 @@ int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_p
     cudaError_t e = launch_gather(p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_gather");
     ctx->launches += 2;
+    return HVX_OK;
+}
+
+// ---- surface publication ---------------------------------------------------------------
+struct hvx_publisher {
+    hvx_ctx* ctx = nullptr;
+    uint32_t slots = 0;
+    void* buf[HVX_PUB_COUNT] = {};
+    uint64_t bytes[HVX_PUB_COUNT] = {};
+    void* stage[4] = {nullptr, nullptr, nullptr, nullptr};  // jobs, job_chunk, page metadata, draw pages
+    uint64_t stage_bytes[4] = {0, 0, 0, 0};
+};
+
+int hvx_publisher_create(hvx_ctx* ctx, uint32_t slots, hvx_publisher** out) {
+    static_assert(sizeof(hvx_surface_job) == 48 && sizeof(hvx_page_meta) == 32 && sizeof(hvx_surface_state) == 48 &&
+                      sizeof(hvx_draw_page) == 48 && sizeof(hvx_surface_feedback) == 32 && sizeof(hvx_draw_indexed_indirect) == 20,
+                  "publication POD layouts");
+    if (!ctx || !out) return HVX_E_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (slots == 0) return fail(ctx, HVX_E_INVALID_CAPACITY, "a publisher needs at least one slot");
+    const hvx_config& c = ctx->cfg;
+    const uint64_t banks = 2ull * slots;
+    if (banks * c.max_vertices > 0x7fffffffull || banks * c.max_indices > 0xffffffffull ||
+        banks * c.max_transition_vertices > 0x7fffffffull || banks * c.max_transition_indices > 0xffffffffull)
+        return fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: %u slots x 2 banks exceed 32-bit draw arguments", slots);
+    DeviceGuard guard(ctx->device);
+    hvx_publisher* pub = new (std::nothrow) hvx_publisher;
+    if (!pub) return fail(ctx, HVX_E_DEVICE_LIMIT, "out of host memory");
+    pub->ctx = ctx;
+    pub->slots = slots;
+    pub->bytes[HVX_PUB_REGULAR_VERTICES] = banks * c.max_vertices * sizeof(hvx_vertex);
+    pub->bytes[HVX_PUB_REGULAR_INDICES] = banks * c.max_indices * 4ull;
+    pub->bytes[HVX_PUB_TRANSITION_VERTICES] = banks * c.max_transition_vertices * sizeof(hvx_vertex);
+    pub->bytes[HVX_PUB_TRANSITION_INDICES] = banks * c.max_transition_indices * 4ull;
+    pub->bytes[HVX_PUB_STATES] = slots * sizeof(hvx_surface_state);
+    pub->bytes[HVX_PUB_REGULAR_DRAWS] = slots * sizeof(hvx_draw_indexed_indirect);
+    pub->bytes[HVX_PUB_TRANSITION_DRAWS] = slots * sizeof(hvx_draw_indexed_indirect);
+    pub->bytes[HVX_PUB_FEEDBACK] = sizeof(hvx_surface_feedback);
+    for (int i = 0; i < HVX_PUB_COUNT; ++i) {
+        if (pub->bytes[i] == 0) continue;
+        cudaError_t e = cudaMalloc(&pub->buf[i], pub->bytes[i]);
+        if (e == cudaSuccess && i >= HVX_PUB_STATES) e = cudaMemsetAsync(pub->buf[i], 0, pub->bytes[i], ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            const int rc = fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: publisher buffer %d requires %llu bytes: %s", i,
+                                static_cast<unsigned long long>(pub->bytes[i]), cudaGetErrorString(e));
+            hvx_publisher_destroy(pub);
+            return rc;
+        }
+        ctx->allocated += pub->bytes[i];
+    }
+    *out = pub;
+    return HVX_OK;
+}
+
+void hvx_publisher_destroy(hvx_publisher* pub) {
+    if (!pub) return;
+    DeviceGuard guard(pub->ctx->device);
+    cudaStreamSynchronize(pub->ctx->stream);
+    for (int i = 0; i < HVX_PUB_COUNT; ++i)
+        if (pub->buf[i]) {
+            cudaFree(pub->buf[i]);
+            pub->ctx->allocated -= pub->bytes[i];
+        }
+    for (int i = 0; i < 4; ++i)
+        if (pub->stage[i]) {
+            cudaFree(pub->stage[i]);
+            pub->ctx->allocated -= pub->stage_bytes[i];
+        }
+    delete pub;
+}
+
+static void fill_publish_params(hvx_publisher* pub, PublishParams& p) {
+    hvx_ctx* ctx = pub->ctx;
+    p.slots = pub->slots;
+    p.has_transition = ctx->cfg.max_transition_vertices != 0 ? 1u : 0u;
+    p.src_max_vertices = ctx->cfg.max_vertices;
+    p.src_max_indices = ctx->cfg.max_indices;
+    p.src_max_tvertices = ctx->cfg.max_transition_vertices;
+    p.src_max_tindices = ctx->cfg.max_transition_indices;
+    p.regular_counters = static_cast<const hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
+    p.transition_counters = static_cast<const hvx_transition_counters*>(ctx->buf[HVX_BUF_TRANSITION_COUNTERS]);
+    p.src_vertices = static_cast<const hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);
+    p.src_indices = static_cast<const uint32_t*>(ctx->buf[HVX_BUF_REGULAR_INDICES]);
+    p.src_tvertices = static_cast<const hvx_vertex*>(ctx->buf[HVX_BUF_TRANSITION_VERTICES]);
+    p.src_tindices = static_cast<const uint32_t*>(ctx->buf[HVX_BUF_TRANSITION_INDICES]);
+    p.states = static_cast<hvx_surface_state*>(pub->buf[HVX_PUB_STATES]);
+    p.vertices = static_cast<hvx_vertex*>(pub->buf[HVX_PUB_REGULAR_VERTICES]);
+    p.indices = static_cast<uint32_t*>(pub->buf[HVX_PUB_REGULAR_INDICES]);
+    p.tvertices = static_cast<hvx_vertex*>(pub->buf[HVX_PUB_TRANSITION_VERTICES]);
+    p.tindices = static_cast<uint32_t*>(pub->buf[HVX_PUB_TRANSITION_INDICES]);
+    p.regular_draws = static_cast<hvx_draw_indexed_indirect*>(pub->buf[HVX_PUB_REGULAR_DRAWS]);
+    p.transition_draws = static_cast<hvx_draw_indexed_indirect*>(pub->buf[HVX_PUB_TRANSITION_DRAWS]);
+    p.feedback = static_cast<hvx_surface_feedback*>(pub->buf[HVX_PUB_FEEDBACK]);
+}
+
+int hvx_publish_surfaces(hvx_publisher* pub, const hvx_surface_job* jobs, const uint32_t* job_chunk,
+                         const hvx_page_meta* page_metadata, uint32_t n) {
+    if (!pub) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = pub->ctx;
+    if (n == 0) return HVX_OK;
+    if (!jobs || !job_chunk || !page_metadata) return fail(ctx, HVX_E_INVALID_ARGUMENT, "jobs, job_chunk and page_metadata must be non-NULL");
+    if (n > pub->slots) return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u jobs exceeds the publisher's %u slots", n, pub->slots);
+    const hvx_config& c = ctx->cfg;
+    std::vector<uint8_t> seen(pub->slots, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const hvx_surface_job& j = jobs[i];
+        if (j.slot >= pub->slots) return fail(ctx, HVX_E_INVALID_ARGUMENT, "job %u names slot %u of %u", i, j.slot, pub->slots);
+        if (seen[j.slot]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "slot %u appears twice in one publication batch", j.slot);
+        seen[j.slot] = 1;
+        if (job_chunk[i] >= c.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "job %u reads chunk %u of %u", i, job_chunk[i], c.max_chunks);
+        if (j.regular_max_vertices != c.max_vertices || j.regular_max_indices != c.max_indices ||
+            j.transition_max_vertices != c.max_transition_vertices || j.transition_max_indices != c.max_transition_indices)
+            return fail(ctx, HVX_E_INVALID_CAPACITY, "job %u was built for bank capacities (%u, %u, %u, %u); the publisher's are (%u, %u, %u, %u)", i,
+                        j.regular_max_vertices, j.regular_max_indices, j.transition_max_vertices, j.transition_max_indices,
+                        c.max_vertices, c.max_indices, c.max_transition_vertices, c.max_transition_indices);
+    }
+    DeviceGuard guard(ctx->device);
+    PublishParams p{};
+    fill_publish_params(pub, p);
+    p.n_jobs = n;
+    const void *dj = nullptr, *dc = nullptr, *dm = nullptr;
+    int rc;
+    if ((rc = stage_to(ctx, &pub->stage[0], &pub->stage_bytes[0], jobs, static_cast<uint64_t>(n) * sizeof(hvx_surface_job), &dj))) return rc;
+    if ((rc = stage_to(ctx, &pub->stage[1], &pub->stage_bytes[1], job_chunk, static_cast<uint64_t>(n) * 4, &dc))) return rc;
+    if ((rc = stage_to(ctx, &pub->stage[2], &pub->stage_bytes[2], page_metadata, static_cast<uint64_t>(pub->slots) * sizeof(hvx_page_meta), &dm))) return rc;
+    p.jobs = static_cast<const hvx_surface_job*>(dj);
+    p.job_chunk = static_cast<const uint32_t*>(dc);
+    p.meta = static_cast<const hvx_page_meta*>(dm);
+    cudaError_t e = launch_publish(p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_publish");
+    ctx->launches += 2;
+    return HVX_OK;
+}
+
+int hvx_refresh_visibility(hvx_publisher* pub, const hvx_draw_page* draw_pages) {
+    if (!pub) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = pub->ctx;
+    if (!draw_pages) return fail(ctx, HVX_E_INVALID_ARGUMENT, "draw_pages is NULL");
+    DeviceGuard guard(ctx->device);
+    PublishParams p{};
+    fill_publish_params(pub, p);
+    const void* dp = nullptr;
+    int rc;
+    if ((rc = stage_to(ctx, &pub->stage[3], &pub->stage_bytes[3], draw_pages, static_cast<uint64_t>(pub->slots) * sizeof(hvx_draw_page), &dp))) return rc;
+    p.draw_pages = static_cast<const hvx_draw_page*>(dp);
+    cudaError_t e = launch_visibility(p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_visibility");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+void* hvx_publisher_buffer(hvx_publisher* pub, int id) { return (pub && id >= 0 && id < HVX_PUB_COUNT) ? pub->buf[id] : nullptr; }
+uint64_t hvx_publisher_buffer_bytes(hvx_publisher* pub, int id) { return (pub && id >= 0 && id < HVX_PUB_COUNT) ? pub->bytes[id] : 0; }
+
+int hvx_publisher_read(hvx_publisher* pub, int id, uint64_t offset, uint64_t bytes, void* dst) {
+    if (!pub || id < 0 || id >= HVX_PUB_COUNT || !dst) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = pub->ctx;
+    if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of publisher buffer %d", id);
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(pub->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+int hvx_publisher_write(hvx_publisher* pub, int id, uint64_t offset, uint64_t bytes, const void* src) {
+    if (!pub || id < 0 || id >= HVX_PUB_COUNT || !src) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = pub->ctx;
+    if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of publisher buffer %d", id);
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(pub->buf[id]) + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HVX_OK;
 }
 

@@ -75,6 +75,30 @@ struct GatherParams {
     uint32_t* indirect;                // [n][24]
 };
 
+struct PublishParams {
+    uint32_t n_jobs, slots;
+    uint32_t has_transition;
+    uint32_t src_max_vertices, src_max_indices, src_max_tvertices, src_max_tindices;  // extraction slot strides
+    const hvx_surface_job* jobs;
+    const uint32_t* job_chunk;
+    const hvx_page_meta* meta;
+    const hvx_emission_counters* regular_counters;
+    const hvx_transition_counters* transition_counters;
+    const hvx_vertex* src_vertices;
+    const uint32_t* src_indices;
+    const hvx_vertex* src_tvertices;
+    const uint32_t* src_tindices;
+    hvx_surface_state* states;
+    hvx_vertex* vertices;
+    uint32_t* indices;
+    hvx_vertex* tvertices;
+    uint32_t* tindices;
+    hvx_draw_indexed_indirect* regular_draws;
+    hvx_draw_indexed_indirect* transition_draws;
+    hvx_surface_feedback* feedback;
+    const hvx_draw_page* draw_pages;
+};
+
 struct MeshletParams {
     uint32_t n_chunks;
     uint32_t transition;                  // 0 regular, 1 transition
@@ -104,6 +128,8 @@ cudaError_t launch_terrain_heights(int edge, const long long* col_xz, const uint
                                    cudaStream_t stream);
 cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_gather(const GatherParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_publish(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_visibility(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
 cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,
                         const hvx_range* packed_ranges, uint32_t n, hvx_vertex* out_vertices,

@@ -271,6 +271,85 @@ typedef struct {
 int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_page_table_entry* table,
                        const uint32_t* atlas, uint64_t atlas_words, const hvx_gather_job* jobs, uint32_t n);
 
+/* ---- surface publication (the step after extraction in the reference's pass) -------- */
+/* GpuSurfaceJob (PV/src/render.rs:466-480) */
+typedef struct {
+    uint32_t slot, transition_mask, generation_low, generation_high;
+    uint32_t regular_max_vertices, regular_max_indices, transition_max_vertices, transition_max_indices;
+    uint32_t regular_max_meshlets, transition_max_meshlets, _pad[2];
+} hvx_surface_job;
+/* GpuPageMeta (crates/helio-planet-voxel-core/src/gpu.rs:62-99) */
+typedef struct {
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod, slot, generation_low, generation_high, transition_mask;
+} hvx_page_meta;
+/* GpuSurfaceState (PV/src/render.rs:505-519) */
+typedef struct {
+    uint32_t generation_low, generation_high, active_bank, valid;
+    uint32_t regular_vertex_count, regular_index_count, transition_vertex_count, transition_index_count;
+    uint32_t regular_meshlet_count, transition_meshlet_count, _pad[2];
+} hvx_surface_state;
+/* GpuDrawPage (PV/src/render.rs:533-544) */
+typedef struct {
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod;
+    float camera_relative_m[3];
+    float lod0_cell_size_m;
+    uint32_t generation_low, generation_high, transition_mask, visible;
+} hvx_draw_page;
+/* GpuSurfaceFeedback (PV/src/render.rs:521-531) */
+typedef struct {
+    uint32_t submitted_jobs, published_jobs, stale_rejections, overflow_rejections, incomplete_rejections, _pad[3];
+} hvx_surface_feedback;
+/* DrawIndexedIndirectArgs (PV/src/render.rs:546-554) */
+typedef struct {
+    uint32_t index_count, instance_count, first_index;
+    int32_t base_vertex;
+    uint32_t first_instance;
+} hvx_draw_indexed_indirect;
+
+/* The double-banked per-slot arenas, surface states, indirect draws and feedback the reference's render
+ * pass owns (PV/src/render.rs), for `slots` residency slots.  Bank capacities are the ctx's per-chunk
+ * capacities: bank b of the regular arena starts at b * max_vertices / b * max_indices, b = slot*2 + bank. */
+typedef struct hvx_publisher hvx_publisher;
+int hvx_publisher_create(hvx_ctx* ctx, uint32_t slots, hvx_publisher** out);
+void hvx_publisher_destroy(hvx_publisher* pub);
+
+/* copy_regular_surface + copy_transition_surface + publish_surface (PV/src/surface_publish.wgsl:125-216)
+ * for n jobs of the ctx's last regular (and, if the ctx has transition capacity, transition) extraction.
+ * job_chunk[i] names the extraction chunk that holds job i's meshes and counters.  Per job, exactly like
+ * the shader: a job whose page metadata moved on (slot / generation mismatch) is a stale rejection; an
+ * incomplete or overflowed extraction is rejected; otherwise the meshes are copied into the slot's
+ * INACTIVE bank (only emitted_vertices / emitted_indices elements, not a capacity-sized dispatch), the
+ * state flips to that bank with the new generation and counts, and both DrawIndexedIndirectArgs are
+ * rewritten with instance_count 0 (visibility is granted by hvx_refresh_visibility).  A ctx without
+ * transition capacity publishes empty, completed transition counters (what the reference's transition
+ * extractor reports for mask 0).  Slots must be distinct within one call (the reference handles one job
+ * per submission; two jobs for one slot in one batch would race on the bank).
+ *   jobs, job_chunk: HOST, n entries.   page_metadata: HOST or DEVICE, `slots` entries. */
+int hvx_publish_surfaces(hvx_publisher* pub, const hvx_surface_job* jobs, const uint32_t* job_chunk,
+                         const hvx_page_meta* page_metadata, uint32_t n);
+/* refresh_visibility (PV/src/surface_publish.wgsl:218-225): instance_count = valid && visible, per slot.
+ *   draw_pages: HOST or DEVICE, `slots` entries. */
+int hvx_refresh_visibility(hvx_publisher* pub, const hvx_draw_page* draw_pages);
+
+typedef enum {
+    HVX_PUB_REGULAR_VERTICES = 0,     /* hvx_vertex [slots*2][max_vertices] */
+    HVX_PUB_REGULAR_INDICES = 1,      /* u32 [slots*2][max_indices] */
+    HVX_PUB_TRANSITION_VERTICES = 2,  /* hvx_vertex [slots*2][max_transition_vertices] (if enabled) */
+    HVX_PUB_TRANSITION_INDICES = 3,
+    HVX_PUB_STATES = 4,               /* hvx_surface_state [slots] */
+    HVX_PUB_REGULAR_DRAWS = 5,        /* hvx_draw_indexed_indirect [slots] */
+    HVX_PUB_TRANSITION_DRAWS = 6,
+    HVX_PUB_FEEDBACK = 7,             /* hvx_surface_feedback [1] */
+    HVX_PUB_COUNT = 8
+} hvx_publisher_buffer_id;
+void* hvx_publisher_buffer(hvx_publisher* pub, int buffer_id);
+uint64_t hvx_publisher_buffer_bytes(hvx_publisher* pub, int buffer_id);
+/* synchronising copies (the states / draws / feedback are caller-visible render state) */
+int hvx_publisher_read(hvx_publisher* pub, int buffer_id, uint64_t byte_offset, uint64_t bytes, void* dst);
+int hvx_publisher_write(hvx_publisher* pub, int buffer_id, uint64_t byte_offset, uint64_t bytes, const void* src);
+
 /* ---- outputs ------------------------------------------------------------------------ */
 typedef enum {
     HVX_BUF_SAMPLES = 0,             /* u32  [max_chunks][(edge+2)^3]          (lazy) */

@@ -1119,3 +1119,74 @@ void hvxo_gather_surface(const hvxo_residency* res, const hvxo_page_table_entry*
         indirect[3 * i + 2] = 1u;
     }
 }
+
+/* ================================================================================================
+ * Surface publication, PV/src/surface_publish.wgsl:104-225 line by line.
+ * ============================================================================================== */
+static int publish_metadata_is_current(const hvxo_surface_job* job, const hvxo_page_meta* meta) { /* :107-112 */
+    const hvxo_page_meta* m = &meta[job->slot];
+    return m->slot == job->slot && m->generation_low == job->generation_low && m->generation_high == job->generation_high;
+}
+
+void hvxo_publish_surface(const hvxo_surface_job* job, const hvxo_page_meta* meta, const uint32_t* rc, const uint32_t* tc,
+                          const hvxo_vertex* src_v, const uint32_t* src_i, const hvxo_vertex* src_tv, const uint32_t* src_ti,
+                          hvxo_surface_state* states, hvxo_vertex* v, uint32_t* idx, hvxo_vertex* tv, uint32_t* tidx,
+                          hvxo_draw_args* rdraw, hvxo_draw_args* tdraw, hvxo_surface_feedback* fb) {
+    /* emission counters: required_v, required_i, emitted_v, emitted_i, v_overflow, i_overflow, completed, pad
+     * transition counters: active_cells, active_faces, required_v, required_i, emitted_v, emitted_i, v_ovf, i_ovf, completed */
+    const uint32_t r_ev = rc[2], r_ei = rc[3], r_vo = rc[4], r_io = rc[5], r_done = rc[6];
+    const uint32_t t_ev = tc[4], t_ei = tc[5], t_vo = tc[6], t_io = tc[7], t_done = tc[8];
+    const int current = publish_metadata_is_current(job, meta);
+    const uint32_t active = states[job->slot].active_bank;
+    const uint32_t next_bank = 1u - (active < 1u ? active : 1u);
+    const uint32_t bank = job->slot * 2u + next_bank;
+    /* copy_regular_surface, :125-136 */
+    if (r_done != 0u && r_vo == 0u && r_io == 0u && current) {
+        if (v && src_v) memcpy(v + (size_t)bank * job->regular_max_vertices, src_v, (size_t)r_ev * sizeof(hvxo_vertex));
+        if (idx && src_i) memcpy(idx + (size_t)bank * job->regular_max_indices, src_i, (size_t)r_ei * 4u);
+    }
+    /* copy_transition_surface, :151-162 */
+    if (t_done != 0u && t_vo == 0u && t_io == 0u && current) {
+        if (tv && src_tv) memcpy(tv + (size_t)bank * job->transition_max_vertices, src_tv, (size_t)t_ev * sizeof(hvxo_vertex));
+        if (tidx && src_ti) memcpy(tidx + (size_t)bank * job->transition_max_indices, src_ti, (size_t)t_ei * 4u);
+    }
+    /* publish_surface, :166-216 */
+    fb->submitted_jobs += 1u;
+    if (!current) {
+        fb->stale_rejections += 1u;
+        return;
+    }
+    if (r_done == 0u || t_done == 0u) {
+        fb->incomplete_rejections += 1u;
+        return;
+    }
+    if (r_vo != 0u || r_io != 0u || t_vo != 0u || t_io != 0u) {
+        fb->overflow_rejections += 1u;
+        return;
+    }
+    hvxo_surface_state s;
+    memset(&s, 0, sizeof(s));
+    s.generation_low = job->generation_low;
+    s.generation_high = job->generation_high;
+    s.active_bank = next_bank;
+    s.valid = 1u;
+    s.regular_vertex_count = r_ev;
+    s.regular_index_count = r_ei;
+    s.transition_vertex_count = t_ev;
+    s.transition_index_count = t_ei;
+    s.regular_meshlet_count = (r_ei + 62u) / 63u;
+    s.transition_meshlet_count = (t_ei + 62u) / 63u;
+    states[job->slot] = s;
+    rdraw[job->slot] = (hvxo_draw_args){r_ei, 0u, bank * job->regular_max_indices, (int32_t)(bank * job->regular_max_vertices), job->slot};
+    tdraw[job->slot] = (hvxo_draw_args){t_ei, 0u, bank * job->transition_max_indices, (int32_t)(bank * job->transition_max_vertices), job->slot};
+    fb->published_jobs += 1u;
+}
+
+void hvxo_refresh_visibility(uint32_t slots, const hvxo_surface_state* states, const uint32_t* visible,
+                             hvxo_draw_args* rdraw, hvxo_draw_args* tdraw) {
+    for (uint32_t i = 0; i < slots; ++i) {
+        const uint32_t vis = (states[i].valid != 0u && visible[i] != 0u) ? 1u : 0u;
+        rdraw[i].instance_count = vis;
+        tdraw[i].instance_count = vis;
+    }
+}

@@ -202,3 +202,40 @@ uint32_t hvxo_page_hash(const uint32_t planet_id[4], const int32_t relative_min[
 void hvxo_gather_surface(const hvxo_residency* residency, const hvxo_page_table_entry* table, const uint32_t* atlas,
                          const hvxo_gather_job* job, uint32_t* regular, uint32_t* transition,
                          hvxo_gather_counters* counters, uint32_t* indirect);
+
+/* ---- surface publication: literal restatement of PV/src/surface_publish.wgsl ---------- */
+typedef struct {
+    uint32_t slot, transition_mask, generation_low, generation_high;
+    uint32_t regular_max_vertices, regular_max_indices, transition_max_vertices, transition_max_indices;
+    uint32_t regular_max_meshlets, transition_max_meshlets, _pad[2];
+} hvxo_surface_job; /* GpuSurfaceJob, PV/src/render.rs:466-480 */
+typedef struct {
+    int32_t relative_lod0_cell_min[3];
+    uint32_t lod, slot, generation_low, generation_high, transition_mask;
+} hvxo_page_meta; /* GpuPageMeta, crates/helio-planet-voxel-core/src/gpu.rs:62-99 */
+typedef struct {
+    uint32_t generation_low, generation_high, active_bank, valid;
+    uint32_t regular_vertex_count, regular_index_count, transition_vertex_count, transition_index_count;
+    uint32_t regular_meshlet_count, transition_meshlet_count, _pad[2];
+} hvxo_surface_state; /* GpuSurfaceState, PV/src/render.rs:505-519 */
+typedef struct {
+    uint32_t submitted_jobs, published_jobs, stale_rejections, overflow_rejections, incomplete_rejections, _pad[3];
+} hvxo_surface_feedback; /* GpuSurfaceFeedback, PV/src/render.rs:521-531 */
+typedef struct {
+    uint32_t index_count, instance_count, first_index;
+    int32_t base_vertex;
+    uint32_t first_instance;
+} hvxo_draw_args; /* DrawIndexedIndirectArgs, PV/src/render.rs:546-554 */
+
+/* One job: copy_regular_surface, copy_transition_surface, publish_surface (surface_publish.wgsl:125-216).
+ * regular_counters: 8 words (GpuTransvoxelEmissionCounters), transition_counters: 12 words
+ * (GpuTransvoxelTransitionCounters).  Source meshes start at element 0; destination arenas are the
+ * double-banked per-slot arenas (any of the four mesh pointers may be NULL to skip that copy). */
+void hvxo_publish_surface(const hvxo_surface_job* job, const hvxo_page_meta* page_metadata, const uint32_t* regular_counters,
+                          const uint32_t* transition_counters, const hvxo_vertex* src_vertices, const uint32_t* src_indices,
+                          const hvxo_vertex* src_tvertices, const uint32_t* src_tindices, hvxo_surface_state* states,
+                          hvxo_vertex* vertices, uint32_t* indices, hvxo_vertex* tvertices, uint32_t* tindices,
+                          hvxo_draw_args* regular_draws, hvxo_draw_args* transition_draws, hvxo_surface_feedback* feedback);
+/* refresh_visibility (surface_publish.wgsl:218-225); visible[i] is GpuDrawPage.visible of slot i */
+void hvxo_refresh_visibility(uint32_t slots, const hvxo_surface_state* states, const uint32_t* visible,
+                             hvxo_draw_args* regular_draws, hvxo_draw_args* transition_draws);
