@@ -31,6 +31,58 @@ pub struct hvx_chunk_desc {
 #[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
 pub struct hvx_range { pub first_vertex: u32, pub vertex_count: u32, pub first_index: u32, pub index_count: u32 }
 
+#[repr(C)]
+pub struct hvx_publisher { _private: [u8; 0] }
+
+/// `GpuSurfaceJob` (PV/src/render.rs:466-480).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_surface_job {
+    pub slot: u32, pub transition_mask: u32, pub generation_low: u32, pub generation_high: u32,
+    pub regular_max_vertices: u32, pub regular_max_indices: u32, pub transition_max_vertices: u32, pub transition_max_indices: u32,
+    pub regular_max_meshlets: u32, pub transition_max_meshlets: u32, pub _pad: [u32; 2],
+}
+
+/// `GpuPageMeta` (crates/helio-planet-voxel-core/src/gpu.rs:62-99).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_page_meta {
+    pub relative_lod0_cell_min: [i32; 3], pub lod: u32, pub slot: u32, pub generation_low: u32, pub generation_high: u32,
+    pub transition_mask: u32,
+}
+
+/// `GpuSurfaceState` (PV/src/render.rs:505-519).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_surface_state {
+    pub generation_low: u32, pub generation_high: u32, pub active_bank: u32, pub valid: u32,
+    pub regular_vertex_count: u32, pub regular_index_count: u32, pub transition_vertex_count: u32, pub transition_index_count: u32,
+    pub regular_meshlet_count: u32, pub transition_meshlet_count: u32, pub _pad: [u32; 2],
+}
+
+/// `GpuDrawPage` (PV/src/render.rs:533-544).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq)]
+pub struct hvx_draw_page {
+    pub relative_lod0_cell_min: [i32; 3], pub lod: u32, pub camera_relative_m: [f32; 3], pub lod0_cell_size_m: f32,
+    pub generation_low: u32, pub generation_high: u32, pub transition_mask: u32, pub visible: u32,
+}
+
+/// `GpuSurfaceFeedback` (PV/src/render.rs:521-531).
+#[repr(C, align(16))]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_surface_feedback {
+    pub submitted_jobs: u32, pub published_jobs: u32, pub stale_rejections: u32, pub overflow_rejections: u32,
+    pub incomplete_rejections: u32, pub _pad: [u32; 3],
+}
+
+/// `DrawIndexedIndirectArgs` (PV/src/render.rs:546-554).
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
+pub struct hvx_draw_indexed_indirect {
+    pub index_count: u32, pub instance_count: u32, pub first_index: u32, pub base_vertex: i32, pub first_instance: u32,
+}
+
 /// `GpuPageTableEntry` (PV/src/table.rs:8-19) -- bytemuck-castable from the reference's own type.
 #[repr(C, align(16))]
 #[derive(Clone, Copy, Debug, Default, PartialEq, Eq)]
@@ -119,6 +171,15 @@ extern "C" {
     pub fn hvx_classify_regular(ctx: *mut hvx_ctx, samples: *const u32, sample_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
     pub fn hvx_extract_transition(ctx: *mut hvx_ctx, slabs: *const u32, slab_words: u64, descs: *const hvx_chunk_desc, n: u32) -> c_int;
     pub fn hvx_build_meshlets(ctx: *mut hvx_ctx, kind: c_int, n: u32) -> c_int;
+    pub fn hvx_publisher_create(ctx: *mut hvx_ctx, slots: u32, out: *mut *mut hvx_publisher) -> c_int;
+    pub fn hvx_publisher_destroy(publisher: *mut hvx_publisher);
+    pub fn hvx_publish_surfaces(publisher: *mut hvx_publisher, jobs: *const hvx_surface_job, job_chunk: *const u32,
+                                page_metadata: *const hvx_page_meta, n: u32) -> c_int;
+    pub fn hvx_refresh_visibility(publisher: *mut hvx_publisher, draw_pages: *const hvx_draw_page) -> c_int;
+    pub fn hvx_publisher_buffer(publisher: *mut hvx_publisher, buffer_id: c_int) -> *mut c_void;
+    pub fn hvx_publisher_buffer_bytes(publisher: *mut hvx_publisher, buffer_id: c_int) -> u64;
+    pub fn hvx_publisher_read(publisher: *mut hvx_publisher, buffer_id: c_int, byte_offset: u64, bytes: u64, dst: *mut c_void) -> c_int;
+    pub fn hvx_publisher_write(publisher: *mut hvx_publisher, buffer_id: c_int, byte_offset: u64, bytes: u64, src: *const c_void) -> c_int;
     pub fn hvx_gather_surface(ctx: *mut hvx_ctx, residency: *const hvx_residency, table: *const hvx_page_table_entry,
                               atlas: *const u32, atlas_words: u64, jobs: *const hvx_gather_job, n: u32) -> c_int;
     pub fn hvx_buffer(ctx: *mut hvx_ctx, buffer_id: c_int) -> *mut c_void;
