@@ -178,6 +178,24 @@ def main():
                 "note": "every call also stages the 384 KB page table and the job array from the host"})
     out.append({"case": f"gather_then_extract_{nj}x32^3", **r_ge, "pages_per_s": nj / (r_ge["ms_median"] * 1e-3),
                 "vertices": int(ec["emitted_vertices"].astype(np.int64).sum())})
+    # the reference's whole per-page pass, batched and device-resident: gather -> extract -> meshlets -> publish
+    pub = H.SurfacePublisher(gctx, nj)
+    meta = np.zeros(nj, dtype=H.PAGE_META_DTYPE)
+    meta["relative_lod0_cell_min"], meta["slot"], meta["generation_low"] = jobs["relative_lod0_cell_min"], np.arange(nj), 5
+    sjobs = np.concatenate([pub.surface_job(i, 5) for i in range(nj)])
+    chunks = np.arange(nj, dtype=np.uint32)
+
+    def whole_pass():
+        sampler.dispatch(res, table, atlas, jobs)
+        sampler.extract()
+        gctx.build_meshlets(nj, 0)
+        pub.publish(sjobs, chunks, meta)
+
+    r_all = timed(stream, whole_pass, 2, 10)
+    fb = pub.feedback()
+    out.append({"case": f"gather_extract_meshlets_publish_{nj}x32^3", **r_all, "pages_per_s": nj / (r_all["ms_median"] * 1e-3),
+                "published_per_call": int(fb["published_jobs"]) // 12, "note": "the reference runs this pass for one page per frame"})
+    pub.close()
     gctx.close()
     for o in out:
         print(json.dumps(o))
