@@ -350,9 +350,132 @@ uint64_t hvx_publisher_buffer_bytes(hvx_publisher* pub, int buffer_id);
 int hvx_publisher_read(hvx_publisher* pub, int buffer_id, uint64_t byte_offset, uint64_t bytes, void* dst);
 int hvx_publisher_write(hvx_publisher* pub, int buffer_id, uint64_t byte_offset, uint64_t bytes, const void* src);
 
+/* ---- bounded extraction publisher: variable-size arena placement ------------------ */
+/* The reference's generation-safe bounded publication contract, PV/src/extraction.rs:8-704
+ * (GpuExtractionRequest, GpuExtractionRange, GpuExtractionCounters, ExtractionLimits,
+ * BoundedExtractionPublisher, first-fit RangeAllocator).  Host-side bookkeeping is plain C++; the one
+ * device step (hvx_extraction_commit) moves a reserved page's mesh out of its fixed-stride extraction
+ * slot into the bounded, tightly packed arenas at the reserved ranges. */
+typedef struct {            /* GpuExtractionRequest, PV/src/extraction.rs:10-21 (32 B) */
+    uint32_t page_slot, generation_low, generation_high, transition_mask;
+    uint32_t dirty_microbricks_low, dirty_microbricks_high, _pad[2];
+} hvx_extraction_request;
+typedef struct {            /* GpuExtractionRange, PV/src/extraction.rs:54-65 (32 B) */
+    uint32_t first_vertex, vertex_count, first_index, index_count;
+    uint32_t first_meshlet, meshlet_count, generation_low, generation_high;
+} hvx_extraction_range;
+typedef struct {            /* GpuExtractionCounters, PV/src/extraction.rs:94-109 (48 B) */
+    uint32_t requests, active_cells, vertices, indices, meshlets, completed, stale_rejected, overflowed;
+    uint32_t vertex_overflow, index_overflow, meshlet_overflow, _pad;
+} hvx_extraction_counters;
+typedef struct {            /* ExtractionLimits, PV/src/extraction.rs:111-118 */
+    uint32_t max_page_slots, max_pending_pages, max_vertices, max_indices, max_meshlets;
+} hvx_extraction_limits;
+typedef struct {            /* ExtractionAllocationPlan, PV/src/extraction.rs:212-221 */
+    uint64_t request_bytes, page_range_bytes, vertex_bytes, index_bytes, meshlet_bytes, counter_bytes, total_bytes;
+} hvx_extraction_plan;
+typedef struct {            /* PlanetPageKey, helio-planet-voxel-core/src/types.rs:312-316 */
+    uint8_t planet_id[16];
+    int64_t page_xyz[3];
+    uint8_t lod, _pad[7];
+} hvx_planet_page_key;
+typedef struct { uint32_t vertices, indices, meshlets; } hvx_surface_counts;       /* SurfaceCounts :223-228 */
+typedef struct { uint32_t first, count; } hvx_arena_slice;                         /* ArenaSlice :246-250 */
+typedef struct { hvx_arena_slice vertices, indices, meshlets; } hvx_surface_allocation; /* :252-257 */
+typedef struct {            /* ExtractionReservation :283-288 */
+    hvx_planet_page_key key;
+    uint64_t generation;
+    hvx_surface_allocation allocation;
+} hvx_reservation;
+typedef struct {            /* PublishedSurface :290-294 */
+    uint64_t generation;
+    hvx_surface_allocation allocation;
+} hvx_published_surface;
+typedef enum {              /* ReservationOutcome :296-302 */
+    HVX_RESERVED = 0, HVX_RESERVE_CURRENT = 1, HVX_RESERVE_DUPLICATE_PENDING = 2, HVX_RESERVE_STALE = 3
+} hvx_reservation_kind;
+typedef struct {
+    uint32_t kind;                       /* hvx_reservation_kind */
+    uint32_t detail;                     /* on HVX_E_ARENA_CAPACITY: 0 vertices, 1 indices, 2 meshlets; on
+                                            HVX_E_PENDING_CAPACITY: the maximum */
+    hvx_reservation reservation;         /* RESERVED, DUPLICATE_PENDING */
+    hvx_published_surface current;       /* CURRENT */
+    uint64_t newest_generation;          /* STALE */
+} hvx_reservation_outcome;
+typedef struct {            /* PublicationOutcome :304-313; kind 0 Published, 1 Stale */
+    uint32_t kind, has_replaced;
+    hvx_published_surface current, replaced;
+    uint64_t newest_generation;
+} hvx_publication_outcome;
+typedef struct {            /* ExtractionEvictOutcome :315-320; kind 0 Evicted, 1 Missing, 2 Stale */
+    uint32_t kind, _pad;
+    uint64_t newest_generation;
+} hvx_evict_outcome;
+typedef struct {            /* ExtractionPublisherCounters :322-340 */
+    uint64_t current_pages, pending_pages;
+    uint32_t used_vertices, used_indices, used_meshlets, _pad0;
+    uint64_t pending_high_water;
+    uint32_t vertex_high_water, index_high_water, meshlet_high_water, _pad1;
+    uint64_t reservations, publications, replacements, cancellations, evictions, stale_rejected, backpressured;
+} hvx_extraction_publisher_counters;
+
+/* GpuExtractionRequest::new (:24-42): HVX_E_TRANSITION_MASK for bits outside the six faces. */
+int hvx_extraction_request_new(uint32_t page_slot, uint64_t generation, uint32_t transition_mask,
+                               uint64_t dirty_microbricks, hvx_extraction_request* out);
+/* ExtractionLimits::new + allocation_plan (:121-178): HVX_E_INVALID_LIMITS / HVX_E_ARITHMETIC_OVERFLOW. */
+int hvx_extraction_limits_plan(const hvx_extraction_limits* limits, hvx_extraction_plan* plan_out);
+/* ExtractionLimits::validate_device (:180-203) against wgpu-style limits: HVX_E_DEVICE_BUFFER_LIMIT with
+ * *name_out = the first buffer that does not fit ("terrain vertices", ...) and *requested_out its bytes. */
+int hvx_extraction_limits_validate_device(const hvx_extraction_limits* limits, uint64_t max_buffer_size,
+                                          uint64_t max_storage_buffer_binding_size, const char** name_out,
+                                          uint64_t* requested_out);
+/* SurfaceAllocation::gpu_range (:268-280). */
+void hvx_extraction_gpu_range(const hvx_surface_allocation* allocation, uint64_t generation, hvx_extraction_range* out);
+
+typedef struct hvx_extraction_publisher hvx_extraction_publisher;
+/* BoundedExtractionPublisher::new (:357-367); limits are validated like ExtractionLimits::new. */
+int hvx_extraction_publisher_create(const hvx_extraction_limits* limits, hvx_extraction_publisher** out);
+void hvx_extraction_publisher_destroy(hvx_extraction_publisher* pub);
+/* reserve (:398-479), publish (:481-518), cancel_pending (:520-539), evict (:541-566). */
+int hvx_extraction_reserve(hvx_extraction_publisher* pub, const hvx_planet_page_key* key, uint64_t generation,
+                           const hvx_surface_counts* counts, hvx_reservation_outcome* out);
+int hvx_extraction_publish(hvx_extraction_publisher* pub, const hvx_reservation* reservation,
+                           hvx_publication_outcome* out);
+int hvx_extraction_cancel_pending(hvx_extraction_publisher* pub, const hvx_planet_page_key* key, uint64_t generation,
+                                  int* cancelled_out);
+int hvx_extraction_evict(hvx_extraction_publisher* pub, const hvx_planet_page_key* key, uint64_t generation,
+                         hvx_evict_outcome* out);
+/* current / pending (:373-379): return 1 and fill *out if present, 0 if not. */
+int hvx_extraction_current(const hvx_extraction_publisher* pub, const hvx_planet_page_key* key,
+                           hvx_published_surface* out);
+int hvx_extraction_pending(const hvx_extraction_publisher* pub, const hvx_planet_page_key* key, hvx_reservation* out);
+/* counters (:381-396). */
+int hvx_extraction_publisher_counters(const hvx_extraction_publisher* pub, hvx_extraction_publisher_counters* out);
+
+/* Device side of the contract.  attach: allocate the plan's bounded arenas on the ctx's device
+ * (vertices, indices, page ranges, counters).  commit: for n reserved pages, copy the REGULAR mesh of
+ * extraction chunk chunk[i] (ctx's last hvx_extract_regular) to the reserved vertex / index ranges and
+ * write page_ranges[page_slot[i]] = gpu_range(generation); one launch for the whole batch, 16 bytes per
+ * thread.  A reservation whose counts differ from what the chunk emitted (or a chunk that overflowed) is
+ * not copied: it bumps counters.overflowed and leaves the page range untouched.  The caller then calls
+ * hvx_extraction_publish (host) -- the old ranges are recycled only after that, like the reference. */
+int hvx_extraction_publisher_attach(hvx_extraction_publisher* pub, hvx_ctx* ctx);
+int hvx_extraction_commit(hvx_extraction_publisher* pub, const uint32_t* chunk, const uint32_t* page_slot,
+                          const hvx_reservation* reservations, uint32_t n);
+typedef enum {
+    HVX_XPUB_VERTICES = 0,    /* hvx_vertex [max_vertices] */
+    HVX_XPUB_INDICES = 1,     /* u32 [max_indices] */
+    HVX_XPUB_PAGE_RANGES = 2, /* hvx_extraction_range [max_page_slots] */
+    HVX_XPUB_COUNTERS = 3,    /* hvx_extraction_counters [1] */
+    HVX_XPUB_COUNT = 4
+} hvx_extraction_publisher_buffer_id;
+void* hvx_extraction_publisher_buffer(hvx_extraction_publisher* pub, int buffer_id);
+int hvx_extraction_publisher_read(hvx_extraction_publisher* pub, int buffer_id, uint64_t byte_offset, uint64_t bytes,
+                                  void* dst);
+
 /* ---- outputs ------------------------------------------------------------------------ */
 typedef enum {
-    HVX_BUF_SAMPLES = 0,             /* u32  [max_chunks][(edge+2)^3]          (lazy) */
+    HVX_BUF_SAMPLES = 0,            /* u32  [max_chunks][(edge+2)^3]          (lazy) */
     HVX_BUF_SLABS = 1,               /* u32  [max_chunks][6*3*(2*edge+3)^2]    (lazy) */
     HVX_BUF_REGULAR_VERTICES = 2,    /* hvx_vertex [max_chunks][max_vertices]            vertices_buffer() */
     HVX_BUF_REGULAR_INDICES = 3,     /* u32  [max_chunks][max_indices]                   indices_buffer()  */
