@@ -12,6 +12,11 @@ from .errors import (AddressError, BatchCapacity, CudaError, DeviceLimit, Finest
                      InvalidExtractionCapacity, SampleCount, TerrainLodTopologyError, TransitionDeviceLimit,
                      TransitionInvalidExtractionCapacity, TransitionMask, TransitionSampleCount,
                      TransvoxelGpuError, TransvoxelTransitionGpuError)
+from .extraction import (EXTRACTION_COUNTERS_DTYPE, EXTRACTION_RANGE_DTYPE, EXTRACTION_REQUEST_DTYPE, ArenaSlice,
+                         BoundedExtractionPublisher, ExtractionAllocationPlan, ExtractionError, ExtractionEvictOutcome,
+                         ExtractionLimits, ExtractionPublisherCounters, ExtractionReservation, GpuExtractionRequest,
+                         PlanetPageKey, PublicationOutcome, PublishedSurface, ReservationOutcome, SurfaceAllocation,
+                         SurfaceCounts)
 from .extractor import (EXTRACTION_SAMPLE_COUNT, TRANSITION_ALL_FACE_SLAB_SAMPLE_COUNT,
                         TRANSVOXEL_SCAN_WORKGROUP_SIZE, ChunkBatchExtractor, ResourceStats, TransvoxelGpuClassifier,
                         TransvoxelGpuExtractor, TransvoxelGpuExtractorConfig, TransvoxelGpuTransitionExtractor,

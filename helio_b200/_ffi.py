@@ -32,7 +32,19 @@ HVX_E_TOPOLOGY_PAGE_BUDGET = -26
 HVX_E_TOPOLOGY_MISSING_PARENT = -27
 HVX_E_TOPOLOGY_COVERAGE = -28
 
+HVX_E_INVALID_LIMITS = -40
+HVX_E_ARITHMETIC_OVERFLOW = -41
+HVX_E_NON_TRIANGLE_INDEX_COUNT = -42
+HVX_E_INCOMPLETE_SURFACE_COUNTS = -43
+HVX_E_PENDING_CAPACITY = -44
+HVX_E_ARENA_CAPACITY = -45
+HVX_E_GENERATION_CONFLICT = -46
+HVX_E_RESERVATION_MISSING = -47
+HVX_E_RESERVATION_MISMATCH = -48
+HVX_E_DEVICE_BUFFER_LIMIT = -49
+
 HVX_CFG_DEBUG_RECORDS = 1
+(XPUB_VERTICES, XPUB_INDICES, XPUB_PAGE_RANGES, XPUB_COUNTERS) = range(4)
 (PUB_REGULAR_VERTICES, PUB_REGULAR_INDICES, PUB_TRANSITION_VERTICES, PUB_TRANSITION_INDICES, PUB_STATES, PUB_REGULAR_DRAWS,
  PUB_TRANSITION_DRAWS, PUB_FEEDBACK) = range(8)
 
@@ -70,6 +82,77 @@ class LodStats(C.Structure):
                 ("transition_faces", C.c_uint32)]
 
 
+# ---- bounded extraction publisher (PV/src/extraction.rs) ------------------------------------------------
+def _u32s(*names):
+    return [(n, C.c_uint32) for n in names]
+
+
+class ExtractionRequest(C.Structure):
+    _fields_ = _u32s("page_slot", "generation_low", "generation_high", "transition_mask", "dirty_microbricks_low",
+                     "dirty_microbricks_high") + [("_pad", C.c_uint32 * 2)]
+
+
+class ExtractionRange(C.Structure):
+    _fields_ = _u32s("first_vertex", "vertex_count", "first_index", "index_count", "first_meshlet", "meshlet_count",
+                     "generation_low", "generation_high")
+
+
+class ExtractionLimits(C.Structure):
+    _fields_ = _u32s("max_page_slots", "max_pending_pages", "max_vertices", "max_indices", "max_meshlets")
+
+
+class ExtractionPlan(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("request_bytes", "page_range_bytes", "vertex_bytes", "index_bytes",
+                                          "meshlet_bytes", "counter_bytes", "total_bytes")]
+
+
+class PlanetPageKey(C.Structure):
+    _fields_ = [("planet_id", C.c_uint8 * 16), ("page_xyz", C.c_int64 * 3), ("lod", C.c_uint8), ("_pad", C.c_uint8 * 7)]
+
+
+class SurfaceCounts(C.Structure):
+    _fields_ = _u32s("vertices", "indices", "meshlets")
+
+
+class ArenaSlice(C.Structure):
+    _fields_ = _u32s("first", "count")
+
+
+class SurfaceAllocation(C.Structure):
+    _fields_ = [("vertices", ArenaSlice), ("indices", ArenaSlice), ("meshlets", ArenaSlice)]
+
+
+class Reservation(C.Structure):
+    _fields_ = [("key", PlanetPageKey), ("generation", C.c_uint64), ("allocation", SurfaceAllocation)]
+
+
+class PublishedSurface(C.Structure):
+    _fields_ = [("generation", C.c_uint64), ("allocation", SurfaceAllocation)]
+
+
+class ReservationOutcome(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("detail", C.c_uint32), ("reservation", Reservation), ("current", PublishedSurface),
+                ("newest_generation", C.c_uint64)]
+
+
+class PublicationOutcome(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("has_replaced", C.c_uint32), ("current", PublishedSurface),
+                ("replaced", PublishedSurface), ("newest_generation", C.c_uint64)]
+
+
+class EvictOutcome(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("_pad", C.c_uint32), ("newest_generation", C.c_uint64)]
+
+
+class ExtractionPublisherCounters(C.Structure):
+    _fields_ = [("current_pages", C.c_uint64), ("pending_pages", C.c_uint64), ("used_vertices", C.c_uint32),
+                ("used_indices", C.c_uint32), ("used_meshlets", C.c_uint32), ("_pad0", C.c_uint32),
+                ("pending_high_water", C.c_uint64), ("vertex_high_water", C.c_uint32), ("index_high_water", C.c_uint32),
+                ("meshlet_high_water", C.c_uint32), ("_pad1", C.c_uint32)] + \
+               [(n, C.c_uint64) for n in ("reservations", "publications", "replacements", "cancellations", "evictions",
+                                          "stale_rejected", "backpressured")]
+
+
 # every symbol include/hvx.h declares; tests assert the library exports all of them
 EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
@@ -79,6 +162,12 @@ EXPORTS = [
     "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
     "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
     "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost",
+    "hvx_extraction_request_new", "hvx_extraction_limits_plan", "hvx_extraction_limits_validate_device",
+    "hvx_extraction_gpu_range", "hvx_extraction_publisher_create", "hvx_extraction_publisher_destroy",
+    "hvx_extraction_reserve", "hvx_extraction_publish", "hvx_extraction_cancel_pending", "hvx_extraction_evict",
+    "hvx_extraction_current", "hvx_extraction_pending", "hvx_extraction_publisher_get_counters",
+    "hvx_extraction_publisher_attach", "hvx_extraction_commit", "hvx_extraction_publisher_buffer",
+    "hvx_extraction_publisher_read",
 ]
 
 _lib = None
@@ -146,5 +235,27 @@ def load() -> C.CDLL:
     L.hvx_partition_chunks.argtypes = [u64p, C.c_uint32, C.c_uint32, u32p]
     L.hvx_chunk_cost.argtypes = [C.c_uint32, C.c_uint32]
     L.hvx_chunk_cost.restype = C.c_uint64
+    L.hvx_extraction_request_new.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(ExtractionRequest)]
+    L.hvx_extraction_limits_plan.argtypes = [C.POINTER(ExtractionLimits), C.POINTER(ExtractionPlan)]
+    L.hvx_extraction_limits_validate_device.argtypes = [C.POINTER(ExtractionLimits), C.c_uint64, C.c_uint64,
+                                                        C.POINTER(C.c_char_p), u64p]
+    L.hvx_extraction_gpu_range.argtypes = [C.POINTER(SurfaceAllocation), C.c_uint64, C.POINTER(ExtractionRange)]
+    L.hvx_extraction_gpu_range.restype = None
+    L.hvx_extraction_publisher_create.argtypes = [C.POINTER(ExtractionLimits), C.POINTER(vp)]
+    L.hvx_extraction_publisher_destroy.argtypes = [vp]
+    L.hvx_extraction_publisher_destroy.restype = None
+    L.hvx_extraction_reserve.argtypes = [vp, C.POINTER(PlanetPageKey), C.c_uint64, C.POINTER(SurfaceCounts),
+                                         C.POINTER(ReservationOutcome)]
+    L.hvx_extraction_publish.argtypes = [vp, C.POINTER(Reservation), C.POINTER(PublicationOutcome)]
+    L.hvx_extraction_cancel_pending.argtypes = [vp, C.POINTER(PlanetPageKey), C.c_uint64, C.POINTER(C.c_int)]
+    L.hvx_extraction_evict.argtypes = [vp, C.POINTER(PlanetPageKey), C.c_uint64, C.POINTER(EvictOutcome)]
+    L.hvx_extraction_current.argtypes = [vp, C.POINTER(PlanetPageKey), C.POINTER(PublishedSurface)]
+    L.hvx_extraction_pending.argtypes = [vp, C.POINTER(PlanetPageKey), C.POINTER(Reservation)]
+    L.hvx_extraction_publisher_get_counters.argtypes = [vp, C.POINTER(ExtractionPublisherCounters)]
+    L.hvx_extraction_publisher_attach.argtypes = [vp, vp]
+    L.hvx_extraction_commit.argtypes = [vp, u32p, u32p, C.POINTER(Reservation), C.c_uint32]
+    L.hvx_extraction_publisher_buffer.argtypes = [vp, C.c_int]
+    L.hvx_extraction_publisher_buffer.restype = vp
+    L.hvx_extraction_publisher_read.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
     _lib = L
     return L

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "extraction_publisher.h"
 #include "hvx_kernels.h"
 
 using namespace hvx;
@@ -371,6 +372,16 @@ const char* hvx_status_name(int status) {
         case HVX_E_TOPOLOGY_PAGE_BUDGET: return "HVX_E_TOPOLOGY_PAGE_BUDGET";
         case HVX_E_TOPOLOGY_MISSING_PARENT: return "HVX_E_TOPOLOGY_MISSING_PARENT";
         case HVX_E_TOPOLOGY_COVERAGE: return "HVX_E_TOPOLOGY_COVERAGE";
+        case HVX_E_INVALID_LIMITS: return "HVX_E_INVALID_LIMITS";
+        case HVX_E_ARITHMETIC_OVERFLOW: return "HVX_E_ARITHMETIC_OVERFLOW";
+        case HVX_E_NON_TRIANGLE_INDEX_COUNT: return "HVX_E_NON_TRIANGLE_INDEX_COUNT";
+        case HVX_E_INCOMPLETE_SURFACE_COUNTS: return "HVX_E_INCOMPLETE_SURFACE_COUNTS";
+        case HVX_E_PENDING_CAPACITY: return "HVX_E_PENDING_CAPACITY";
+        case HVX_E_ARENA_CAPACITY: return "HVX_E_ARENA_CAPACITY";
+        case HVX_E_GENERATION_CONFLICT: return "HVX_E_GENERATION_CONFLICT";
+        case HVX_E_RESERVATION_MISSING: return "HVX_E_RESERVATION_MISSING";
+        case HVX_E_RESERVATION_MISMATCH: return "HVX_E_RESERVATION_MISMATCH";
+        case HVX_E_DEVICE_BUFFER_LIMIT: return "HVX_E_DEVICE_BUFFER_LIMIT";
         default: return "HVX_E_UNKNOWN";
     }
 }
@@ -804,6 +815,115 @@ int hvx_publisher_write(hvx_publisher* pub, int id, uint64_t offset, uint64_t by
     if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of publisher buffer %d", id);
     DeviceGuard guard(ctx->device);
     HVX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(pub->buf[id]) + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+// ---- bounded extraction publisher, device side (PV/src/extraction.rs) --------------------
+static void extraction_publisher_release_device(hvx_extraction_publisher* pub) {
+    if (!pub->ctx) return;
+    hvx_ctx* ctx = pub->ctx;
+    DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < HVX_XPUB_COUNT; ++i)
+        if (pub->buf[i]) {
+            cudaFree(pub->buf[i]);
+            ctx->allocated -= pub->bytes[i];
+            pub->buf[i] = nullptr;
+        }
+    if (pub->d_jobs) {
+        cudaFree(pub->d_jobs);
+        ctx->allocated -= pub->d_jobs_bytes;
+        pub->d_jobs = nullptr;
+    }
+    pub->ctx = nullptr;
+}
+
+int hvx_extraction_publisher_attach(hvx_extraction_publisher* pub, hvx_ctx* ctx) {
+    static_assert(sizeof(hvx_extraction_request) == 32 && sizeof(hvx_extraction_range) == 32 &&
+                      sizeof(hvx_extraction_counters) == 48 && sizeof(CommitJob) == 40,
+                  "extraction POD layouts (PV/src/extraction.rs:8-109)");
+    if (!pub || !ctx) return HVX_E_INVALID_ARGUMENT;
+    if (pub->ctx) return fail(ctx, HVX_E_INVALID_ARGUMENT, "the extraction publisher is already attached");
+    hvx_extraction_plan plan;
+    const hvx_extraction_limits limits = pub->host.limits();
+    if (int rc = hvx_extraction_limits_plan(&limits, &plan)) return fail(ctx, rc, "%s", hvx_status_name(rc));
+    DeviceGuard guard(ctx->device);
+    pub->ctx = ctx;
+    pub->release_device = extraction_publisher_release_device;
+    pub->bytes[HVX_XPUB_VERTICES] = plan.vertex_bytes;
+    pub->bytes[HVX_XPUB_INDICES] = plan.index_bytes;
+    pub->bytes[HVX_XPUB_PAGE_RANGES] = plan.page_range_bytes;
+    pub->bytes[HVX_XPUB_COUNTERS] = plan.counter_bytes;
+    for (int i = 0; i < HVX_XPUB_COUNT; ++i) {
+        cudaError_t e = cudaMalloc(&pub->buf[i], pub->bytes[i]);
+        if (e == cudaSuccess && i >= HVX_XPUB_PAGE_RANGES) e = cudaMemsetAsync(pub->buf[i], 0, pub->bytes[i], ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            pub->buf[i] = nullptr;
+            const int rc = fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: extraction arena %d requires %llu bytes: %s", i,
+                                static_cast<unsigned long long>(pub->bytes[i]), cudaGetErrorString(e));
+            extraction_publisher_release_device(pub);
+            return rc;
+        }
+        ctx->allocated += pub->bytes[i];
+    }
+    return HVX_OK;
+}
+
+int hvx_extraction_commit(hvx_extraction_publisher* pub, const uint32_t* chunk, const uint32_t* page_slot,
+                          const hvx_reservation* reservations, uint32_t n) {
+    if (!pub || !pub->ctx) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = pub->ctx;
+    if (n == 0) return HVX_OK;
+    if (!chunk || !page_slot || !reservations) return fail(ctx, HVX_E_INVALID_ARGUMENT, "hvx_extraction_commit: NULL argument");
+    const hvx_extraction_limits limits = pub->host.limits();
+    std::vector<CommitJob> jobs(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const hvx_surface_allocation& a = reservations[i].allocation;
+        if (chunk[i] >= ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "job %u: chunk %u exceeds max_chunks %u", i, chunk[i], ctx->cfg.max_chunks);
+        if (page_slot[i] >= limits.max_page_slots)
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "job %u: page slot %u exceeds max_page_slots %u", i, page_slot[i], limits.max_page_slots);
+        if (static_cast<uint64_t>(a.vertices.first) + a.vertices.count > limits.max_vertices ||
+            static_cast<uint64_t>(a.indices.first) + a.indices.count > limits.max_indices)
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "job %u: reservation lies outside the bounded arenas", i);
+        jobs[i].chunk = chunk[i];
+        jobs[i].page_slot = page_slot[i];
+        jobs[i].range = gpu_range(a, reservations[i].generation);
+    }
+    DeviceGuard guard(ctx->device);
+    const void* dj = nullptr;
+    int rc;
+    if ((rc = stage_to(ctx, &pub->d_jobs, &pub->d_jobs_bytes, jobs.data(), static_cast<uint64_t>(n) * sizeof(CommitJob), &dj))) return rc;
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `jobs` is pageable host memory that dies with this call
+    CommitParams p{};
+    p.n_jobs = n;
+    p.src_max_vertices = ctx->cfg.max_vertices;
+    p.src_max_indices = ctx->cfg.max_indices;
+    p.jobs = static_cast<const CommitJob*>(dj);
+    p.regular_counters = static_cast<const hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
+    p.src_vertices = static_cast<const hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);
+    p.src_indices = static_cast<const uint32_t*>(ctx->buf[HVX_BUF_REGULAR_INDICES]);
+    p.vertices = static_cast<hvx_vertex*>(pub->buf[HVX_XPUB_VERTICES]);
+    p.indices = static_cast<uint32_t*>(pub->buf[HVX_XPUB_INDICES]);
+    p.page_ranges = static_cast<hvx_extraction_range*>(pub->buf[HVX_XPUB_PAGE_RANGES]);
+    p.counters = static_cast<hvx_extraction_counters*>(pub->buf[HVX_XPUB_COUNTERS]);
+    cudaError_t e = launch_commit(p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_commit");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+void* hvx_extraction_publisher_buffer(hvx_extraction_publisher* pub, int id) {
+    return (pub && id >= 0 && id < HVX_XPUB_COUNT) ? pub->buf[id] : nullptr;
+}
+
+int hvx_extraction_publisher_read(hvx_extraction_publisher* pub, int id, uint64_t offset, uint64_t bytes, void* dst) {
+    if (!pub || !pub->ctx || id < 0 || id >= HVX_XPUB_COUNT || !dst) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = pub->ctx;
+    if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of extraction arena %d", id);
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(pub->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HVX_OK;
 }

@@ -99,6 +99,25 @@ struct PublishParams {
     const hvx_draw_page* draw_pages;
 };
 
+// hvx_extraction_commit: one reserved page of the bounded extraction publisher (PV/src/extraction.rs:283-288)
+struct CommitJob {
+    uint32_t chunk, page_slot;
+    hvx_extraction_range range;  // reserved placement + generation (SurfaceAllocation::gpu_range)
+};
+
+struct CommitParams {
+    uint32_t n_jobs;
+    uint32_t src_max_vertices, src_max_indices;  // extraction slot strides
+    const CommitJob* jobs;
+    const hvx_emission_counters* regular_counters;
+    const hvx_vertex* src_vertices;
+    const uint32_t* src_indices;
+    hvx_vertex* vertices;                        // bounded arenas
+    uint32_t* indices;
+    hvx_extraction_range* page_ranges;
+    hvx_extraction_counters* counters;
+};
+
 struct MeshletParams {
     uint32_t n_chunks;
     uint32_t transition;                  // 0 regular, 1 transition
@@ -130,6 +149,7 @@ cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaS
 cudaError_t launch_gather(const GatherParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_publish(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_visibility(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_commit(const CommitParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
 cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,
                         const hvx_range* packed_ranges, uint32_t n, hvx_vertex* out_vertices,

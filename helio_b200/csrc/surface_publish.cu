@@ -122,7 +122,52 @@ __global__ void visibility_kernel(const PublishParams p) {
     p.transition_draws[i].instance_count = visible;
 }
 
+// hvx_extraction_commit: move reserved pages' meshes from their fixed-stride extraction slots into the
+// bounded arenas at the reserved ranges (PV/src/extraction.rs: the ranges a BoundedExtractionPublisher
+// reservation holds), and stamp page_ranges[page_slot] with the generation-tagged GpuExtractionRange.
+// grid = (blocks per job, jobs).  A job whose reservation does not match what the chunk emitted is
+// skipped by every block and counted once.
+__global__ void __launch_bounds__(256) commit_kernel(const CommitParams p) {
+    const CommitJob job = p.jobs[blockIdx.y];
+    const hvx_emission_counters c = p.regular_counters[job.chunk];
+    const bool ok = c.completed != 0u && c.vertex_overflow == 0u && c.index_overflow == 0u &&
+                    c.emitted_vertices == job.range.vertex_count && c.emitted_indices == job.range.index_count;
+    const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+    if (leader) atomicAdd(&p.counters->requests, 1u);
+    if (!ok) {
+        if (leader) {
+            atomicAdd(&p.counters->overflowed, 1u);
+            if (c.vertex_overflow != 0u || c.emitted_vertices != job.range.vertex_count) atomicAdd(&p.counters->vertex_overflow, 1u);
+            if (c.index_overflow != 0u || c.emitted_indices != job.range.index_count) atomicAdd(&p.counters->index_overflow, 1u);
+        }
+        return;
+    }
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    const uint4* sv = reinterpret_cast<const uint4*>(p.src_vertices + static_cast<size_t>(job.chunk) * p.src_max_vertices);
+    uint4* dv = reinterpret_cast<uint4*>(p.vertices + job.range.first_vertex);
+    for (uint32_t q = tid; q < 2u * job.range.vertex_count; q += stride) dv[q] = sv[q];
+    // index ranges start anywhere in the arena, so only the source is 16-byte aligned: scalar stores, coalesced
+    const uint32_t* si = p.src_indices + static_cast<size_t>(job.chunk) * p.src_max_indices;
+    uint32_t* di = p.indices + job.range.first_index;
+    for (uint32_t q = tid; q < job.range.index_count; q += stride) di[q] = si[q];
+    if (leader) {
+        p.page_ranges[job.page_slot] = job.range;
+        atomicAdd(&p.counters->vertices, job.range.vertex_count);
+        atomicAdd(&p.counters->indices, job.range.index_count);
+        atomicAdd(&p.counters->meshlets, job.range.meshlet_count);
+        atomicAdd(&p.counters->completed, 1u);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_commit(const CommitParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+    if (p.n_jobs == 0) return cudaSuccess;
+    uint32_t per_job = 8;
+    while (per_job > 1 && static_cast<uint64_t>(per_job) * p.n_jobs > 64ull * dev.sm_count) per_job >>= 1;
+    commit_kernel<<<dim3(per_job, p.n_jobs), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_publish(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream) {
     if (p.n_jobs == 0) return cudaSuccess;

@@ -54,7 +54,18 @@ typedef enum {
     HVX_E_TOPOLOGY_MINIMUM_LOD = -25,
     HVX_E_TOPOLOGY_PAGE_BUDGET = -26,
     HVX_E_TOPOLOGY_MISSING_PARENT = -27,
-    HVX_E_TOPOLOGY_COVERAGE = -28
+    HVX_E_TOPOLOGY_COVERAGE = -28,
+    /* PV/src/extraction.rs:672-698 ExtractionError */
+    HVX_E_INVALID_LIMITS = -40,
+    HVX_E_ARITHMETIC_OVERFLOW = -41,
+    HVX_E_NON_TRIANGLE_INDEX_COUNT = -42,
+    HVX_E_INCOMPLETE_SURFACE_COUNTS = -43,
+    HVX_E_PENDING_CAPACITY = -44,       /* PendingCapacity { maximum } */
+    HVX_E_ARENA_CAPACITY = -45,         /* ArenaCapacity { capacity } */
+    HVX_E_GENERATION_CONFLICT = -46,
+    HVX_E_RESERVATION_MISSING = -47,
+    HVX_E_RESERVATION_MISMATCH = -48,
+    HVX_E_DEVICE_BUFFER_LIMIT = -49     /* DeviceBufferLimit { name, requested, .. } */
 } hvx_status;
 
 /* PV/src/extraction.rs:72-79 GpuTerrainVertex (repr(C, align(16)), 32 B). */
@@ -450,7 +461,7 @@ int hvx_extraction_current(const hvx_extraction_publisher* pub, const hvx_planet
                            hvx_published_surface* out);
 int hvx_extraction_pending(const hvx_extraction_publisher* pub, const hvx_planet_page_key* key, hvx_reservation* out);
 /* counters (:381-396). */
-int hvx_extraction_publisher_counters(const hvx_extraction_publisher* pub, hvx_extraction_publisher_counters* out);
+int hvx_extraction_publisher_get_counters(const hvx_extraction_publisher* pub, hvx_extraction_publisher_counters* out);
 
 /* Device side of the contract.  attach: allocate the plan's bounded arenas on the ctx's device
  * (vertices, indices, page ranges, counters).  commit: for n reserved pages, copy the REGULAR mesh of

@@ -3,6 +3,7 @@
 //! (PV/src/render.rs:579-580 holds the two fields) for the types below.  Where the reference takes
 //! `(&wgpu::Device, &wgpu::Queue)` these take a CUDA device ordinal at construction.
 pub mod ffi;
+pub mod extraction;
 
 use bytemuck::{Pod, Zeroable};
 use core::ffi::{c_int, c_void, CStr};
