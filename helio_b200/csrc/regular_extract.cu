@@ -35,6 +35,19 @@
 #include "hvx_device.cuh"
 #include "hvx_kernels.h"
 
+// edge-32 decoupled kernel: emission warps, ring slots and CTAs per SM (tuning knobs; measured on B200:
+// 3 CTAs x (4 front + 6 emission + 2) warps beat 2 x (4 + 8 + 2) by 17-20 % -- the per-slab front-end chain is
+// latency bound at this slab size, so a third CTA per SM is a third chain in flight)
+#ifndef HVX_E32_NW
+#define HVX_E32_NW 6
+#endif
+#ifndef HVX_E32_RS
+#define HVX_E32_RS 6
+#endif
+#ifndef HVX_E32_CTAS
+#define HVX_E32_CTAS 3
+#endif
+
 namespace hvx {
 
 namespace {
@@ -855,7 +868,7 @@ struct DecoupledCfg {
 };
 
 template <class C>
-__global__ void __launch_bounds__(DecoupledCfg<C>::NT_ALL, C::E == 32 ? 2 : 1)
+__global__ void __launch_bounds__(DecoupledCfg<C>::NT_ALL, C::E == 32 ? HVX_E32_CTAS : 1)
 regular_extract_decoupled_kernel(const RegularParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using SM = SmemD<C>;
@@ -1313,7 +1326,7 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
 using Cfg64 = Cfg<64, 2, 6, 16>;
 using Cfg32 = Cfg<32, 2, 10, 8>;
 using Cfg64D = Cfg<64, 1, 6, 20>;  // decoupled kernel at edge 64: 8 front + 20 emission + producer + scheduler warps
-using Cfg32D = Cfg<32, 1, 10, 8>;  // decoupled kernel at edge 32: 4 front + 8 emission + producer + scheduler warps, 2 CTAs / SM
+using Cfg32D = Cfg<32, 1, HVX_E32_RS, HVX_E32_NW>;  // decoupled kernel at edge 32: 4 front + 6 emission + producer + scheduler warps, 3 CTAs / SM
 
 // HVX_REGULAR_VARIANT=1 selects the first-generation kernel (identical output); default: decoupled.
 int variant_from_env() {

@@ -1,4 +1,4 @@
-for v in 0 1; do HVX_REGULAR_VARIANT=$v timeout 120 python - <<'PY'
+for v in 0; do timeout 120 python - <<'PY'
 import os, sys, numpy as np, torch
 sys.path.insert(0, '.')
 import helio_b200 as H
