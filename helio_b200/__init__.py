@@ -6,6 +6,9 @@ extractor objects.  Importing the package does not load the library; creating an
 does, and fails loudly if it is missing -- there is no CPU fallback.
 """
 from . import _ffi
+from .brick import (BRICK_DRAW_DTYPE, BRICK_MESHLET_DTYPE, BRICK_META_DTYPE, DIRTY_BRICK_DTYPE, MAX_SURFACE_INDICES_PER_BRICK,
+                    MAX_SURFACE_VERTS_PER_BRICK, VOXEL_MESH_BRICK_VOXEL_WORDS, VOXEL_MESH_MAX_BRICKS, VOXEL_MESH_MAX_DIRTY,
+                    ActiveBrickRange, VoxelMeshExtractor, pack_brick)
 from .context import (GATHER_COUNTERS_DTYPE, CELL_OFFSET_DTYPE, CELL_RECORD_DTYPE, CLASSIFY_COUNTERS_DTYPE, EMISSION_COUNTERS_DTYPE,
                       MESHLET_BOUNDS_DTYPE, MESHLET_DTYPE, RANGE_DTYPE, TERRAIN_MESHLET_BUILD_INDICES, SCAN_BLOCK_DTYPE, TRANSITION_COUNTERS_DTYPE, VERTEX_DTYPE, Context, make_descs)
 from .errors import (AddressError, BatchCapacity, CudaError, DeviceLimit, FinestLodHasNoFinerNeighbor, HvxError,

@@ -45,6 +45,7 @@ HVX_E_DEVICE_BUFFER_LIMIT = -49
 
 HVX_CFG_DEBUG_RECORDS = 1
 (XPUB_VERTICES, XPUB_INDICES, XPUB_PAGE_RANGES, XPUB_COUNTERS) = range(4)
+(BRICK_VERTICES, BRICK_NORMALS, BRICK_INDICES, BRICK_DESCRIPTORS, BRICK_DRAWS, BRICK_REJECTED) = range(6)
 (PUB_REGULAR_VERTICES, PUB_REGULAR_INDICES, PUB_TRANSITION_VERTICES, PUB_TRANSITION_INDICES, PUB_STATES, PUB_REGULAR_DRAWS,
  PUB_TRANSITION_DRAWS, PUB_FEEDBACK) = range(8)
 
@@ -168,6 +169,8 @@ EXPORTS = [
     "hvx_extraction_current", "hvx_extraction_pending", "hvx_extraction_publisher_get_counters",
     "hvx_extraction_publisher_attach", "hvx_extraction_commit", "hvx_extraction_publisher_buffer",
     "hvx_extraction_publisher_read",
+    "hvx_brick_mesher_create", "hvx_brick_mesher_destroy", "hvx_brick_extract", "hvx_brick_clear_slot", "hvx_brick_buffer",
+    "hvx_brick_buffer_bytes", "hvx_brick_read",
 ]
 
 _lib = None
@@ -257,5 +260,15 @@ def load() -> C.CDLL:
     L.hvx_extraction_publisher_buffer.argtypes = [vp, C.c_int]
     L.hvx_extraction_publisher_buffer.restype = vp
     L.hvx_extraction_publisher_read.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
+    L.hvx_brick_mesher_create.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+    L.hvx_brick_mesher_destroy.argtypes = [vp]
+    L.hvx_brick_mesher_destroy.restype = None
+    L.hvx_brick_extract.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint64, vp, C.c_uint32]
+    L.hvx_brick_clear_slot.argtypes = [vp, C.c_uint32]
+    L.hvx_brick_buffer.argtypes = [vp, C.c_int]
+    L.hvx_brick_buffer.restype = vp
+    L.hvx_brick_buffer_bytes.argtypes = [vp, C.c_int]
+    L.hvx_brick_buffer_bytes.restype = C.c_uint64
+    L.hvx_brick_read.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, vp]
     _lib = L
     return L

@@ -928,6 +928,150 @@ int hvx_extraction_publisher_read(hvx_extraction_publisher* pub, int id, uint64_
     return HVX_OK;
 }
 
+// ---- legacy 8^3-brick marching cubes (helio-pass-voxel-mesh) -----------------------------
+struct hvx_brick_mesher {
+    hvx_ctx* ctx = nullptr;
+    uint32_t max_bricks = 0;
+    void* buf[HVX_BRICK_BUF_COUNT] = {};
+    uint64_t bytes[HVX_BRICK_BUF_COUNT] = {};
+    void* stage[3] = {nullptr, nullptr, nullptr};  // meta, voxels, dirty list
+    uint64_t stage_bytes[3] = {0, 0, 0};
+};
+
+int hvx_brick_mesher_create(hvx_ctx* ctx, uint32_t max_bricks, hvx_brick_mesher** out) {
+    static_assert(sizeof(hvx_brick_meta) == 8 && sizeof(hvx_dirty_brick) == 32 && sizeof(hvx_brick_meshlet) == 32,
+                  "legacy brick POD layouts");
+    if (!ctx || !out) return HVX_E_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (max_bricks == 0) return fail(ctx, HVX_E_INVALID_CAPACITY, "a brick mesher needs at least one brick slot");
+    if (static_cast<uint64_t>(max_bricks) * HVX_BRICK_MAX_ENTRIES > 0x7fffffffull)
+        return fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: %u brick slots exceed 32-bit draw arguments", max_bricks);
+    DeviceGuard guard(ctx->device);
+    hvx_brick_mesher* m = new (std::nothrow) hvx_brick_mesher;
+    if (!m) return fail(ctx, HVX_E_DEVICE_LIMIT, "out of host memory");
+    m->ctx = ctx;
+    m->max_bricks = max_bricks;
+    const uint64_t entries = static_cast<uint64_t>(max_bricks) * HVX_BRICK_MAX_ENTRIES;
+    m->bytes[HVX_BRICK_VERTICES] = entries * 16ull;
+    m->bytes[HVX_BRICK_NORMALS] = entries * 16ull;
+    m->bytes[HVX_BRICK_INDICES] = entries * 4ull;
+    m->bytes[HVX_BRICK_DESCRIPTORS] = max_bricks * sizeof(hvx_brick_meshlet);
+    m->bytes[HVX_BRICK_DRAWS] = max_bricks * sizeof(hvx_draw_indexed_indirect);
+    m->bytes[HVX_BRICK_REJECTED] = sizeof(uint32_t);
+    for (int i = 0; i < HVX_BRICK_BUF_COUNT; ++i) {
+        cudaError_t e = cudaMalloc(&m->buf[i], m->bytes[i]);
+        if (e == cudaSuccess && i >= HVX_BRICK_DESCRIPTORS) e = cudaMemsetAsync(m->buf[i], 0, m->bytes[i], ctx->stream);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            m->buf[i] = nullptr;
+            const int rc = fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: brick buffer %d requires %llu bytes: %s", i,
+                                static_cast<unsigned long long>(m->bytes[i]), cudaGetErrorString(e));
+            hvx_brick_mesher_destroy(m);
+            return rc;
+        }
+        ctx->allocated += m->bytes[i];
+    }
+    *out = m;
+    return HVX_OK;
+}
+
+void hvx_brick_mesher_destroy(hvx_brick_mesher* m) {
+    if (!m) return;
+    DeviceGuard guard(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    for (int i = 0; i < HVX_BRICK_BUF_COUNT; ++i)
+        if (m->buf[i]) {
+            cudaFree(m->buf[i]);
+            m->ctx->allocated -= m->bytes[i];
+        }
+    for (int i = 0; i < 3; ++i)
+        if (m->stage[i]) {
+            cudaFree(m->stage[i]);
+            m->ctx->allocated -= m->stage_bytes[i];
+        }
+    delete m;
+}
+
+int hvx_brick_extract(hvx_brick_mesher* m, const hvx_brick_meta* meta, uint32_t n_meta, const uint32_t* voxels,
+                      uint64_t n_words, const hvx_dirty_brick* dirty, uint32_t n_dirty) {
+    if (!m) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = m->ctx;
+    if (n_dirty == 0) return HVX_OK;
+    if (!meta || !voxels || !dirty) return fail(ctx, HVX_E_INVALID_ARGUMENT, "hvx_brick_extract: NULL argument");
+    // Host-resident lists are validated here, before anything touches the GPU.  Device-resident lists (the
+    // steady-state path: metadata and dirty list produced on the device) are bounds-checked by the kernel, which
+    // skips an offending entry and counts it in HVX_BRICK_REJECTED.
+    auto on_device = [](const void* ptr) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    };
+    const bool host_lists = !on_device(meta) && !on_device(dirty);
+    if (!host_lists && (!on_device(meta) || !on_device(dirty)))
+        return fail(ctx, HVX_E_INVALID_ARGUMENT, "meta and dirty must both be host arrays or both be device arrays");
+    for (uint32_t i = 0; host_lists && i < n_dirty; ++i) {
+        const uint32_t slot = dirty[i].brick_slot;
+        if (slot >= m->max_bricks || slot >= n_meta)
+            return fail(ctx, HVX_E_BATCH_CAPACITY, "dirty brick %u: slot %u exceeds capacity %u", i, slot,
+                        m->max_bricks < n_meta ? m->max_bricks : n_meta);
+        if (static_cast<uint64_t>(meta[slot].data_offset) + HVX_BRICK_VOXEL_WORDS > n_words)
+            return fail(ctx, HVX_E_SAMPLE_COUNT, "SampleCount: brick slot %u needs words [%u, %u) of %llu", slot,
+                        meta[slot].data_offset, meta[slot].data_offset + HVX_BRICK_VOXEL_WORDS,
+                        static_cast<unsigned long long>(n_words));
+    }
+    DeviceGuard guard(ctx->device);
+    const void *dm = nullptr, *dv = nullptr, *dd = nullptr;
+    int rc;
+    if ((rc = stage_to(ctx, &m->stage[0], &m->stage_bytes[0], meta, static_cast<uint64_t>(n_meta) * sizeof(hvx_brick_meta), &dm))) return rc;
+    if ((rc = stage_to(ctx, &m->stage[1], &m->stage_bytes[1], voxels, n_words * 4ull, &dv))) return rc;
+    if ((rc = stage_to(ctx, &m->stage[2], &m->stage_bytes[2], dirty, static_cast<uint64_t>(n_dirty) * sizeof(hvx_dirty_brick), &dd))) return rc;
+    BrickParams p{};
+    p.n_dirty = n_dirty;
+    p.slot_limit = m->max_bricks < n_meta ? m->max_bricks : n_meta;
+    p.n_words = n_words;
+    p.rejected = static_cast<uint32_t*>(m->buf[HVX_BRICK_REJECTED]);
+    p.meta = static_cast<const hvx_brick_meta*>(dm);
+    p.voxels = static_cast<const uint32_t*>(dv);
+    p.dirty = static_cast<const hvx_dirty_brick*>(dd);
+    p.vertices = static_cast<float4*>(m->buf[HVX_BRICK_VERTICES]);
+    p.normals = static_cast<float4*>(m->buf[HVX_BRICK_NORMALS]);
+    p.indices = static_cast<uint32_t*>(m->buf[HVX_BRICK_INDICES]);
+    p.descriptors = static_cast<hvx_brick_meshlet*>(m->buf[HVX_BRICK_DESCRIPTORS]);
+    p.draws = static_cast<hvx_draw_indexed_indirect*>(m->buf[HVX_BRICK_DRAWS]);
+    cudaError_t e = launch_bricks(p, ctx->dev, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_bricks");
+    ctx->launches += 1;
+    // caller-owned pageable arrays: the staged copies must have left them before we return
+    if (host_lists) HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
+int hvx_brick_clear_slot(hvx_brick_mesher* m, uint32_t brick_slot) {
+    if (!m) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = m->ctx;
+    if (brick_slot >= m->max_bricks) return fail(ctx, HVX_E_BATCH_CAPACITY, "brick slot %u exceeds capacity %u", brick_slot, m->max_bricks);
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaMemsetAsync(static_cast<char*>(m->buf[HVX_BRICK_DRAWS]) + static_cast<size_t>(brick_slot) * sizeof(hvx_draw_indexed_indirect),
+                                  0, sizeof(hvx_draw_indexed_indirect), ctx->stream));
+    return HVX_OK;
+}
+
+void* hvx_brick_buffer(hvx_brick_mesher* m, int id) { return (m && id >= 0 && id < HVX_BRICK_BUF_COUNT) ? m->buf[id] : nullptr; }
+uint64_t hvx_brick_buffer_bytes(hvx_brick_mesher* m, int id) { return (m && id >= 0 && id < HVX_BRICK_BUF_COUNT) ? m->bytes[id] : 0; }
+
+int hvx_brick_read(hvx_brick_mesher* m, int id, uint64_t offset, uint64_t bytes, void* dst) {
+    if (!m || id < 0 || id >= HVX_BRICK_BUF_COUNT || !dst) return HVX_E_INVALID_ARGUMENT;
+    hvx_ctx* ctx = m->ctx;
+    if (offset + bytes > m->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of brick buffer %d", id);
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(m->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HVX_OK;
+}
+
 int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
     if (kind != 0 && kind != 1) return fail(ctx, HVX_E_INVALID_ARGUMENT, "kind must be 0 (regular) or 1 (transition)");

@@ -118,6 +118,22 @@ struct CommitParams {
     hvx_extraction_counters* counters;
 };
 
+// hvx_brick_extract: legacy 8^3-brick marching cubes (helio-pass-voxel-mesh)
+struct BrickParams {
+    uint32_t n_dirty;
+    uint32_t slot_limit;  // min(max_bricks, n_meta)
+    uint64_t n_words;
+    uint32_t* rejected;   // entries skipped by the in-kernel bounds check
+    const hvx_brick_meta* meta;
+    const uint32_t* voxels;
+    const hvx_dirty_brick* dirty;
+    float4* vertices;
+    float4* normals;
+    uint32_t* indices;
+    hvx_brick_meshlet* descriptors;
+    hvx_draw_indexed_indirect* draws;
+};
+
 struct MeshletParams {
     uint32_t n_chunks;
     uint32_t transition;                  // 0 regular, 1 transition
@@ -149,6 +165,7 @@ cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaS
 cudaError_t launch_gather(const GatherParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_publish(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_visibility(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_bricks(const BrickParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_commit(const CommitParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // Packs per-chunk slots into a dense staging arena (for hvx_read_meshes).
 cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, const hvx_range* slot_ranges,

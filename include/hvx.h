@@ -484,6 +484,53 @@ void* hvx_extraction_publisher_buffer(hvx_extraction_publisher* pub, int buffer_
 int hvx_extraction_publisher_read(hvx_extraction_publisher* pub, int buffer_id, uint64_t byte_offset, uint64_t bytes,
                                   void* dst);
 
+/* ---- legacy 8^3-brick marching cubes (helio-voxel-core bricks) ------------------------ */
+/* The extraction half of VoxelMeshPass (crates/passes/3d/helio-pass-voxel-mesh/src/lib.rs:153-726,
+ * shaders/voxel_surface_extract.wgsl) for a batch of dirty bricks.  PODs as in the reference: */
+typedef struct { uint32_t data_offset, occupancy; } hvx_brick_meta;          /* GpuBrickMeta, helio-voxel-core/src/gpu_types.rs:18-22;
+                                                                                data_offset in WORDS into voxel_data */
+typedef struct {            /* DirtyBrick, helio-pass-voxel-mesh/src/lib.rs:64-69 (32 B) */
+    uint32_t brick_slot, volume_id, _pad[2];
+    float origin_size[4];   /* xyz = world origin, w = voxel size */
+} hvx_dirty_brick;
+typedef struct {            /* GpuBrickMeshlet, helio-voxel-core/src/gpu_types.rs:25-33 (32 B) */
+    uint32_t vertex_offset, index_offset, vertex_count, index_count, brick_index, volume_id, _pad[2];
+} hvx_brick_meshlet;
+#define HVX_BRICK_VOXEL_WORDS 183u   /* padded 9x9x9 bytes, VOXEL_MESH_BRICK_VOXEL_WORDS */
+#define HVX_BRICK_MAX_ENTRIES 2048u  /* MAX_SURFACE_VERTS_PER_BRICK == MAX_SURFACE_INDICES_PER_BRICK */
+
+/* Owns vertex_buf / normal_buf (float4 [max_bricks][2048]), index_buf (u32 [max_bricks][2048]), descriptors and
+ * indirect draws (per brick slot), like VoxelMeshPass::new (reference capacity: 1,024 bricks). */
+typedef struct hvx_brick_mesher hvx_brick_mesher;
+int hvx_brick_mesher_create(hvx_ctx* ctx, uint32_t max_bricks, hvx_brick_mesher** out);
+void hvx_brick_mesher_destroy(hvx_brick_mesher* mesher);
+/* The compute step of VoxelMeshPass::execute (lib.rs:653-667) for n_dirty bricks: marching cubes over each brick's
+ * padded 9^3 block -> edge-midpoint vertices (xyz, material), central-difference normals, one index per vertex, the
+ * brick's GpuBrickMeshlet descriptor and DrawIndexedIndirect.  Within a brick, cells are emitted in linear order
+ * (the reference's order depends on its atomics; this is one of its possible outcomes).  A cell that would pass
+ * 2,048 entries is dropped, counts are clamped -- the reference's overflow rule.
+ *   meta:   n_meta entries (indexed by brick slot);  dirty: n_dirty entries -- both HOST or both DEVICE;
+ *   voxels: HOST or DEVICE, n_words words.
+ * Host lists: HVX_E_BATCH_CAPACITY if a slot >= max_bricks or >= n_meta, HVX_E_SAMPLE_COUNT if a brick's 183
+ * words do not lie inside voxels, before anything is launched.  Device lists: the kernel makes the same checks,
+ * skips the entry and counts it in HVX_BRICK_REJECTED. */
+int hvx_brick_extract(hvx_brick_mesher* mesher, const hvx_brick_meta* meta, uint32_t n_meta, const uint32_t* voxels,
+                      uint64_t n_words, const hvx_dirty_brick* dirty, uint32_t n_dirty);
+/* clear_brick_slot (lib.rs:590-615): zero the slot's indirect draw. */
+int hvx_brick_clear_slot(hvx_brick_mesher* mesher, uint32_t brick_slot);
+typedef enum {
+    HVX_BRICK_VERTICES = 0,     /* float4 [max_bricks][2048]: xyz world position, w = material */
+    HVX_BRICK_NORMALS = 1,      /* float4 [max_bricks][2048] */
+    HVX_BRICK_INDICES = 2,      /* u32 [max_bricks][2048], brick-local */
+    HVX_BRICK_DESCRIPTORS = 3,  /* hvx_brick_meshlet [max_bricks] */
+    HVX_BRICK_DRAWS = 4,        /* hvx_draw_indexed_indirect [max_bricks] */
+    HVX_BRICK_REJECTED = 5,     /* u32 [1]: dirty entries of DEVICE-resident lists skipped by the kernel's bounds check */
+    HVX_BRICK_BUF_COUNT = 6
+} hvx_brick_buffer_id;
+void* hvx_brick_buffer(hvx_brick_mesher* mesher, int buffer_id);
+uint64_t hvx_brick_buffer_bytes(hvx_brick_mesher* mesher, int buffer_id);
+int hvx_brick_read(hvx_brick_mesher* mesher, int buffer_id, uint64_t byte_offset, uint64_t bytes, void* dst);
+
 /* ---- outputs ------------------------------------------------------------------------ */
 typedef enum {
     HVX_BUF_SAMPLES = 0,            /* u32  [max_chunks][(edge+2)^3]          (lazy) */

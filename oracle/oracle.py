@@ -48,7 +48,7 @@ class FixtureMetrics(C.Structure):
 def build(force: bool = False) -> Path:
     """Compile oracle/libhvx_oracle.so with the committed Makefile (gcc, -ffp-contract=off)."""
     so = _HERE / "libhvx_oracle.so"
-    src_mtime = max((_HERE / f).stat().st_mtime for f in ("hvx_oracle.c", "hvx_oracle.h", "tables.inc"))
+    src_mtime = max((_HERE / f).stat().st_mtime for f in ("hvx_oracle.c", "brick_oracle.c", "hvx_oracle.h", "tables.inc", "mc_tables.inc"))
     if force or not so.exists() or so.stat().st_mtime < src_mtime:
         env = dict(os.environ)
         env.pop("CC", None)
@@ -295,3 +295,23 @@ def page_hash(planet_id, relative_min, lod: int) -> int:
     pid = np.ascontiguousarray(planet_id, dtype=np.uint32)
     rel = np.ascontiguousarray(relative_min, dtype=np.int32)
     return int(lib().hvxo_page_hash(_u32p(pid), rel.ctypes.data_as(C.POINTER(C.c_int32)), lod))
+
+
+def brick_extract(voxel_words: np.ndarray, data_offset: int, origin, voxel_size: float):
+    """Legacy 8^3-brick marching cubes (oracle/brick_oracle.c) for one brick, cells in linear order.
+    Returns (vertices [n,4], normals [n,4], indices [n], raw_count); n = min(raw_count, 2048) is what the shader
+    publishes, entries of cells dropped by the overflow rule are left zero."""
+    L = lib()
+    L.hvxo_brick_extract.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                     C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    words = np.ascontiguousarray(voxel_words, dtype=np.uint32)
+    os_ = (C.c_float * 4)(*[float(v) for v in origin], float(voxel_size))
+    v = np.zeros((2048, 4), dtype=np.float32)
+    n = np.zeros((2048, 4), dtype=np.float32)
+    i = np.zeros(2048, dtype=np.uint32)
+    raw = C.c_uint32()
+    rc = L.hvxo_brick_extract(_u32p(words), data_offset, os_, v.ctypes.data_as(C.POINTER(C.c_float)),
+                              n.ctypes.data_as(C.POINTER(C.c_float)), _u32p(i), C.byref(raw))
+    assert rc == 0
+    count = min(raw.value, 2048)
+    return v[:count], n[:count], i[:count], raw.value
