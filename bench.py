@@ -64,6 +64,29 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, so the pinned host buffers of the e2e leg
+    are first-touched in memory local to that GPU's PCIe root (matters when 8 ranks upload at once)."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def profiled_traffic(alg_bytes):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
     (profiles/r01_traffic.json), scaled by nothing: only reported when it was taken on this exact workload."""
@@ -183,6 +206,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa else None
+    print(f"[bench] rank {rank}: GPU {local_rank} numa node {numa_node}, {len(os.sched_getaffinity(0))} cpus", file=sys.stderr)
 
     # ---- scheduler: global chunk list -> this rank's shard (no data-path collective) ----------
     pages_all = chunk_grid(world)
@@ -288,7 +313,8 @@ def run_ours(args):
                "h2d_bytes_per_step": n * words * 4 + n * 24 + n * 16,
                "d2h_bytes_per_step": 32 * total_v + 4 * total_i + n * 16 + n * 32,
                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-               "path": "hvx_extract_regular(host samples) + hvx_read_meshes + counters, pinned host memory"}
+               "path": "hvx_extract_regular(host samples) + hvx_read_meshes + counters, pinned host memory",
+               "numa_node": numa_node}
 
     # ---- CPU baseline on this box's cores (rank 0, N=1 only) ------------------------------------
     cpu = None
@@ -344,6 +370,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (N > 1)")
     ap.add_argument("--cpu-stride", type=int, default=2, help="CPU baseline runs every k-th chunk of the workload")
     ap.add_argument("--cpu-offset", type=int, default=0)
     ap.add_argument("--workload", choices=["terrain", "surface", "empty"], default="terrain")
