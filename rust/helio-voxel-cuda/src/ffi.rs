@@ -189,3 +189,28 @@ extern "C" {
                            indices_out: *mut u32, index_cap: u64, ranges_out: *mut hvx_range,
                            total_vertices: *mut u64, total_indices: *mut u64) -> c_int;
 }
+
+// ---- legacy 8^3-brick marching cubes (include/hvx.h, "legacy 8^3-brick marching cubes") ----------------
+// PODs are the reference's own: GpuBrickMeta / GpuBrickMeshlet (helio-voxel-core/src/gpu_types.rs:18-33),
+// DirtyBrick (helio-pass-voxel-mesh/src/lib.rs:64-69).
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct hvx_brick_meta { pub data_offset: u32, pub occupancy: u32 }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct hvx_dirty_brick { pub brick_slot: u32, pub volume_id: u32, pub _pad: [u32; 2], pub origin_size: [f32; 4] }
+#[repr(C)] #[derive(Clone, Copy, Default)] pub struct hvx_brick_meshlet { pub vertex_offset: u32, pub index_offset: u32, pub vertex_count: u32, pub index_count: u32, pub brick_index: u32, pub volume_id: u32, pub _pad: [u32; 2] }
+#[repr(C)] pub struct hvx_brick_mesher { _private: [u8; 0] }
+pub const HVX_BRICK_VERTICES: c_int = 0;
+pub const HVX_BRICK_NORMALS: c_int = 1;
+pub const HVX_BRICK_INDICES: c_int = 2;
+pub const HVX_BRICK_DESCRIPTORS: c_int = 3;
+pub const HVX_BRICK_DRAWS: c_int = 4;
+pub const HVX_BRICK_REJECTED: c_int = 5;
+
+extern "C" {
+    pub fn hvx_brick_mesher_create(ctx: *mut hvx_ctx, max_bricks: u32, out: *mut *mut hvx_brick_mesher) -> c_int;
+    pub fn hvx_brick_mesher_destroy(mesher: *mut hvx_brick_mesher);
+    pub fn hvx_brick_extract(mesher: *mut hvx_brick_mesher, meta: *const hvx_brick_meta, n_meta: u32, voxels: *const u32,
+                             n_words: u64, dirty: *const hvx_dirty_brick, n_dirty: u32) -> c_int;
+    pub fn hvx_brick_clear_slot(mesher: *mut hvx_brick_mesher, brick_slot: u32) -> c_int;
+    pub fn hvx_brick_buffer(mesher: *mut hvx_brick_mesher, buffer_id: c_int) -> *mut c_void;
+    pub fn hvx_brick_buffer_bytes(mesher: *mut hvx_brick_mesher, buffer_id: c_int) -> u64;
+    pub fn hvx_brick_read(mesher: *mut hvx_brick_mesher, buffer_id: c_int, byte_offset: u64, bytes: u64, dst: *mut c_void) -> c_int;
+}

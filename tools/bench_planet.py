@@ -129,6 +129,19 @@ def main():
     e.record(stream)
     barrier()
     ms = a.elapsed_time(e) / args.steps
+    # where the step goes: the two launches timed apart (same stream, back to back)
+    parts = []
+    for fn in (lambda: ctx.extract_regular(None, d_reg, n), (lambda: ctx.extract_transition(None, d_tr, nt)) if nt else None):
+        if fn is None:
+            parts.append(0.0)
+            continue
+        a2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record(stream)
+        for _ in range(args.steps):
+            fn()
+        e2.record(stream)
+        e2.synchronize()
+        parts.append(a2.elapsed_time(e2) / args.steps)
 
     rc = batch.counters(n)
     totals = [int(rc["emitted_vertices"].astype(np.int64).sum()), int(rc["emitted_indices"].astype(np.int64).sum()), 0, 0,
@@ -153,7 +166,7 @@ def main():
         print(json.dumps({
             "case": "planet_scale_horizon_plans_32^3_plane", "n_gpus": world, "foci": args.foci, "pages": n_all,
             "pages_with_transition_faces": t[6], "transition_faces": t[7], "lod_histogram": np.bincount(lods_all).tolist(),
-            "ms_per_step": ms, "pages_per_s": n_all / (ms * 1e-3), "cells_per_s": n_all * EDGE ** 3 / (ms * 1e-3),
+            "ms_per_step": ms, "ms_regular_rank0": parts[0], "ms_transition_rank0": parts[1], "pages_per_s": n_all / (ms * 1e-3), "cells_per_s": n_all * EDGE ** 3 / (ms * 1e-3),
             "algorithmic_GBps": t[8] / (ms * 1e-3) / 1e9,
             "regular_vertices": t[0], "regular_indices": t[1], "transition_vertices": t[2], "transition_indices": t[3],
             "overflowed": t[4], "scaling": "strong (fixed global page list, LPT partition, no data-path collective)",
