@@ -23,4 +23,39 @@ for edge in (32, 64):
     t = b.transition_counters(n)
     print(edge, int(c["emitted_vertices"].sum()), int(t["emitted_vertices"].sum()))
     b.close()
+
+# no debug records -> the decoupled (default) kernel at edge 32 as well
+b = H.ChunkBatchExtractor(0, edge=32, max_chunks=6, max_vertices=40000, max_indices=60000)
+b.fill_density(16, [[0, -1, 0], [0, 0, 0], [1, -1, 1], [-1, -1, 0], [0, 1, 0], [2, -1, -2]])
+b.extract_regular(None, 6, transition_mask=[0, 0x3F, 1, 2, 0, 0x15])
+ec = b.counters(6)
+
+# bounded extraction publisher: commit into the packed arenas
+pub = H.BoundedExtractionPublisher(H.ExtractionLimits.new(8, 6, 60000, 90000, 2000))
+pub.attach(b.ctx)
+res = []
+for k in range(6):
+    ni = int(ec["emitted_indices"][k])
+    counts = H.SurfaceCounts(int(ec["emitted_vertices"][k]), ni, H.max_meshlets_for_indices(ni) if ni else 0)
+    res.append(pub.reserve(H.PlanetPageKey.new(bytes(16), H.PageKey(0, (k, 0, 0))), 1, counts).reservation)
+pub.commit(range(6), range(6), res)
+print("commit", pub.read(3, H.EXTRACTION_COUNTERS_DTYPE)[0])
+pub.close()
+b.close()
+
+# legacy 8^3-brick marching cubes: noise, checker (overflow), empty, full
+rng = np.random.default_rng(5)
+z, y, x = np.indices((9, 9, 9))
+bricks = [(rng.random((9, 9, 9)) < 0.4) * 7, ((x + y + z) & 1) * 4, np.zeros((9, 9, 9)), np.full((9, 9, 9), 9)]
+words = np.concatenate([H.pack_brick(v.astype(np.uint8)) for v in bricks])
+ex = H.VoxelMeshExtractor(0, max_bricks=4)
+meta = np.zeros(4, dtype=H.BRICK_META_DTYPE)
+meta["data_offset"] = np.arange(4) * 183
+ex.write_brick_meta(meta)
+ex.write_voxel_data(words)
+for k in range(4):
+    ex.mark_dirty(k, 0, (0.0, 0.0, 0.0), 0.5, True)
+ex.execute()
+print("bricks", ex.descriptors()["vertex_count"])
+ex.close()
 print("sanitize workload done")
