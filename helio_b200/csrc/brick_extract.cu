@@ -122,8 +122,7 @@ __global__ void __launch_bounds__(BRICK_WARPS * 32) brick_extract_kernel(const B
                 if (first + (info >> 16) > BRICK_MAX_ENTRIES) continue;  // the whole cell is dropped (:193-195)
                 const uint32_t oc = round * 32u + o, ox = oc & 7u, oy = (oc >> 3) & 7u, oz = oc >> 6;
                 const uint32_t case_index = info & 0xffu;
-                const uint32_t word = HVX_MC_TRI_TABLE[2u * case_index + (i >> 3)];
-                const uint32_t h = edge_mid_halves((word >> ((i & 7u) * 4u)) & 0xfu);
+                const uint32_t h = edge_mid_halves(HVX_MC_EDGES[case_index][i]);
                 const uint32_t hx = h & 3u, hy = (h >> 2) & 3u, hz = h >> 4;
                 // world = (cell * vs + origin) + local * vs, local in {0, 0.5, 1}
                 float4 v;

@@ -77,9 +77,9 @@ int hvxo_brick_extract(const uint32_t* voxel_words, uint32_t data_offset, const 
                 material = corner[i];   /* ends as the FIRST non-zero corner, :202-208 */
             }
         if (cube == 0u || cube == 0xffu) continue;
-        const uint32_t w0 = HVXO_MC_TRI_TABLE[2 * cube], w1 = HVXO_MC_TRI_TABLE[2 * cube + 1];
+        const uint8_t* row = HVXO_MC_EDGES[cube];      /* the packed_tri_table row, one edge per entry */
         uint32_t n = 0;
-        while (n < 15u && (((n < 8u ? w0 : w1) >> ((n % 8u) * 4u)) & 0xfu) != 0xfu) ++n;
+        while (n < 15u && row[n] != 0xffu) ++n;        /* :174-180, 0xF nibble == 255 here */
         if (n == 0u) continue;
         const uint32_t base = counter;
         counter += n;                                   /* both atomics advance by the same amount */
@@ -87,7 +87,7 @@ int hvxo_brick_extract(const uint32_t* voxel_words, uint32_t data_offset, const 
         const float cell_world[3] = {(float)cx * vs + origin_size[0], (float)cy * vs + origin_size[1],
                                      (float)cz * vs + origin_size[2]};
         for (uint32_t i = 0; i < n; ++i) {
-            const uint32_t edge = ((i < 8u ? w0 : w1) >> ((i % 8u) * 4u)) & 0xfu;
+            const uint32_t edge = row[i];
             const float* mid = EDGE_MID[edge];
             float* v = vertices + 4u * (base + i);
             v[0] = cell_world[0] + mid[0] * vs;

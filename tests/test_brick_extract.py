@@ -66,8 +66,9 @@ def test_every_cube_case_emits_its_table_row():
     corners = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
     import re
     from pathlib import Path
-    text = (Path(O.__file__).parent / "mc_tables.inc").read_text().split("HVXO_MC_TRI_TABLE", 1)[1].split("};", 1)[0]
-    table = [int(w, 16) for w in re.findall(r"0x[0-9A-Fa-f]+", text)]
+    text = (Path(O.__file__).parent / "mc_tables.inc").read_text().split("HVXO_MC_EDGES", 1)[1].split("};", 1)[0]
+    table = [int(w, 16) for w in re.findall(r"0x[0-9A-Fa-f]+", text.split("=", 1)[1])]
+    assert len(table) == 256 * 16
     for case in range(1, 255):
         v = brick()
         for bit, (x, y, z) in enumerate(corners):              # isolate the case in cell (3, 3, 3)
@@ -75,8 +76,8 @@ def test_every_cube_case_emits_its_table_row():
                 v[3 + z, 3 + y, 3 + x] = 10 + bit
         verts, normals, idx, raw = run_oracle(v)
         # find this cell's entries: vertices inside [3,4]^3 whose cell is exactly (3,3,3) come after the cells before it
-        row = [(table[2 * case + (i >> 3)] >> (4 * (i & 7))) & 15 for i in range(16)]
-        row = row[:row.index(15)]
+        row = table[16 * case:16 * case + 16]
+        row = row[:row.index(255)]
         want = np.array([edge_mid[e] + 3 for e in row], dtype=np.float32)
         # neighbouring cells see a subset of the corners; locate the run that matches the row
         pos = verts[:, :3]
