@@ -744,7 +744,8 @@ __device__ __forceinline__ void emit_regular_vertex_fast(const uint32_t* __restr
     const float gx = fmix(ga[0], gb[0], t), gy = fmix(ga[1], gb[1], t), gz = fmix(ga[2], gb[2], t);
     const float s = fadd(fadd(fmul(gx, gx), fmul(gy, gy)), fmul(gz, gz));
     const bool sound = s > 1.0e-12f;
-    const float inv = fdiv(1.0f, fsqrt(sound ? s : 1.0f));
+    // s is a sum of squares of differences of i16 densities: 1e-12 < s < 2^35, inside the branch-free range
+    const float inv = inv_sqrt_rn_normal(sound ? s : 1.0f);
     n[0] = sound ? fmul(gx, inv) : 0.0f;
     n[1] = sound ? fmul(gy, inv) : 1.0f;
     n[2] = sound ? fmul(gz, inv) : 0.0f;
