@@ -211,4 +211,59 @@ class GpuSurfaceSampler {
     std::vector<hvx_gather_job> jobs_;
 };
 
+/// BoundedExtractionPublisher (PV/src/extraction.rs:342-603) over hvx_extraction_*: host-side, generation-safe
+/// arena placement.  Errors (ExtractionError, :672-698) surface as Error with the HVX_E_* status; `detail()` of
+/// a failed reserve is the exhausted arena (0 vertices, 1 indices, 2 meshlets) or the pending-page maximum.
+class BoundedExtractionPublisher {
+   public:
+    explicit BoundedExtractionPublisher(const hvx_extraction_limits& limits) : limits_(limits) {
+        const int status = hvx_extraction_publisher_create(&limits, &pub_);
+        if (status != HVX_OK) throw Error(status, hvx_status_name(status));
+    }
+    ~BoundedExtractionPublisher() { hvx_extraction_publisher_destroy(pub_); }
+    BoundedExtractionPublisher(const BoundedExtractionPublisher&) = delete;
+    BoundedExtractionPublisher& operator=(const BoundedExtractionPublisher&) = delete;
+
+    const hvx_extraction_limits& limits() const { return limits_; }
+    hvx_reservation_outcome reserve(const hvx_planet_page_key& key, uint64_t generation, const hvx_surface_counts& counts) {
+        hvx_reservation_outcome out{};
+        const int status = hvx_extraction_reserve(pub_, &key, generation, &counts, &out);
+        detail_ = out.detail;
+        if (status != HVX_OK) throw Error(status, hvx_status_name(status));
+        return out;
+    }
+    hvx_publication_outcome publish(const hvx_reservation& reservation) {
+        hvx_publication_outcome out{};
+        const int status = hvx_extraction_publish(pub_, &reservation, &out);
+        if (status != HVX_OK) throw Error(status, hvx_status_name(status));
+        return out;
+    }
+    bool cancel_pending(const hvx_planet_page_key& key, uint64_t generation) {
+        int cancelled = 0;
+        const int status = hvx_extraction_cancel_pending(pub_, &key, generation, &cancelled);
+        if (status != HVX_OK) throw Error(status, hvx_status_name(status));
+        return cancelled != 0;
+    }
+    hvx_evict_outcome evict(const hvx_planet_page_key& key, uint64_t generation) {
+        hvx_evict_outcome out{};
+        hvx_extraction_evict(pub_, &key, generation, &out);
+        return out;
+    }
+    bool current(const hvx_planet_page_key& key, hvx_published_surface* out) const { return hvx_extraction_current(pub_, &key, out) == 1; }
+    bool pending(const hvx_planet_page_key& key, hvx_reservation* out) const { return hvx_extraction_pending(pub_, &key, out) == 1; }
+    hvx_extraction_publisher_counters counters() const {
+        hvx_extraction_publisher_counters out{};
+        hvx_extraction_publisher_get_counters(pub_, &out);
+        return out;
+    }
+    uint32_t detail() const { return detail_; }
+    /// device side: bounded arenas on the context's GPU + one copy launch per batch of reservations
+    hvx_extraction_publisher* handle() { return pub_; }
+
+   private:
+    hvx_extraction_limits limits_;
+    hvx_extraction_publisher* pub_ = nullptr;
+    uint32_t detail_ = 0;
+};
+
 }  // namespace helio_voxel_cuda
