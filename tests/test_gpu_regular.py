@@ -225,19 +225,21 @@ def test_batch_of_mixed_chunks(edge):
     batch.close()
 
 
-@pytest.mark.parametrize("edge,n", [(64, 592), (32, 1184)])
-def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, n, monkeypatch):
+@pytest.mark.parametrize("edge,n,all_surface", [(64, 592, False), (32, 1184, False), (64, 1184, True), (32, 2368, True)])
+def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, n, all_surface, monkeypatch):
     """Race detector for the asynchronous (decoupled) kernel at a size where every SM walks several chunks.
 
     A terrain batch (surface and empty chunks mixed, random transition masks, a few partially dirty
     chunks) is extracted three times with the default kernel and once with the first-generation
     kernel (CTA-wide barriers, HVX_REGULAR_VARIANT=1): counters, ranges and every mesh byte must be
-    identical, and a sample of chunks must equal the oracle.
+    identical, and a sample of chunks must equal the oracle.  ``all_surface`` puts every chunk on the
+    surface layer: the emission warps are the bottleneck throughout, the work queue stays full and the
+    front end is throttled by the slab ring -- the opposite regime of the headline batch.
     """
     rng = np.random.default_rng(7)
     side = int(round(n ** 0.5)) + 1
-    pages = np.array([[x - side // 2, -1 if (x + z) % 3 else 0, z - side // 2] for z in range(side) for x in range(side)][:n],
-                     dtype=np.int64)
+    pages = np.array([[x - side // 2, -1 if all_surface or (x + z) % 3 else 0, z - side // 2]
+                      for z in range(side) for x in range(side)][:n], dtype=np.int64)
     batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=49_152 if edge == 64 else 12_288,
                                   max_indices=73_728 if edge == 64 else 18_432)
     batch.fill_density(O.FIELD_TERRAIN_FBM, pages)
