@@ -213,3 +213,30 @@ def test_packed_vertex_table_is_the_row_table_without_its_unused_tails():
             assert c1 > c0 and (c0 ^ c1) in (1, 2, 4) and c1 < 8
         at += nv
     assert at == 1536
+
+
+def test_planet_scale_page_set_is_reproducible_and_partitions_evenly():
+    """BASELINE config 4 (tools/bench_planet.py): the horizon plans drawn like the reference's randomized test
+    (PV/src/lod_topology.rs:507-520) give the same page list every time, only coarse pages own transition faces,
+    and the LPT partition hands every rank the same bytes to within a page."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from bench_planet import next_random, planet_page_set
+
+    x = 0x4D595DF4D0F33173                       # one xorshift64 step (13, 7, 17), spelled out
+    x ^= (x << 13) & (2**64 - 1)
+    x ^= x >> 7
+    x ^= (x << 17) & (2**64 - 1)
+    assert next_random(0x4D595DF4D0F33173) == x == 0x76e0cf04b412ebd1
+    pages, lods, masks = planet_page_set(12)
+    again = planet_page_set(12)
+    assert np.array_equal(pages, again[0]) and np.array_equal(lods, again[1]) and np.array_equal(masks, again[2])
+    assert 12 * 20 < len(pages) <= 12 * 192
+    assert np.all(masks[lods == 0] == 0) and np.any(masks != 0) and np.all(masks < 64)
+    costs = np.array([H.chunk_cost(32, int(m)) for m in masks], dtype=np.uint64)
+    for ranks in (2, 4, 8):
+        owner = H.partition_chunks(costs, ranks)
+        load = np.array([costs[owner == r].sum() for r in range(ranks)], dtype=np.float64)
+        assert set(owner) == set(range(ranks))
+        assert load.max() - load.min() <= float(costs.max()), (ranks, load)
