@@ -222,6 +222,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     p.descs = ctx->d_descs;
     p.n_chunks = n;
     p.mode = mode;
+    for (uint32_t i = 0; i < n && !p.any_partial; ++i) p.any_partial = descs[i].dirty_microbricks != ~0ull;
     if (const char* dbg = getenv("HVX_DEBUG_STREAM_ONLY"))  // diagnostics only: skip all compute
         if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY; else if (dbg[0] == '2') p.mode = MODE_BITS_ONLY;
     if (const char* f = getenv("HVX_DEBUG_FLAGS")) p.debug_flags = static_cast<uint32_t>(atoi(f));

@@ -24,6 +24,7 @@ struct RegularParams {
     uint32_t n_chunks;
     uint32_t mode;
     uint32_t debug_flags;  // diagnostics: bit 0 disables the classification fast-reject
+    uint32_t any_partial;  // some chunk of the batch is partially dirty (picks the slab-skipping instantiation)
     uint32_t max_vertices, max_indices;  // per-chunk slot capacity
     hvx_vertex* vertices;                // [n][max_vertices]
     uint32_t* indices;                   // [n][max_indices]

@@ -886,7 +886,10 @@ struct DecoupledCfg {
     static_assert(CW <= 4 && C::RS <= 15 && C::NSLAB <= 255, "queue entry packing");
 };
 
-template <class C>
+// PARTIAL: the batch holds partially dirty chunks (incremental edits): slabs no dirty step reads are neither
+// fetched nor balloted nor classified.  A separate instantiation, so the fully dirty batches (the headline) keep
+// the front-end loop free of the per-slab test and its registers (measured: 0.804 vs 0.814 ms with it compiled in).
+template <class C, bool PARTIAL>
 __global__ void __launch_bounds__(DecoupledCfg<C>::NT_ALL, C::E == 32 ? HVX_E32_CTAS : 1)
 regular_extract_decoupled_kernel(const RegularParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -934,7 +937,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     break;
                 }
                 const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words;
-                const uint64_t need = slabs_of_steps(dirty_steps<C>(p.descs[id].dirty_microbricks));
+                const uint64_t need = PARTIAL ? slabs_of_steps(dirty_steps<C>(p.descs[id].dirty_microbricks)) : ~0ull;
                 for (int j = 0; j < C::NSLAB; ++j) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     if ((need >> j) & 1ull) {
@@ -960,16 +963,19 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         uint32_t round = 0;
         int bcur = 0, bprev = 2;  // bits ring: slab j in bits[bcur], slab j-1 in bits[bprev]
         for (uint32_t kc = 0;; ++kc) {
-            uint64_t dirty = 0;
+            uint64_t dirty = 0, need = ~0ull;
             for (int j = 0; j < C::NSLAB; ++j) {
                 mbar_wait_parked(&sm.full_bar[slot], round & 1u);
                 if (j == 0) {
                     const uint32_t chunk = sm.chunk_ids[kc & 3];
                     if (chunk >= p.n_chunks) return;
                     dirty = p.descs[chunk].dirty_microbricks;
+                    if (PARTIAL) need = slabs_of_steps(dirty_steps<C>(dirty));
                 }
-                const bool classify = j >= 1 && p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY;
-                if (p.mode != MODE_STREAM_ONLY) {
+                // a slab no dirty step reads was not fetched: no ballots, and its own step (not dirty) has no cells
+                const bool live = !PARTIAL || ((need >> j) & 1ull);
+                const bool classify = j >= 1 && live && p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY;
+                if (live && p.mode != MODE_STREAM_ONLY) {
                     // P1: blocks warp, warp + FW, ... of the slab: LDS, sign test, VOTE, STS.  PB loads in
                     // flight, then setp+vote pairs kept adjacent (inline PTX) so the compiler does not
                     // park 17 predicates in a register and dig them out again.
@@ -1334,7 +1340,8 @@ cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream
     const size_t smem = GEN == 2 ? sizeof(SmemD<C>) : sizeof(Smem<C>);
     static_assert(sizeof(SmemD<C>) <= 232448 && sizeof(Smem<C>) <= 232448, "shared memory budget (227 KB per CTA)");
     const int threads = GEN == 2 ? DecoupledCfg<C>::NT_ALL : C::NT_ALL;
-    auto* kernel = GEN == 2 ? regular_extract_decoupled_kernel<C> : regular_extract_kernel<C>;
+    auto* kernel = GEN == 0 ? regular_extract_kernel<C>
+                            : p.any_partial ? regular_extract_decoupled_kernel<C, true> : regular_extract_decoupled_kernel<C, false>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
     int ctas_per_sm = 1;
