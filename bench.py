@@ -203,7 +203,10 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            torch.cuda.set_device(local_rank)
+            dist.barrier()          # creates the communicator now, with stdout parked
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa else None
@@ -358,6 +361,21 @@ def run_ours(args):
     batch.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+class quiet_stdout:
+    """Send file descriptor 1 to stderr for a while: torch prints "NCCL version ..." on stdout when the
+    communicator is created, and stdout is reserved for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
 
 
 def main():

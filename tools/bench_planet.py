@@ -67,6 +67,21 @@ def planet_page_set(n_foci):
     return (np.array(pages, dtype=np.int64), np.array(lods, dtype=np.uint8), np.array(masks, dtype=np.uint32))
 
 
+class quiet_stdout:
+    """Send file descriptor 1 to stderr for a while: torch prints "NCCL version ..." on stdout when the
+    communicator is created, and stdout is reserved for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--foci", type=int, default=256)
@@ -83,7 +98,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        with quiet_stdout():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            torch.cuda.set_device(local_rank)
+            dist.barrier()
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
 
