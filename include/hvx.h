@@ -19,6 +19,9 @@
  *     reference PODs so Rust can bytemuck::cast_slice them.
  *   - there is no CPU fallback: without a CUDA device hvx_create fails with
  *     HVX_E_CUDA.
+ *   - objects created FROM a ctx (hvx_publisher, hvx_brick_mesher, an attached
+ *     hvx_extraction_publisher) borrow its device and stream: destroy them
+ *     before the ctx.
  */
 #ifndef HVX_H
 #define HVX_H
