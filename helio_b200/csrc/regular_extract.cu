@@ -875,14 +875,14 @@ struct DecoupledCfg {
     static constexpr int CW = C::PWS;                          // classifying front warps (one lane per cell row)
     static constexpr int FW = 2 * C::PWS;                      // front warps; all of them turn slabs into sign bits
     static constexpr int NT_ALL = (FW + C::NW + 2) * 32;       // front + emission + producer + scheduler
-    static constexpr int FB = (C::FULL + FW - 1) / FW;         // ballot blocks per front warp per slab
-    static constexpr int PB = FB % 17 == 0 ? 17 : 18;          // loads in flight per batch
+    static constexpr int GB = CW + 3 * (FW - CW);              // ballot blocks per group: 1 per classifying warp, 3 per other
+    static constexpr int NG = C::FULL / GB;                    // groups per slab = loads in flight per batch (17 / 9)
     // cells per tile: a typical surface cell has 4 vertices, so 30 cells fill four 32-lane vertex
     // passes (~120 vertices); 32 cells would spill a handful of vertices into a fifth
     static constexpr int TC = 30;
     static_assert(TC * 12 <= 360, "owner map size");
     static_assert(C::STEP_ROWS == CW * 32, "one classifying lane per cell row");
-    static_assert(C::FULL % FW == 0 && FB % PB == 0, "front warps split the slab's ballot blocks evenly");
+    static_assert(C::FULL % GB == 0 && NG <= 18, "the slab's ballot blocks split into whole groups");
     static_assert(CW <= 4 && C::RS <= 15 && C::NSLAB <= 255, "queue entry packing");
 };
 
@@ -976,18 +976,23 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 const bool live = !PARTIAL || ((need >> j) & 1ull);
                 const bool classify = j >= 1 && live && p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY;
                 if (live && p.mode != MODE_STREAM_ONLY) {
-                    // P1: blocks warp, warp + FW, ... of the slab: LDS, sign test, VOTE, STS.  PB loads in
-                    // flight, then setp+vote pairs kept adjacent (inline PTX) so the compiler does not
-                    // park 17 predicates in a register and dig them out again.
-                    const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * (32 * warp + lane);
-                    uint32_t* dst = sm.bits[bcur] + warp;
+                    // P1: LDS, sign test, VOTE, STS for this warp's ballot blocks.  The warps that classify afterwards
+                    // take one block of every group of GB, the others three, so the classifying warps (the critical
+                    // path of the slab) reach the barrier with a third of the others' ballot work.  NG loads in
+                    // flight, then setp+vote pairs kept adjacent (inline PTX) so the compiler does not park 17
+                    // predicates in a register and dig them out again.
+                    const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * lane;
+                    uint32_t* dst = sm.bits[bcur];
+                    const int batches = warp < CW ? 1 : 3;
+                    const int first = warp < CW ? warp : CW + 3 * (warp - CW);
 #pragma unroll 1
-                    for (int k0 = 0; k0 < D::FB; k0 += D::PB) {
-                        int dens[D::PB];
+                    for (int g = 0; g < batches; ++g) {
+                        const int b0 = first + g;  // block b0 + GB * k
+                        int dens[D::NG];
 #pragma unroll
-                        for (int k = 0; k < D::PB; ++k) dens[k] = src[64 * FW * (k0 + k)];
+                        for (int k = 0; k < D::NG; ++k) dens[k] = src[64 * (b0 + D::GB * k)];
 #pragma unroll
-                        for (int k = 0; k < D::PB; ++k) {
+                        for (int k = 0; k < D::NG; ++k) {
                             uint32_t v;
                             asm volatile(
                                 "{\n\t.reg .pred p;\n\t"
@@ -995,7 +1000,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                 "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}"
                                 : "=r"(v)
                                 : "r"(dens[k]));
-                            if (lane == 0) dst[FW * (k0 + k)] = v;
+                            if (lane == 0) dst[b0 + D::GB * k] = v;
                         }
                     }
                     if (C::TAIL != 0 && warp == FW - 1) {
