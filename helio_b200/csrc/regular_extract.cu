@@ -35,9 +35,6 @@
 #include "hvx_device.cuh"
 #include "hvx_kernels.h"
 
-#ifndef HVX_CLASSIFIER_BLOCKS
-#define HVX_CLASSIFIER_BLOCKS 1
-#endif
 // edge-32 decoupled kernel: emission warps, ring slots and CTAs per SM (tuning knobs; measured on B200:
 // 3 CTAs x (4 front + 6 emission + 2) warps beat 2 x (4 + 8 + 2) by 17-20 % -- the per-slab front-end chain is
 // latency bound at this slab size, so a third CTA per SM is a third chain in flight)
@@ -986,13 +983,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     // predicates in a register and dig them out again.
                     const short* src = reinterpret_cast<const short*>(&sm.ring[slot][0]) + 2 * lane;
                     uint32_t* dst = sm.bits[bcur];
-#if HVX_CLASSIFIER_BLOCKS
                     const int batches = warp < CW ? 1 : 3;
                     const int first = warp < CW ? warp : CW + 3 * (warp - CW);
-#else
-                    const int batches = warp < CW ? 0 : 4;
-                    const int first = warp < CW ? 0 : 4 * (warp - CW);
-#endif
 #pragma unroll 1
                     for (int g = 0; g < batches; ++g) {
                         const int b0 = first + g;  // block b0 + GB * k
