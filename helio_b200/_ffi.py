@@ -65,7 +65,7 @@ class Config(C.Structure):
 
 class ChunkDesc(C.Structure):
     _fields_ = [("generation", C.c_uint64), ("dirty_microbricks", C.c_uint64), ("transition_mask", C.c_uint32),
-                ("_pad", C.c_uint32)]
+                ("cost_hint", C.c_uint32)]
 
 
 class Range(C.Structure):

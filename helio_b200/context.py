@@ -65,11 +65,12 @@ def _input_pointer(array, expected_dtype=np.uint32):
     return C.c_void_p(arr.ctypes.data), arr.size, arr
 
 
-_DESC_DTYPE = np.dtype([("generation", "<u8"), ("dirty_microbricks", "<u8"), ("transition_mask", "<u4"), ("_pad", "<u4")])
+_DESC_DTYPE = np.dtype([("generation", "<u8"), ("dirty_microbricks", "<u8"), ("transition_mask", "<u4"), ("cost_hint", "<u4")])
 
 
-def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask=0):
-    """ctypes array of ``hvx_chunk_desc``; scalar arguments broadcast, sequences are per chunk."""
+def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask=0, cost_hint=0):
+    """ctypes array of ``hvx_chunk_desc``; scalar arguments broadcast, sequences are per chunk.  ``cost_hint``
+    (e.g. each chunk's vertex count last time) makes the batch start its heaviest chunks first."""
     arr = np.zeros(max(n, 1), dtype=_DESC_DTYPE)
 
     def column(value, mask):
@@ -80,6 +81,7 @@ def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask
     arr["generation"][:n] = column(generation, (1 << 64) - 1)
     arr["dirty_microbricks"][:n] = column(dirty_microbricks, (1 << 64) - 1)
     arr["transition_mask"][:n] = column(transition_mask, 0xFFFFFFFF)
+    arr["cost_hint"][:n] = column(cost_hint, 0xFFFFFFFF)
     descs = (_ffi.ChunkDesc * max(n, 1)).from_buffer(arr)
     descs._keepalive = arr
     return descs

@@ -6,6 +6,7 @@
 //   TransvoxelGpuTransitionExtractor  PV/src/transvoxel_transition_gpu.rs:190-520
 // Ownership follows the reference: the ctx owns every device buffer, the caller borrows inputs
 // for the duration of the call, outputs are overwritten by the next dispatch.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdlib>
@@ -29,6 +30,7 @@ struct hvx_ctx {
     void* buf[HVX_BUF_COUNT] = {};
     uint64_t buf_bytes[HVX_BUF_COUNT] = {};
     ChunkDesc* d_descs = nullptr;
+    uint32_t* d_order = nullptr;      // [max_chunks] start order of a batch with cost hints
     int64_t* d_pages = nullptr;
     uint8_t* d_lod = nullptr;
     // fBm terrain fill: distinct (x, z, lod) columns of the batch and their shared height maps
@@ -223,6 +225,17 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     p.n_chunks = n;
     p.mode = mode;
     for (uint32_t i = 0; i < n && !p.any_partial; ++i) p.any_partial = descs[i].dirty_microbricks != ~0ull;
+    // cost hints -> start order: descending hint, ties in chunk order (the scheduler's LPT rule)
+    bool hinted = false;
+    for (uint32_t i = 0; i < n && !hinted; ++i) hinted = descs[i].cost_hint != 0u;
+    if (hinted) {
+        std::vector<uint32_t> order(n);
+        for (uint32_t i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].cost_hint > descs[b].cost_hint; });
+        // pageable source: cudaMemcpyAsync returns once it is staged, so the temporary may go out of scope
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, order.data(), static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        p.order = ctx->d_order;
+    }
     if (const char* dbg = getenv("HVX_DEBUG_STREAM_ONLY"))  // diagnostics only: skip all compute
         if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY; else if (dbg[0] == '2') p.mode = MODE_BITS_ONLY;
     if (const char* f = getenv("HVX_DEBUG_FLAGS")) p.debug_flags = static_cast<uint32_t>(atoi(f));
@@ -444,6 +457,7 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     ctx->stream = ctx->own_stream;
     int rc;
     if ((rc = small_alloc(ctx, &ctx->d_descs, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_order, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_index, c.max_chunks))) return bail(rc);
@@ -465,6 +479,7 @@ void hvx_destroy(hvx_ctx* ctx) {
     for (void*& b : ctx->buf)
         if (b) cudaFree(b);
     cudaFree(ctx->d_descs);
+    cudaFree(ctx->d_order);
     cudaFree(ctx->d_pages);
     cudaFree(ctx->d_lod);
     cudaFree(ctx->d_col_index);

@@ -13,7 +13,7 @@ struct ChunkDesc {
     uint64_t generation;
     uint64_t dirty_microbricks;
     uint32_t transition_mask;
-    uint32_t _pad;
+    uint32_t cost_hint;
 };
 
 enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1, MODE_STREAM_ONLY = 2, MODE_BITS_ONLY = 3 };
@@ -21,6 +21,7 @@ enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1, MODE_STREAM_ONLY = 2, MOD
 struct RegularParams {
     const uint32_t* samples;  // [n][(E+2)^3]
     const ChunkDesc* descs;   // [n] device
+    const uint32_t* order;    // nullable, [n] device: the k-th chunk to start (descending cost hints)
     uint32_t n_chunks;
     uint32_t mode;
     uint32_t debug_flags;  // diagnostics: bit 0 disables the classification fast-reject

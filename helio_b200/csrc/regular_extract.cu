@@ -929,7 +929,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             int slot = 0;
             uint32_t round = 0;
             for (uint32_t k = 0;; ++k) {
-                const uint32_t id = atomicAdd(p.work_counter, 1u);
+                const uint32_t ticket = atomicAdd(p.work_counter, 1u);
+                // heaviest chunks first when the caller supplied cost hints (a chunk's slot does not depend on when it runs)
+                const uint32_t id = (ticket < p.n_chunks && p.order != nullptr) ? p.order[ticket] : ticket;
                 sm.chunk_ids[k & 3] = id;
                 if (id >= p.n_chunks) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);

@@ -151,7 +151,10 @@ typedef struct {
     uint64_t generation;
     uint64_t dirty_microbricks; /* 4x4x4 microbricks of (edge/4)^3 cells; bit = mx + 4*my + 16*mz */
     uint32_t transition_mask;   /* TransitionFace bits 0..5 (-X,+X,-Y,+Y,-Z,+Z) */
-    uint32_t _pad;
+    uint32_t cost_hint;         /* scheduler input, 0 = unknown: a relative cost estimate, e.g. the chunk's vertex
+                                   count at its last extraction.  When any chunk of a batch carries a hint, the
+                                   batch is STARTED in descending hint order (longest first, so the kernel does not
+                                   end on a lone heavy chunk); slots, ranges and meshes do not depend on it. */
 } hvx_chunk_desc;
 
 /* PV/src/transvoxel_emit.rs:57-85 TransvoxelGpuExtractorConfig +

@@ -24,7 +24,7 @@ pub struct hvx_chunk_desc {
     pub generation: u64,
     pub dirty_microbricks: u64,
     pub transition_mask: u32,
-    pub _pad: u32,
+    pub cost_hint: u32,
 }
 
 #[repr(C)]

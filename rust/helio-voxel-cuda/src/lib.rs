@@ -98,7 +98,7 @@ impl TransvoxelGpuExtractor {
     /// PV/src/transvoxel_emit.rs:233-254
     pub fn dispatch(&self, samples: &[CellWord], generation: u64, dirty_microbricks: u64, transition_mask: u8)
         -> Result<(), TransvoxelGpuError> {
-        let desc = ffi::hvx_chunk_desc { generation, dirty_microbricks, transition_mask: transition_mask as u32, _pad: 0 };
+        let desc = ffi::hvx_chunk_desc { generation, dirty_microbricks, transition_mask: transition_mask as u32, cost_hint: 0 };
         let words: &[u32] = bytemuck::cast_slice(samples);
         let status = unsafe { ffi::hvx_extract_regular(self.ctx.0, words.as_ptr(), words.len() as u64, &desc, 1) };
         if status != ffi::HVX_OK { return Err(error(self.ctx.0, status, samples.len(), 34 * 34 * 34, transition_mask, self.config)); }
@@ -140,7 +140,7 @@ impl TransvoxelGpuTransitionExtractor {
 
     /// PV/src/transvoxel_transition_gpu.rs:366-380 (mask before generation, like the reference)
     pub fn dispatch(&self, face_slabs: &[CellWord], transition_mask: u8, generation: u64) -> Result<(), TransvoxelGpuError> {
-        let desc = ffi::hvx_chunk_desc { generation, dirty_microbricks: u64::MAX, transition_mask: transition_mask as u32, _pad: 0 };
+        let desc = ffi::hvx_chunk_desc { generation, dirty_microbricks: u64::MAX, transition_mask: transition_mask as u32, cost_hint: 0 };
         let words: &[u32] = bytemuck::cast_slice(face_slabs);
         let status = unsafe { ffi::hvx_extract_transition(self.ctx.0, words.as_ptr(), words.len() as u64, &desc, 1) };
         if status != ffi::HVX_OK { return Err(error(self.ctx.0, status, face_slabs.len(), 6 * 3 * 67 * 67, transition_mask, self.config)); }

@@ -277,3 +277,28 @@ def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, 
         assert_vertices_equal(first[2][r["first_vertex"]:r["first_vertex"] + r["vertex_count"]], want.vertices, f"chunk {k}")
         assert np.array_equal(first[3][r["first_index"]:r["first_index"] + r["index_count"]], want.indices), k
     batch.close()
+
+
+def test_cost_hints_change_the_start_order_and_nothing_else():
+    """hvx_chunk_desc.cost_hint: heaviest-first scheduling must leave counters, ranges and every mesh byte alone."""
+    rng = np.random.default_rng(3)
+    n = 300
+    pages = np.array([[x - 10, -1 if (x + z) % 2 else 1, z - 8] for z in range(15) for x in range(20)][:n], dtype=np.int64)
+    batch = H.ChunkBatchExtractor(0, edge=64, max_chunks=n, max_vertices=49_152, max_indices=73_728)
+    batch.fill_density(O.FIELD_TERRAIN_FBM, pages)
+    masks = [int(m) for m in rng.integers(0, 64, n)]
+
+    def run(descs):
+        batch.ctx.extract_regular(None, descs, n)
+        c, r = batch.counters(n).copy(), batch.ranges(n).copy()
+        v, i, packed = batch.ctx.read_meshes(0, 0, n)
+        return c, r, v.copy(), i.copy(), packed.copy()
+
+    plain = run(H.make_descs(n, transition_mask=masks))
+    hints = [int(v) for v in plain[0]["required_vertices"]]
+    assert max(hints) > 0 and min(hints) == 0
+    for h in (hints, [int(v) for v in rng.integers(0, 1000, n)], [7] * n):
+        again = run(H.make_descs(n, transition_mask=masks, cost_hint=h))
+        for a, b in zip(plain, again):
+            assert a.tobytes() == b.tobytes()
+    batch.close()
