@@ -44,6 +44,7 @@ HVX_E_RESERVATION_MISMATCH = -48
 HVX_E_DEVICE_BUFFER_LIMIT = -49
 
 HVX_CFG_DEBUG_RECORDS = 1
+HVX_CFG_FIRST_GENERATION = 2
 (XPUB_VERTICES, XPUB_INDICES, XPUB_PAGE_RANGES, XPUB_COUNTERS) = range(4)
 (BRICK_VERTICES, BRICK_NORMALS, BRICK_INDICES, BRICK_DESCRIPTORS, BRICK_DRAWS, BRICK_REJECTED) = range(6)
 (PUB_REGULAR_VERTICES, PUB_REGULAR_INDICES, PUB_TRANSITION_VERTICES, PUB_TRANSITION_INDICES, PUB_STATES, PUB_REGULAR_DRAWS,
@@ -157,7 +158,7 @@ class ExtractionPublisherCounters(C.Structure):
 # every symbol include/hvx.h declares; tests assert the library exports all of them
 EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
-    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count",
+    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_selftest_edge_parameter",
     "hvx_fill_density", "hvx_fill_slabs", "hvx_extract_regular", "hvx_classify_regular", "hvx_extract_transition",
     "hvx_build_meshlets", "hvx_gather_surface", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
     "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
@@ -206,6 +207,8 @@ def load() -> C.CDLL:
     L.hvx_synchronize.argtypes = [vp]
     L.hvx_launch_count.argtypes = [vp]
     L.hvx_launch_count.restype = C.c_uint64
+    L.hvx_debug_set_mode.argtypes = [vp, C.c_uint32]
+    L.hvx_selftest_edge_parameter.argtypes = [C.c_int, u64p, u32p]
     L.hvx_fill_density.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
     L.hvx_fill_slabs.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
     L.hvx_extract_regular.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]

@@ -91,12 +91,14 @@ class Context:
     """One device, one stream, one set of fixed-stride output arenas (``hvx_ctx``)."""
 
     def __init__(self, device=0, *, edge=32, max_chunks=1, max_vertices=393_216, max_indices=491_520,
-                 max_transition_vertices=0, max_transition_indices=0, debug_records=False, error_kind="regular"):
+                 max_transition_vertices=0, max_transition_indices=0, debug_records=False, first_generation=False,
+                 error_kind="regular"):
         self._lib = _ffi.load()
         self._handle = C.c_void_p()
         self._error_kind = error_kind
         cfg = _ffi.Config(edge, max_chunks, max_vertices, max_indices, max_transition_vertices,
-                          max_transition_indices, _ffi.HVX_CFG_DEBUG_RECORDS if debug_records else 0, 0)
+                          max_transition_indices, (_ffi.HVX_CFG_DEBUG_RECORDS if debug_records else 0) |
+                          (_ffi.HVX_CFG_FIRST_GENERATION if first_generation else 0), 0)
         status = self._lib.hvx_create(C.byref(self._handle), int(device), C.byref(cfg))
         if status != _ffi.HVX_OK:
             message = self._lib.hvx_last_error(None).decode()
@@ -110,6 +112,7 @@ class Context:
         self.max_transition_vertices = max_transition_vertices
         self.max_transition_indices = max_transition_indices
         self.debug_records = debug_records
+        self.first_generation = first_generation
         self.sample_words = (edge + 2) ** 3
         self.slab_words = 18 * (2 * edge + 3) ** 2
         self.cells = edge ** 3
@@ -144,6 +147,10 @@ class Context:
 
     def synchronize(self):
         self._check(self._lib.hvx_synchronize(self._handle))
+
+    def debug_set_mode(self, mode):
+        """Roofline probes of the regular kernel: 0 normal, 1 stream only, 2 stream + sign bits (no meshes)."""
+        self._check(self._lib.hvx_debug_set_mode(self._handle, int(mode)))
 
     @property
     def launch_count(self):

@@ -27,9 +27,13 @@ struct hvx_ctx {
     DeviceInfo dev{};
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaEvent_t handover = nullptr;   // orders a new stream after the old one (hvx_set_stream)
     void* buf[HVX_BUF_COUNT] = {};
     uint64_t buf_bytes[HVX_BUF_COUNT] = {};
-    ChunkDesc* d_descs = nullptr;
+    ChunkDesc* d_descs = nullptr;     // [max_chunks] descriptors of the last REGULAR dispatch
+    ChunkDesc* d_tdescs = nullptr;    // [max_chunks] descriptors of the last TRANSITION dispatch
+    uint32_t n_regular = 0, n_transition = 0;  // sizes of those dispatches (hvx_build_meshlets reads the generations)
+    uint32_t debug_mode = 0;          // hvx_debug_set_mode
     uint32_t* d_order = nullptr;      // [max_chunks] start order of a batch with cost hints
     int64_t* d_pages = nullptr;
     uint8_t* d_lod = nullptr;
@@ -191,9 +195,9 @@ int resolve_input(hvx_ctx* ctx, const uint32_t* ptr, uint64_t words, int arena_i
     return HVX_OK;
 }
 
-int upload_descs(hvx_ctx* ctx, const hvx_chunk_desc* descs, uint32_t n) {
+int upload_descs(hvx_ctx* ctx, ChunkDesc* dst, const hvx_chunk_desc* descs, uint32_t n) {
     static_assert(sizeof(hvx_chunk_desc) == sizeof(ChunkDesc), "desc layout");
-    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_descs, descs, static_cast<size_t>(n) * sizeof(ChunkDesc),
+    HVX_CUDA(ctx, cudaMemcpyAsync(dst, descs, static_cast<size_t>(n) * sizeof(ChunkDesc),
                                   cudaMemcpyHostToDevice, ctx->stream));
     return HVX_OK;
 }
@@ -218,7 +222,8 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     DeviceGuard guard(ctx->device);
     const uint32_t* d_samples = nullptr;
     if ((rc = resolve_input(ctx, samples, words, HVX_BUF_SAMPLES, &d_samples))) return rc;
-    if ((rc = upload_descs(ctx, descs, n))) return rc;
+    if ((rc = upload_descs(ctx, ctx->d_descs, descs, n))) return rc;
+    ctx->n_regular = n;
     RegularParams p{};
     p.samples = d_samples;
     p.descs = ctx->d_descs;
@@ -236,9 +241,9 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, order.data(), static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         p.order = ctx->d_order;
     }
-    if (const char* dbg = getenv("HVX_DEBUG_STREAM_ONLY"))  // diagnostics only: skip all compute
-        if (dbg[0] == '1') p.mode = MODE_STREAM_ONLY; else if (dbg[0] == '2') p.mode = MODE_BITS_ONLY;
-    if (const char* f = getenv("HVX_DEBUG_FLAGS")) p.debug_flags = static_cast<uint32_t>(atoi(f));
+    if (ctx->debug_mode == 1) p.mode = MODE_STREAM_ONLY;  // hvx_debug_set_mode: roofline probes, no compute
+    else if (ctx->debug_mode == 2) p.mode = MODE_BITS_ONLY;
+    p.first_generation = (ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) ? 1u : 0u;
     p.max_vertices = ctx->cfg.max_vertices;
     p.max_indices = ctx->cfg.max_indices;
     p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);
@@ -252,7 +257,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     p.work_counter = ctx->d_work;
     cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
-    ctx->launches += 1;
+    ctx->launches += (p.cells != nullptr && !p.first_generation) ? 3 : 1;  // + the two record kernels
     return HVX_OK;
 }
 
@@ -334,7 +339,6 @@ int run_fill(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t
             if (ctx->d_heights) {
                 HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
                 cudaFree(ctx->d_heights);
-    for (void* b : ctx->stage) cudaFree(b);
                 ctx->allocated -= ctx->heights_cols * s * s * sizeof(float);
                 ctx->d_heights = nullptr;
                 ctx->heights_cols = 0;
@@ -408,6 +412,8 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     const hvx_config c = *config;
     if (c.edge != 32 && c.edge != 64) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "edge must be 32 or 64, got %u", c.edge);
     if (c.max_chunks == 0) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "max_chunks must be nonzero");
+    if (c.flags & ~(HVX_CFG_DEBUG_RECORDS | HVX_CFG_FIRST_GENERATION))
+        return fail(nullptr, HVX_E_INVALID_ARGUMENT, "unknown configuration flags %#x", c.flags);
     // TransvoxelGpuExtractorConfig::new, PV/src/transvoxel_emit.rs:63-75
     if (c.max_vertices == 0 || c.max_indices == 0)
         return fail(nullptr, HVX_E_INVALID_CAPACITY,
@@ -447,6 +453,7 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if (prop.major < 10)
         return bail(fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: requires compute capability 10.0 (sm_100a), device is %d.%d",
                          prop.major, prop.minor));
+    ctx->dev.ordinal = device;
     ctx->dev.sm_count = prop.multiProcessorCount;
     ctx->dev.max_smem_optin = static_cast<int>(prop.sharedMemPerBlockOptin);
     if (regular_smem_bytes(static_cast<int>(c.edge)) > prop.sharedMemPerBlockOptin)
@@ -455,8 +462,11 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaStreamCreate"));
     ctx->stream = ctx->own_stream;
+    if ((e = cudaEventCreateWithFlags(&ctx->handover, cudaEventDisableTiming)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaEventCreate"));
     int rc;
     if ((rc = small_alloc(ctx, &ctx->d_descs, c.max_chunks))) return bail(rc);
+    if (c.max_transition_vertices != 0 && (rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_order, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
@@ -479,6 +489,7 @@ void hvx_destroy(hvx_ctx* ctx) {
     for (void*& b : ctx->buf)
         if (b) cudaFree(b);
     cudaFree(ctx->d_descs);
+    cudaFree(ctx->d_tdescs);
     cudaFree(ctx->d_order);
     cudaFree(ctx->d_pages);
     cudaFree(ctx->d_lod);
@@ -491,6 +502,7 @@ void hvx_destroy(hvx_ctx* ctx) {
     cudaFree(ctx->d_packed);
     cudaFree(ctx->pack_v);
     cudaFree(ctx->pack_i);
+    if (ctx->handover) cudaEventDestroy(ctx->handover);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -506,7 +518,21 @@ uint64_t hvx_launch_count(const hvx_ctx* ctx) { return ctx ? ctx->launches : 0; 
 
 int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
-    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    cudaStream_t next = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    if (next == ctx->stream) return HVX_OK;
+    // the ctx scratch (descriptors, work counters, staging) may still be in use by work queued on the old stream:
+    // the new stream starts after it
+    DeviceGuard guard(ctx->device);
+    HVX_CUDA(ctx, cudaEventRecord(ctx->handover, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamWaitEvent(next, ctx->handover, 0));
+    ctx->stream = next;
+    return HVX_OK;
+}
+
+int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (mode > 2) return fail(ctx, HVX_E_INVALID_ARGUMENT, "debug mode must be 0 (off), 1 (stream only) or 2 (stream + sign bits)");
+    ctx->debug_mode = mode;
     return HVX_OK;
 }
 
@@ -554,10 +580,11 @@ int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t words, 
     DeviceGuard guard(ctx->device);
     const uint32_t* d_slabs = nullptr;
     if ((rc = resolve_input(ctx, slabs, words, HVX_BUF_SLABS, &d_slabs))) return rc;
-    if ((rc = upload_descs(ctx, descs, n))) return rc;
+    if ((rc = upload_descs(ctx, ctx->d_tdescs, descs, n))) return rc;
+    ctx->n_transition = n;
     TransitionParams p{};
     p.slabs = d_slabs;
-    p.descs = ctx->d_descs;
+    p.descs = ctx->d_tdescs;
     p.n_chunks = n;
     p.max_vertices = ctx->cfg.max_transition_vertices;
     p.max_indices = ctx->cfg.max_transition_indices;
@@ -818,7 +845,7 @@ uint64_t hvx_publisher_buffer_bytes(hvx_publisher* pub, int id) { return (pub &&
 int hvx_publisher_read(hvx_publisher* pub, int id, uint64_t offset, uint64_t bytes, void* dst) {
     if (!pub || id < 0 || id >= HVX_PUB_COUNT || !dst) return HVX_E_INVALID_ARGUMENT;
     hvx_ctx* ctx = pub->ctx;
-    if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of publisher buffer %d", id);
+    if (offset > pub->bytes[id] || bytes > pub->bytes[id] - offset) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of publisher buffer %d", id);
     DeviceGuard guard(ctx->device);
     HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(pub->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -828,7 +855,7 @@ int hvx_publisher_read(hvx_publisher* pub, int id, uint64_t offset, uint64_t byt
 int hvx_publisher_write(hvx_publisher* pub, int id, uint64_t offset, uint64_t bytes, const void* src) {
     if (!pub || id < 0 || id >= HVX_PUB_COUNT || !src) return HVX_E_INVALID_ARGUMENT;
     hvx_ctx* ctx = pub->ctx;
-    if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of publisher buffer %d", id);
+    if (offset > pub->bytes[id] || bytes > pub->bytes[id] - offset) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of publisher buffer %d", id);
     DeviceGuard guard(ctx->device);
     HVX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(pub->buf[id]) + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -876,6 +903,7 @@ int hvx_extraction_publisher_attach(hvx_extraction_publisher* pub, hvx_ctx* ctx)
         if (e == cudaSuccess && i >= HVX_XPUB_PAGE_RANGES) e = cudaMemsetAsync(pub->buf[i], 0, pub->bytes[i], ctx->stream);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            if (pub->buf[i]) cudaFree(pub->buf[i]);  // allocated, but the clear failed
             pub->buf[i] = nullptr;
             const int rc = fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: extraction arena %d requires %llu bytes: %s", i,
                                 static_cast<unsigned long long>(pub->bytes[i]), cudaGetErrorString(e));
@@ -937,7 +965,7 @@ void* hvx_extraction_publisher_buffer(hvx_extraction_publisher* pub, int id) {
 int hvx_extraction_publisher_read(hvx_extraction_publisher* pub, int id, uint64_t offset, uint64_t bytes, void* dst) {
     if (!pub || !pub->ctx || id < 0 || id >= HVX_XPUB_COUNT || !dst) return HVX_E_INVALID_ARGUMENT;
     hvx_ctx* ctx = pub->ctx;
-    if (offset + bytes > pub->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of extraction arena %d", id);
+    if (offset > pub->bytes[id] || bytes > pub->bytes[id] - offset) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of extraction arena %d", id);
     DeviceGuard guard(ctx->device);
     HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(pub->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -979,6 +1007,7 @@ int hvx_brick_mesher_create(hvx_ctx* ctx, uint32_t max_bricks, hvx_brick_mesher*
         if (e == cudaSuccess && i >= HVX_BRICK_DESCRIPTORS) e = cudaMemsetAsync(m->buf[i], 0, m->bytes[i], ctx->stream);
         if (e != cudaSuccess) {
             cudaGetLastError();
+            if (m->buf[i]) cudaFree(m->buf[i]);  // allocated, but the clear failed
             m->buf[i] = nullptr;
             const int rc = fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: brick buffer %d requires %llu bytes: %s", i,
                                 static_cast<unsigned long long>(m->bytes[i]), cudaGetErrorString(e));
@@ -1081,7 +1110,7 @@ uint64_t hvx_brick_buffer_bytes(hvx_brick_mesher* m, int id) { return (m && id >
 int hvx_brick_read(hvx_brick_mesher* m, int id, uint64_t offset, uint64_t bytes, void* dst) {
     if (!m || id < 0 || id >= HVX_BRICK_BUF_COUNT || !dst) return HVX_E_INVALID_ARGUMENT;
     hvx_ctx* ctx = m->ctx;
-    if (offset + bytes > m->bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of brick buffer %d", id);
+    if (offset > m->bytes[id] || bytes > m->bytes[id] - offset) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of brick buffer %d", id);
     DeviceGuard guard(ctx->device);
     HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(m->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1095,6 +1124,10 @@ int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n) {
     if (kind == 1 && ctx->cfg.max_transition_vertices == 0)
         return fail(ctx, HVX_E_INVALID_CAPACITY, "Transvoxel transition capacities must be nonzero (vertices=0, indices=0)");
     if (n == 0) return HVX_OK;
+    const uint32_t last = kind ? ctx->n_transition : ctx->n_regular;
+    if (n > last)
+        return fail(ctx, HVX_E_BATCH_CAPACITY, "meshlets requested for %u chunks, the last %s extraction held %u", n,
+                    kind ? "transition" : "regular", last);
     DeviceGuard guard(ctx->device);
     const int mid = kind ? HVX_BUF_TRANSITION_MESHLETS : HVX_BUF_REGULAR_MESHLETS;
     int rc;
@@ -1110,7 +1143,7 @@ int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n) {
     p.indices = static_cast<uint32_t*>(ctx->buf[kind ? HVX_BUF_TRANSITION_INDICES : HVX_BUF_REGULAR_INDICES]);
     p.regular_counters = static_cast<hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
     p.transition_counters = static_cast<hvx_transition_counters*>(ctx->buf[HVX_BUF_TRANSITION_COUNTERS]);
-    p.descs = ctx->d_descs;
+    p.descs = kind ? ctx->d_tdescs : ctx->d_descs;
     p.meshlets = static_cast<hvx_meshlet*>(ctx->buf[mid]);
     p.bounds = static_cast<hvx_meshlet_bounds*>(ctx->buf[mid + 1]);
     p.meshlet_counts = static_cast<uint32_t*>(ctx->buf[mid + 2]);
@@ -1135,7 +1168,7 @@ uint64_t hvx_buffer_bytes(hvx_ctx* ctx, int id) {
 int hvx_read(hvx_ctx* ctx, int id, uint64_t offset, uint64_t bytes, void* dst) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
     if (id < 0 || id >= HVX_BUF_COUNT || !ctx->buf[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "buffer %d is not allocated", id);
-    if (offset + bytes > ctx->buf_bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of buffer %d", id);
+    if (offset > ctx->buf_bytes[id] || bytes > ctx->buf_bytes[id] - offset) return fail(ctx, HVX_E_INVALID_ARGUMENT, "read past the end of buffer %d", id);
     if (bytes == 0) return HVX_OK;
     DeviceGuard guard(ctx->device);
     HVX_CUDA(ctx, cudaMemcpyAsync(dst, static_cast<const char*>(ctx->buf[id]) + offset, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1148,7 +1181,7 @@ int hvx_write(hvx_ctx* ctx, int id, uint64_t offset, uint64_t bytes, const void*
     DeviceGuard guard(ctx->device);
     int rc = ensure_buffer(ctx, id);
     if (rc) return rc;
-    if (offset + bytes > ctx->buf_bytes[id]) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of buffer %d", id);
+    if (offset > ctx->buf_bytes[id] || bytes > ctx->buf_bytes[id] - offset) return fail(ctx, HVX_E_INVALID_ARGUMENT, "write past the end of buffer %d", id);
     if (bytes == 0) return HVX_OK;
     HVX_CUDA(ctx, cudaMemcpyAsync(static_cast<char*>(ctx->buf[id]) + offset, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

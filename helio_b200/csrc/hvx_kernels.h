@@ -26,6 +26,7 @@ struct RegularParams {
     uint32_t mode;
     uint32_t debug_flags;  // diagnostics: bit 0 disables the classification fast-reject
     uint32_t any_partial;  // some chunk of the batch is partially dirty (picks the slab-skipping instantiation)
+    uint32_t first_generation;  // HVX_CFG_FIRST_GENERATION: run the first-generation kernel (cross-check only)
     uint32_t max_vertices, max_indices;  // per-chunk slot capacity
     hvx_vertex* vertices;                // [n][max_vertices]
     uint32_t* indices;                   // [n][max_indices]
@@ -67,6 +68,7 @@ struct FillParams {
 
 struct GatherParams {
     uint32_t n_jobs;
+    uint32_t job_base;                 // first job of this launch (grids tile the batch in steps of 65,535 jobs)
     hvx_residency residency;
     const hvx_page_table_entry* table;
     const uint32_t* atlas;
@@ -79,6 +81,7 @@ struct GatherParams {
 
 struct PublishParams {
     uint32_t n_jobs, slots;
+    uint32_t job_base;
     uint32_t has_transition;
     uint32_t src_max_vertices, src_max_indices, src_max_tvertices, src_max_tindices;  // extraction slot strides
     const hvx_surface_job* jobs;
@@ -109,6 +112,7 @@ struct CommitJob {
 
 struct CommitParams {
     uint32_t n_jobs;
+    uint32_t job_base;
     uint32_t src_max_vertices, src_max_indices;  // extraction slot strides
     const CommitJob* jobs;
     const hvx_emission_counters* regular_counters;
@@ -138,6 +142,7 @@ struct BrickParams {
 
 struct MeshletParams {
     uint32_t n_chunks;
+    uint32_t chunk_base;
     uint32_t transition;                  // 0 regular, 1 transition
     uint32_t max_vertices, max_indices;   // per-chunk slot capacity of the source arenas
     uint32_t max_meshlets;                // ceil(max_indices / 63)
@@ -152,12 +157,15 @@ struct MeshletParams {
 };
 
 struct DeviceInfo {
+    int ordinal;
     int sm_count;
     int max_smem_optin;
 };
 
 // Each returns the number of kernels launched (>= 1) or a negative cudaError-mapped status.
 cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream);
+// per-cell records, block-relative offsets and scan blocks (HVX_CFG_DEBUG_RECORDS), after the extraction
+cudaError_t launch_regular_records(int edge, const RegularParams& p, cudaStream_t stream);
 cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_samples(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);

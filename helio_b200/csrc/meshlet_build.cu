@@ -38,7 +38,7 @@ __device__ __forceinline__ bool vnormalize(V3 v, V3& out) {
 }
 
 __global__ void __launch_bounds__(64) meshlet_build_kernel(const MeshletParams p) {
-    const uint32_t chunk = blockIdx.y;
+    const uint32_t chunk = p.chunk_base + blockIdx.y;
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t emitted_indices, completed, overflow;
     if (p.transition) {
@@ -134,8 +134,13 @@ __global__ void __launch_bounds__(64) meshlet_build_kernel(const MeshletParams p
 
 cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo&, cudaStream_t stream) {
     if (p.n_chunks == 0 || p.max_meshlets == 0) return cudaSuccess;
-    const dim3 grid((p.max_meshlets + 63u) / 64u, p.n_chunks);
-    meshlet_build_kernel<<<grid, 64, 0, stream>>>(p);
+    // gridDim.y is limited to 65,535: larger batches go in several launches
+    for (uint32_t first = 0; first < p.n_chunks; first += 65535u) {
+        MeshletParams q = p;
+        q.chunk_base = first;
+        const dim3 grid((p.max_meshlets + 63u) / 64u, min(65535u, p.n_chunks - first));
+        meshlet_build_kernel<<<grid, 64, 0, stream>>>(q);
+    }
     return cudaGetLastError();
 }
 

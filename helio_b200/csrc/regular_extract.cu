@@ -30,14 +30,17 @@
 //     per VERTEX reading its 14 samples from the shared-memory bricks (no HBM re-read).
 //   * no single-address atomics: the reference's 5 atomicAdd per cell become one counter record
 //     written once per chunk.
-#include <cstdlib>
-
 #include "hvx_device.cuh"
 #include "hvx_kernels.h"
 
 // edge-32 decoupled kernel: emission warps, ring slots and CTAs per SM (tuning knobs; measured on B200:
 // 3 CTAs x (4 front + 6 emission + 2) warps beat 2 x (4 + 8 + 2) by 17-20 % -- the per-slab front-end chain is
 // latency bound at this slab size, so a third CTA per SM is a third chain in flight)
+// the decoupled kernel's edge parameter: 1 = branch-free division (edge_parameter_int16), 0 = __fdiv_rn with its
+// range check and slow-path call; bit-identical (tests/test_gpu_regular.py::test_edge_parameter_division_is_exact)
+#ifndef HVX_FAST_EDGE
+#define HVX_FAST_EDGE 1
+#endif
 #ifndef HVX_E32_NW
 #define HVX_E32_NW 6
 #endif
@@ -51,6 +54,40 @@
 namespace hvx {
 
 namespace {
+
+// ---- stress-build hooks (tools/repro_race.py; both compile to nothing in the product build) -------------------
+// HVX_JITTER: random sleeps at every hand-off of the decoupled kernel, so orderings that the protocol allows
+//   but a quiet machine never produces do occur (1 = one draw per warp, 2 = one draw per lane: also splits warps
+//   in front of every collective).  HVX_SELFCHECK: invariants of a tile (cell select inside the row mask, a
+//   surface case, vertex ownership, prefix fields) recorded into a device log instead of faulting later.
+#ifdef HVX_JITTER
+__device__ __forceinline__ void jitter(uint32_t salt) {
+    uint32_t c = (static_cast<uint32_t>(clock()) ^ (salt * 0x9E3779B9u) ^ (blockIdx.x * 0x85EBCA6Bu)) * 2654435761u;
+#if HVX_JITTER >= 2
+    c = (c ^ ((threadIdx.x & 31u) * 0xC2B2AE35u)) * 2246822519u;
+#else
+    c = (c ^ ((threadIdx.x >> 5) * 0xC2B2AE35u)) * 2246822519u;
+#endif
+    if ((c >> 29) == 0u) __nanosleep((c >> 8) & 8191u);
+}
+#define HVX_JIT(salt) jitter(salt)
+#else
+#define HVX_JIT(salt) ((void)0)
+#endif
+#ifdef HVX_SELFCHECK
+__device__ uint32_t g_selfcheck_count;
+__device__ uint32_t g_selfcheck_log[64][8];
+__device__ __noinline__ void selfcheck_fail(uint32_t code, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) {
+    const uint32_t i = atomicAdd(&g_selfcheck_count, 1u);
+    if (i < 64u) {
+        uint32_t* r = g_selfcheck_log[i];
+        r[0] = code; r[1] = blockIdx.x; r[2] = threadIdx.x; r[3] = a; r[4] = b; r[5] = c; r[6] = d; r[7] = e;
+    }
+}
+#define HVX_CHECK(cond, code, a, b, c, d, e) do { if (!(cond)) selfcheck_fail(code, a, b, c, d, e); } while (0)
+#else
+#define HVX_CHECK(cond, code, a, b, c, d, e) ((void)0)
+#endif
 
 // Lengyel's tables live in device global memory (statically initialised); every CTA copies the
 // 3.8 KB it needs into shared memory once (the kernel is persistent).
@@ -735,7 +772,11 @@ __device__ __forceinline__ void emit_regular_vertex_fast(const uint32_t* __restr
     endpoint(ax, ay, ea, az, wa, ma, ga);
     endpoint(bx, by, eb, bz, wb, mb, gb);
     const float d0 = fsub(ma, BIAS), d1 = fsub(mb, BIAS);
+#if HVX_FAST_EDGE
+    const float t = edge_parameter_int16(d0, d1);
+#else
     const float t = edge_parameter(d0, d1);
+#endif
     float p[3], n[3];
     const float fx = static_cast<float>(ax - 1), fy = static_cast<float>(ay - 1), fz = static_cast<float>(az - 1);
     p[0] = (axis & 1) ? fadd(fx, t) : fx;
@@ -942,6 +983,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 const uint64_t need = PARTIAL ? slabs_of_steps(dirty_steps<C>(p.descs[id].dirty_microbricks)) : ~0ull;
                 for (int j = 0; j < C::NSLAB; ++j) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    HVX_JIT(30);
                     if ((need >> j) & 1ull) {
                         mbar_arrive_expect_tx(&sm.full_bar[slot], C::SLAB_BYTES);
                         bulk_g2s(&sm.ring[slot][0], src + static_cast<size_t>(j) * C::SLAB_WORDS, C::SLAB_BYTES,
@@ -968,6 +1010,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             uint64_t dirty = 0, need = ~0ull;
             for (int j = 0; j < C::NSLAB; ++j) {
                 mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+                HVX_JIT(20);
                 if (j == 0) {
                     const uint32_t chunk = sm.chunk_ids[kc & 3];
                     if (chunk >= p.n_chunks) return;
@@ -1013,6 +1056,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     }
                 }
                 asm volatile("bar.sync 2, %0;" ::"n"(FW * 32) : "memory");  // the slab's bits are complete
+                HVX_JIT(21);
                 if (warp < CW) {
                     uint32_t incl = 0;
                     if (classify) {
@@ -1045,6 +1089,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
                     }
                     if (lane == 31) sm.wtot[slot][warp] = incl;
+                    HVX_JIT(22);
                     __syncwarp();  // every lane's stores are ordered before lane 0's releasing arrive
                     if (lane == 0) mbar_arrive(&sm.rec_bar[slot]);
                 }
@@ -1072,6 +1117,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             *reinterpret_cast<uint4*>(&sm.queue[qi][4]) = make_uint4(w4, w5, w6, w7);
             sm.q_ctr[qi] = 0u;
             sm.q_done[qi] = 0u;
+            HVX_JIT(11);
             mbar_arrive(&sm.q_bar[qi]);  // release: the entry is visible to whoever sees the phase flip
             ++q_tail;
         };
@@ -1090,6 +1136,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             bool prev_empty = false;
             for (int j = 0; j < C::NSLAB; ++j) {
                 mbar_wait_parked(&sm.rec_bar[slot], round & 1u);
+                HVX_JIT(10);
                 const int prev_slot = slot == 0 ? RS - 1 : slot - 1;
                 if (j == 0) {
                     // slab 0 has no steps -1 and 0: make their arrivals; slab 1 gets "step 0 done" next round
@@ -1144,6 +1191,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     for (uint32_t k = 0;; ++k) {
         const uint32_t qi = k & (NQ - 1);
         mbar_wait_parked(&sm.q_bar[qi], (k / NQ) & 1u);
+        HVX_JIT(1);
         const uint4 e0 = *reinterpret_cast<const uint4*>(&sm.queue[qi][0]);
         const uint4 e1 = *reinterpret_cast<const uint4*>(&sm.queue[qi][4]);
         const uint32_t kind = e0.x >> 30;
@@ -1195,7 +1243,18 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             const uint32_t n_cells = e0.z, tile_base = e0.w;
             const uint32_t cum[3] = {e1.x, e1.y, e1.z};
             const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
-            if (*const_cast<volatile uint32_t*>(&sm.q_ctr[qi]) < ntiles) {
+            HVX_JIT(2);
+            // "are there tiles left" must be ONE decision per warp: the counter moves while the lanes look at it, and
+            // a warp whose lanes disagreed would meet itself in the collectives below from two different entries
+            // (lane 0 reads, the shuffle makes the warp converge and agree)
+#ifdef HVX_LEGACY_PROTOCOL  // stress builds: the round-1 form (every lane reads for itself)
+            const uint32_t pulled = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]);
+#else
+            uint32_t pulled = 0;
+            if (lane == 0) pulled = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]);
+            pulled = __shfl_sync(0xffffffffu, pulled, 0);
+#endif
+            if (pulled < ntiles) {
                 const int slot_m = slot == 0 ? RS - 1 : slot - 1, slot_p = slot + 1 == RS ? 0 : slot + 1;
                 // the z gradient of the step's upper layer reads the first layer of slab st+1
                 if (st + 1 < C::NSLAB) mbar_wait(&sm.full_bar[slot_p], next_parity);
@@ -1214,9 +1273,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     if (lane == 0) t = atomicAdd(&sm.q_ctr[qi], 1u);
                     t = __shfl_sync(0xffffffffu, t, 0);
                     if (t >= ntiles) break;
+                    HVX_JIT(3);
                     // ---- one tile: TC consecutive active cells of the step ---------------------------
                     const uint32_t seq = tile_base + t;
                     const bool first = first_of_chunk != 0u && t == 0u;
+                    HVX_CHECK(slot < RS && st >= 1 && st < C::NSLAB && seq - tile_base < ntiles, 7u, chunk, st | (slot << 8), seq, t, ntiles);
                     const uint32_t r = D::TC * t + static_cast<uint32_t>(lane);
                     const bool valid = lane < D::TC && r < n_cells;
                     uint32_t rec = 0, packed = 0, info = 0, vbase = 0;
@@ -1247,6 +1308,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                 x = 32;
                             }
                         }
+                        HVX_CHECK(kk < static_cast<uint32_t>(__popc(w)), 1u, chunk, st | (slot << 8), seq, row | (kk << 16), w);
                         x += select_bit32(w, kk);
                         const int zl = row / E, y = row % E;
                         const uint32_t* l0 = ring_flat + wl[zl + 1] + (y + 1) * S + (x + 1);
@@ -1255,6 +1317,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                            (cw_solid(l0[S]) ? 4u : 0u) | (cw_solid(l0[S + 1]) ? 8u : 0u) |
                                            (cw_solid(l1[0]) ? 16u : 0u) | (cw_solid(l1[1]) ? 32u : 0u) |
                                            (cw_solid(l1[S]) ? 64u : 0u) | (cw_solid(l1[S + 1]) ? 128u : 0u);
+                        HVX_CHECK(c != 0u && c != 255u, 2u, chunk, st | (slot << 8), seq, row | (x << 16), c);
                         info = sm.case_info[c];
                         vbase = sm.vertex_base[c];
                         rec = static_cast<uint32_t>(x) | (row << 8) | (c << 16);
@@ -1273,16 +1336,27 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     const uint32_t vo_vb = vo | (vbase << 9);  // what a vertex lane needs from its cell: first vertex, code run
                     // chained prefix: wait for the previous tile's inclusive totals, publish ours.  Every
                     // lane polls the same word (a broadcast read), so the warp never splits around the spin.
+                    // The first tile of a chunk starts from zero but still waits for its predecessor (the previous chunk's
+                    // last tile; for the CTA's very first tile the initial ~0 carries the matching tag): publications
+                    // then happen strictly in sequence order, which is what lets 32 prefix words serve any number of
+                    // tiles -- tile q can only overwrite word q & 31 after tile q - 31 has read tile q - 32's totals.
+                    HVX_JIT(4);
                     uint64_t base = 0;
-                    if (!first) {
+#ifdef HVX_LEGACY_PROTOCOL  // stress builds: the round-1 form (a chunk's first tile does not wait)
+                    if (!first)
+#endif
+                    {
                         const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 31u];
                         const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
                         uint64_t got;
                         do {
                             got = *prev;
                         } while ((got >> 44) != want);
-                        base = got & ((1ull << 44) - 1ull);
+                        if (!first) base = got & ((1ull << 44) - 1ull);
                     }
+                    HVX_CHECK((base & FIELD) + tot_v <= FIELD && ((base >> 22) & FIELD) + tot_i <= FIELD, 5u, chunk, st | (slot << 8), seq,
+                              static_cast<uint32_t>(base), static_cast<uint32_t>(base >> 32));
+                    HVX_JIT(5);
                     if (lane == 0) {
                         const uint64_t mine = (base + static_cast<uint64_t>(tot_v) + (static_cast<uint64_t>(tot_i) << 22)) |
                                               (static_cast<uint64_t>(seq & 0xfffffu) << 44);
@@ -1312,6 +1386,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                         out_i[dst + q] = first_vertex + ((words[q >> 2] >> (8 * (q & 3))) & 0xffu);
                             }
                         }
+                        HVX_JIT(6);
                         __syncwarp();
                         for (uint32_t v0 = 0; v0 < tot_v; v0 += 32u) {
                             const uint32_t v = v0 + static_cast<uint32_t>(lane);
@@ -1319,6 +1394,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             const uint32_t o = on ? ow[v] : 0u;
                             const uint32_t cr = __shfl_sync(0xffffffffu, rec, o);
                             const uint32_t cvv = __shfl_sync(0xffffffffu, vo_vb, o);
+                            HVX_CHECK(!on || (v >= (cvv & 511u) && v - (cvv & 511u) < 12u && (cvv >> 9) + (v - (cvv & 511u)) < 1536u), 4u, chunk,
+                                      st | (slot << 8), seq, v | (o << 16), cvv);
                             if (on && v_base + v < p.max_vertices) {
                                 const int x = cr & 63, rw = (cr >> 8) & 255;
                                 const int zl = rw / E, y = rw % E;
@@ -1327,6 +1404,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             }
                         }
                     }
+                    HVX_JIT(7);
                     __syncwarp();  // every ring read of the tile is done; the owner map is free again
                     if (lane == 0 && atomicAdd(&sm.q_done[qi], 1u) + 1u == ntiles) {
                         // last tile of the step: "step st done" for slabs st-1, st, st+1
@@ -1342,34 +1420,45 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     }
 }
 
-template <class C, int GEN>
-cudaError_t launch_cfg(const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
-    const size_t smem = GEN == 2 ? sizeof(SmemD<C>) : sizeof(Smem<C>);
-    static_assert(sizeof(SmemD<C>) <= 232448 && sizeof(Smem<C>) <= 232448, "shared memory budget (227 KB per CTA)");
-    const int threads = GEN == 2 ? DecoupledCfg<C>::NT_ALL : C::NT_ALL;
-    auto* kernel = GEN == 0 ? regular_extract_kernel<C>
-                            : p.any_partial ? regular_extract_decoupled_kernel<C, true> : regular_extract_decoupled_kernel<C, false>;
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (err != cudaSuccess) return err;
-    int ctas_per_sm = 1;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, threads, smem);
-    if (err != cudaSuccess) return err;
-    if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
+using Cfg64 = Cfg<64, 2, 6, 16>;
+using Cfg32 = Cfg<32, 2, 10, 8>;
+using Cfg64D = Cfg<64, 1, 6, 20>;  // decoupled kernel at edge 64: 8 front + 20 emission + producer + scheduler warps
+using Cfg32D = Cfg<32, 1, HVX_E32_RS, HVX_E32_NW>;  // decoupled kernel at edge 32: 4 front + 6 emission + producer + scheduler warps, 3 CTAs / SM
+
+// One launch.  The shared-memory opt-in and the occupancy query are per device and do not change: they are made
+// on a device's first launch of a kernel and remembered (two driver calls less on the single-page latency path).
+template <class Kernel>
+cudaError_t launch_persistent(Kernel* kernel, int* ctas_cache, int threads, size_t smem, const RegularParams& p,
+                              const DeviceInfo& dev, cudaStream_t stream) {
+    int ctas_per_sm = dev.ordinal >= 0 && dev.ordinal < 64 ? __atomic_load_n(&ctas_cache[dev.ordinal], __ATOMIC_ACQUIRE) : 0;
+    if (ctas_per_sm == 0) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kernel, threads, smem);
+        if (err != cudaSuccess) return err;
+        if (ctas_per_sm < 1) return cudaErrorInvalidConfiguration;
+        if (dev.ordinal >= 0 && dev.ordinal < 64) __atomic_store_n(&ctas_cache[dev.ordinal], ctas_per_sm, __ATOMIC_RELEASE);
+    }
     const uint32_t grid = static_cast<uint32_t>(
         min(static_cast<long long>(p.n_chunks), static_cast<long long>(dev.sm_count) * ctas_per_sm));
     kernel<<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-using Cfg64 = Cfg<64, 2, 6, 16>;
-using Cfg32 = Cfg<32, 2, 10, 8>;
-using Cfg64D = Cfg<64, 1, 6, 20>;  // decoupled kernel at edge 64: 8 front + 20 emission + producer + scheduler warps
-using Cfg32D = Cfg<32, 1, HVX_E32_RS, HVX_E32_NW>;  // decoupled kernel at edge 32: 4 front + 6 emission + producer + scheduler warps, 3 CTAs / SM
+template <class C>
+cudaError_t launch_first_generation(const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+    static_assert(sizeof(Smem<C>) <= 232448, "shared memory budget (227 KB per CTA)");
+    static int ctas[64];
+    return launch_persistent(regular_extract_kernel<C>, ctas, C::NT_ALL, sizeof(Smem<C>), p, dev, stream);
+}
 
-// HVX_REGULAR_VARIANT=1 selects the first-generation kernel (identical output); default: decoupled.
-int variant_from_env() {
-    const char* v = getenv("HVX_REGULAR_VARIANT");
-    return v ? atoi(v) : 0;
+template <class C>
+cudaError_t launch_decoupled(const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+    static_assert(sizeof(SmemD<C>) <= 232448, "shared memory budget (227 KB per CTA)");
+    static int ctas[2][64];
+    if (p.any_partial)
+        return launch_persistent(regular_extract_decoupled_kernel<C, true>, ctas[1], DecoupledCfg<C>::NT_ALL, sizeof(SmemD<C>), p, dev, stream);
+    return launch_persistent(regular_extract_decoupled_kernel<C, false>, ctas[0], DecoupledCfg<C>::NT_ALL, sizeof(SmemD<C>), p, dev, stream);
 }
 
 }  // namespace
@@ -1382,11 +1471,35 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     if (p.n_chunks == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
-    // debug records (per-cell words, offsets, scan blocks) only exist in the first-generation kernel
-    const bool first_gen = p.cells != nullptr || variant_from_env() == 1;
-    if (edge == 64) return first_gen ? launch_cfg<Cfg64, 0>(p, dev, stream) : launch_cfg<Cfg64D, 2>(p, dev, stream);
-    if (edge == 32) return first_gen ? launch_cfg<Cfg32, 0>(p, dev, stream) : launch_cfg<Cfg32D, 2>(p, dev, stream);
-    return cudaErrorInvalidValue;
+    // The decoupled kernel is the product.  The first-generation kernel (CTA-wide barriers; writes the debug records
+    // itself) only runs for contexts created with HVX_CFG_FIRST_GENERATION: the cross-check of the stress tests.
+    if (p.first_generation) {
+        if (edge == 64) return launch_first_generation<Cfg64>(p, dev, stream);
+        if (edge == 32) return launch_first_generation<Cfg32>(p, dev, stream);
+        return cudaErrorInvalidValue;
+    }
+    RegularParams q = p;
+    q.cells = nullptr;  // per-cell records come from regular_records.cu
+    q.offsets = nullptr;
+    q.blocks = nullptr;
+    if (edge == 64) e = launch_decoupled<Cfg64D>(q, dev, stream);
+    else if (edge == 32) e = launch_decoupled<Cfg32D>(q, dev, stream);
+    else return cudaErrorInvalidValue;
+    if (e != cudaSuccess) return e;
+    return launch_regular_records(edge, p, stream);
 }
+
+#ifdef HVX_SELFCHECK
+// stress builds only (tools/repro_race.py): the invariant log of the decoupled kernel
+extern "C" int hvx_debug_selfcheck_read(uint32_t* count, uint32_t* log /* [64][8] */, int reset) {
+    if (cudaMemcpyFromSymbol(count, g_selfcheck_count, sizeof(uint32_t)) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(log, g_selfcheck_log, sizeof(uint32_t) * 64 * 8) != cudaSuccess) return -1;
+    if (reset) {
+        const uint32_t zero = 0;
+        if (cudaMemcpyToSymbol(g_selfcheck_count, &zero, sizeof zero) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 
 }  // namespace hvx

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
     __shared__ uint32_t pg_origin[64];  // atlas word index of the page's (0,0,0) texel, or ~0 when missing
     __shared__ uint32_t pg_probes[64];
     __shared__ uint32_t red[3][8];
-    const uint32_t jobi = blockIdx.y;
+    const uint32_t jobi = p.job_base + blockIdx.y;
     const int part = blockIdx.x;
     const hvx_gather_job job = p.jobs[jobi];
     const hvx_residency res = p.residency;
@@ -191,7 +191,11 @@ __global__ void gather_finalize_kernel(const GatherParams p) {
 
 cudaError_t launch_gather(const GatherParams& p, const DeviceInfo&, cudaStream_t stream) {
     if (p.n_jobs == 0) return cudaSuccess;
-    gather_kernel<<<dim3(7, p.n_jobs), 256, 0, stream>>>(p);
+    for (uint32_t first = 0; first < p.n_jobs; first += 65535u) {  // gridDim.y is limited to 65,535
+        GatherParams q = p;
+        q.job_base = first;
+        gather_kernel<<<dim3(7, min(65535u, p.n_jobs - first)), 256, 0, stream>>>(q);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     gather_finalize_kernel<<<(p.n_jobs + 127) / 128, 128, 0, stream>>>(p);

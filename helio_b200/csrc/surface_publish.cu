@@ -27,7 +27,7 @@ __device__ __forceinline__ hvx_transition_counters transition_counters_of(const 
 
 // grid = (blocks per job, jobs, 2): z = 0 regular, 1 transition
 __global__ void __launch_bounds__(256) publish_copy_kernel(const PublishParams p) {
-    const uint32_t j = blockIdx.y;
+    const uint32_t j = p.job_base + blockIdx.y;
     const bool transition = blockIdx.z != 0;
     if (transition && !p.has_transition) return;
     const hvx_surface_job job = p.jobs[j];
@@ -128,7 +128,7 @@ __global__ void visibility_kernel(const PublishParams p) {
 // grid = (blocks per job, jobs).  A job whose reservation does not match what the chunk emitted is
 // skipped by every block and counted once.
 __global__ void __launch_bounds__(256) commit_kernel(const CommitParams p) {
-    const CommitJob job = p.jobs[blockIdx.y];
+    const CommitJob job = p.jobs[p.job_base + blockIdx.y];
     const hvx_emission_counters c = p.regular_counters[job.chunk];
     const bool ok = c.completed != 0u && c.vertex_overflow == 0u && c.index_overflow == 0u &&
                     c.emitted_vertices == job.range.vertex_count && c.emitted_indices == job.range.index_count;
@@ -165,7 +165,11 @@ cudaError_t launch_commit(const CommitParams& p, const DeviceInfo& dev, cudaStre
     if (p.n_jobs == 0) return cudaSuccess;
     uint32_t per_job = 8;
     while (per_job > 1 && static_cast<uint64_t>(per_job) * p.n_jobs > 64ull * dev.sm_count) per_job >>= 1;
-    commit_kernel<<<dim3(per_job, p.n_jobs), 256, 0, stream>>>(p);
+    for (uint32_t first = 0; first < p.n_jobs; first += 65535u) {  // gridDim.y is limited to 65,535
+        CommitParams q = p;
+        q.job_base = first;
+        commit_kernel<<<dim3(per_job, min(65535u, p.n_jobs - first)), 256, 0, stream>>>(q);
+    }
     return cudaGetLastError();
 }
 
@@ -174,7 +178,11 @@ cudaError_t launch_publish(const PublishParams& p, const DeviceInfo& dev, cudaSt
     // enough blocks per job to cover a typical mesh in one or two grid-stride steps, bounded by the machine
     uint32_t per_job = 8;
     while (per_job > 1 && static_cast<uint64_t>(per_job) * p.n_jobs * 2 > 64ull * dev.sm_count) per_job >>= 1;
-    publish_copy_kernel<<<dim3(per_job, p.n_jobs, 2), 256, 0, stream>>>(p);
+    for (uint32_t first = 0; first < p.n_jobs; first += 65535u) {  // gridDim.y is limited to 65,535
+        PublishParams q = p;
+        q.job_base = first;
+        publish_copy_kernel<<<dim3(per_job, min(65535u, p.n_jobs - first), 2), 256, 0, stream>>>(q);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     publish_state_kernel<<<(p.n_jobs + 127) / 128, 128, 0, stream>>>(p);

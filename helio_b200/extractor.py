@@ -86,11 +86,15 @@ class _Single:
 class TransvoxelGpuExtractor(_Single):
     """Regular-cell extractor for one page per dispatch (the reference's shape)."""
 
-    def __init__(self, device=0, config=None, *, edge=32, debug_records=True):
+    def __init__(self, device=0, config=None, *, edge=32, debug_records=True, first_generation=False):
+        """``debug_records``: also produce the per-cell records behind cells_buffer / offsets_buffer / blocks_buffer
+        (two extra launches per dispatch; the meshes come from the same kernel either way).
+        ``first_generation``: diagnostics, extract with the first-generation kernel (identical output)."""
         config = config or TransvoxelGpuExtractorConfig()
         TransvoxelGpuExtractorConfig.new(config.max_vertices, config.max_indices)
         super().__init__(Context(device, edge=edge, max_chunks=1, max_vertices=config.max_vertices,
-                                 max_indices=config.max_indices, debug_records=debug_records))
+                                 max_indices=config.max_indices, debug_records=debug_records,
+                                 first_generation=first_generation))
         self._config = config
 
     def config(self):
@@ -128,8 +132,8 @@ class TransvoxelGpuExtractor(_Single):
 class TransvoxelGpuClassifier(_Single):
     """Classification only (PV/src/transvoxel_gpu.rs:148-356)."""
 
-    def __init__(self, device=0, *, edge=32):
-        super().__init__(Context(device, edge=edge, max_chunks=1, debug_records=True))
+    def __init__(self, device=0, *, edge=32, first_generation=False):
+        super().__init__(Context(device, edge=edge, max_chunks=1, debug_records=True, first_generation=first_generation))
 
     def dispatch(self, samples, generation, dirty_microbricks):
         count = samples.numel() if hasattr(samples, "numel") else np.asarray(samples).size
@@ -191,10 +195,11 @@ class ChunkBatchExtractor:
     """
 
     def __init__(self, device=0, *, edge=64, max_chunks=256, max_vertices=49_152, max_indices=73_728,
-                 max_transition_vertices=0, max_transition_indices=0, debug_records=False):
+                 max_transition_vertices=0, max_transition_indices=0, debug_records=False, first_generation=False):
         self.ctx = Context(device, edge=edge, max_chunks=max_chunks, max_vertices=max_vertices,
                            max_indices=max_indices, max_transition_vertices=max_transition_vertices,
-                           max_transition_indices=max_transition_indices, debug_records=debug_records)
+                           max_transition_indices=max_transition_indices, debug_records=debug_records,
+                           first_generation=first_generation)
 
     def fill_density(self, kind, page_xyz, lod=None, out_ptr=None):
         return self.ctx.fill_density(kind, page_xyz, lod, out_ptr)

@@ -170,7 +170,10 @@ typedef struct {
     uint32_t _reserved;
 } hvx_config;
 
-#define HVX_CFG_DEBUG_RECORDS 1u /* also write per-cell records, offsets and scan blocks */
+#define HVX_CFG_DEBUG_RECORDS 1u    /* also write per-cell records, offsets and scan blocks (two extra launches) */
+#define HVX_CFG_FIRST_GENERATION 2u /* diagnostics: extract regular cells with the first-generation kernel (CTA-wide
+                                       barriers instead of the decoupled warps); identical output, slower.  The stress
+                                       tests use it as an independent second implementation. */
 
 typedef struct hvx_ctx hvx_ctx;
 
@@ -192,6 +195,15 @@ void* hvx_get_stream(const hvx_ctx* ctx);
 int hvx_synchronize(hvx_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t hvx_launch_count(const hvx_ctx* ctx);
+/* Roofline probes for the regular kernel (bench tools only): 0 = normal, 1 = stream the samples and do nothing else,
+ * 2 = stream + sign bits.  Modes 1 and 2 produce no meshes. */
+int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode);
+
+/* Device-side proof of an arithmetic shortcut (diagnostics; tests/test_gpu_regular.py): the regular kernel divides
+ * d0 / (d0 - d1) without the IEEE slow path.  Checks all 2^32 pairs of i16 densities against the reference formula
+ * with __fdiv_rn; *mismatches_out = pairs whose result bits differ (must be 0), *witness_out = (d0+32768)<<16 | (d1+32768)
+ * of one of them. */
+int hvx_selftest_edge_parameter(int device, uint64_t* mismatches_out, uint32_t* witness_out);
 
 /* ---- K1: density / SDF fill -------------------------------------------------------- */
 /* ExtractionFixture::new (PV/src/fixture.rs:95-124) on the device.

@@ -13,9 +13,17 @@ from hvx_testutil import ALL, FIXTURE_PAGES, assert_vertices_equal, check_offset
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def extractor():
-    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig())
+# Every pinned case runs three ways: the decoupled kernel alone (what the bench times and production runs), the
+# decoupled kernel plus the per-cell record kernels (HVX_CFG_DEBUG_RECORDS), and the first-generation kernel
+# (HVX_CFG_FIRST_GENERATION, an independent second implementation that writes the records itself).
+VARIANTS = {"decoupled": dict(debug_records=False), "records": dict(debug_records=True),
+            "first_generation": dict(debug_records=True, first_generation=True)}
+
+
+@pytest.fixture(scope="module", params=list(VARIANTS))
+def extractor(request):
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig(), **VARIANTS[request.param])
+    ex.has_records = VARIANTS[request.param]["debug_records"]
     yield ex
     ex.close()
 
@@ -46,10 +54,11 @@ def test_emission_matches_cpu_geometry_on_every_fixture(extractor, name):
     samples = O.fixture_fill(kind, page)
     want, got_v, got_i = _check_dispatch(extractor, samples, generation, ALL, 0, name)
     # per-cell records and ranges (debug outputs a6 / a11)
-    cells = extractor.cells_buffer()
-    assert np.array_equal(cells["packed_case_class_counts"], want.cell_words[:, 0]), name
-    assert np.array_equal(cells["generation_low"], want.cell_words[:, 1]), name
-    check_offsets(extractor.offsets_buffer(), extractor.blocks_buffer(), want.cell_ranges, generation, name)
+    if extractor.has_records:
+        cells = extractor.cells_buffer()
+        assert np.array_equal(cells["packed_case_class_counts"], want.cell_words[:, 0]), name
+        assert np.array_equal(cells["generation_low"], want.cell_words[:, 1]), name
+        check_offsets(extractor.offsets_buffer(), extractor.blocks_buffer(), want.cell_ranges, generation, name)
     # byte-identical on repeat (gpu_transvoxel_emission.rs:125-151)
     extractor.dispatch(samples, generation, ALL, 0)
     assert extractor.vertices_buffer(len(got_v)).tobytes() == got_v.tobytes()
@@ -72,11 +81,12 @@ def test_dirty_microbrick_subset(extractor):
     extractor.dispatch(samples, 1400, ALL, 0)
     want, _, _ = _check_dispatch(extractor, samples, 1500, 1 << 12, 0, "dirty")
     assert len(want.vertices) > 0
-    gen = check_offsets(extractor.offsets_buffer(), extractor.blocks_buffer(), want.cell_ranges, 1500, "dirty")
-    visited = want.cell_ranges[:, 0] != 0xFFFFFFFF
-    assert visited.sum() == 512 and np.all(gen[~visited] != 1500)
-    cells = extractor.cells_buffer()
-    assert np.all(cells["generation_low"][visited] == 1500) and np.all(cells["generation_low"][~visited] == 1400)
+    if extractor.has_records:
+        gen = check_offsets(extractor.offsets_buffer(), extractor.blocks_buffer(), want.cell_ranges, 1500, "dirty")
+        visited = want.cell_ranges[:, 0] != 0xFFFFFFFF
+        assert visited.sum() == 512 and np.all(gen[~visited] != 1500)
+        cells = extractor.cells_buffer()
+        assert np.all(cells["generation_low"][visited] == 1500) and np.all(cells["generation_low"][~visited] == 1400)
     cls = extractor.classify_counters_buffer()
     assert cls["visited_cells"] == 8 * 8 * 8 and cls["active_cells"] > 0
 
@@ -98,15 +108,34 @@ def test_secondary_positions_all_faces(extractor, mask):
         _check_dispatch(extractor, O.fixture_fill(kind, page), 3, ALL, mask, f"mask {mask:#x} {page}")
 
 
-def test_overflow_contract():
-    """gpu_transvoxel_emission.rs:249-262: capacity (1,1) suppresses the emission, reports the need."""
-    tiny = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig.new(1, 1))
+@pytest.mark.parametrize("variant", list(VARIANTS))
+@pytest.mark.parametrize("capacity", [(1, 1), (4095, 6144), (4096, 6143), (100, 1_000_000), (1_000_000, 100)])
+def test_overflow_contract(variant, capacity):
+    """gpu_transvoxel_emission.rs:249-262: capacity (1,1) suppresses the emission, reports the need; one element
+    short in either arena does the same (and a neighbouring guard word stays untouched)."""
+    tiny = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig.new(*capacity), **VARIANTS[variant])
     tiny.dispatch(O.fixture_fill(O.FIELD_PLANE, [0, -1, 0]), 2000, ALL, 0)
     c = tiny.counters_buffer()
-    assert c["completed"] == 1 and c["vertex_overflow"] != 0 and c["index_overflow"] != 0
+    assert c["completed"] == 1
+    assert (c["vertex_overflow"] != 0) == (capacity[0] < 4096) and (c["index_overflow"] != 0) == (capacity[1] < 6144)
     assert c["emitted_vertices"] == 0 and c["emitted_indices"] == 0
     assert c["required_vertices"] == 4096 and c["required_indices"] == 6144
+    r = tiny.context.read(H._ffi.BUF_REGULAR_RANGES, 0, 1)[0]
+    assert r["vertex_count"] == 0 and r["index_count"] == 0
     tiny.close()
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_exact_capacity_is_not_an_overflow(variant):
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig.new(4096, 6144), **VARIANTS[variant])
+    samples = O.fixture_fill(O.FIELD_PLANE, [0, -1, 0])
+    want = O.extract_regular(samples, generation=3)
+    ex.dispatch(samples, 3, ALL, 0)
+    c = ex.counters_buffer()
+    assert c["vertex_overflow"] == 0 and c["index_overflow"] == 0 and c["emitted_vertices"] == 4096
+    assert_vertices_equal(ex.vertices_buffer(4096), want.vertices, "exact capacity")
+    assert np.array_equal(ex.indices_buffer(6144), want.indices)
+    ex.close()
 
 
 def test_errors_mirror_the_reference(extractor):
@@ -123,9 +152,10 @@ def test_errors_mirror_the_reference(extractor):
     assert extractor.resource_stats() == stats
 
 
-def test_classifier_matches_cpu(extractor):
+@pytest.mark.parametrize("first_generation", [False, True])
+def test_classifier_matches_cpu(first_generation):
     """gpu_transvoxel.rs:10-136: every GpuTransvoxelCell + counters, determinism, dirty subset."""
-    clf = H.TransvoxelGpuClassifier(0)
+    clf = H.TransvoxelGpuClassifier(0, first_generation=first_generation)
     for name, (kind, page) in FIXTURE_PAGES.items():
         samples = O.fixture_fill(kind, page)
         want = O.extract_regular(samples, generation=10 + kind)
@@ -165,15 +195,17 @@ def test_device_resident_samples(extractor):
     (O.FIELD_CAVE, [-1, 0, 0], 0), (O.FIELD_SHARP_CORNER, [0, 0, 0], 0), (O.FIELD_MATERIAL_SEAM, [-1, -1, 0], 1),
     (O.FIELD_TERRAIN_FBM, [0, -1, 0], 0), (O.FIELD_TERRAIN_FBM, [3, -1, -7], 0), (O.FIELD_TERRAIN_FBM, [0, -1, 0], 2),
 ])
-def test_edge64_matches_oracle(kind, page, lod):
-    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig(262_144, 393_216), edge=64)
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_edge64_matches_oracle(kind, page, lod, variant):
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig(262_144, 393_216), edge=64, **VARIANTS[variant])
     samples = O.fixture_fill(kind, page, lod=lod, edge=64)
     for mask, dirty in [(0, ALL), (0x3F, ALL), (0x12, 0x0F0F_0000_FFFF_00F0)]:
         want, _, _ = _check_dispatch(ex, samples, 42, dirty, mask, f"e64 kind {kind} {page} mask {mask:#x}", edge=64)
-        cells = ex.cells_buffer()
-        visited = want.cell_ranges[:, 0] != 0xFFFFFFFF
-        assert np.array_equal(cells["packed_case_class_counts"][visited], want.cell_words[visited, 0])
-        check_offsets(ex.offsets_buffer(), ex.blocks_buffer(), want.cell_ranges, 42, "e64")
+        if VARIANTS[variant]["debug_records"]:
+            cells = ex.cells_buffer()
+            visited = want.cell_ranges[:, 0] != 0xFFFFFFFF
+            assert np.array_equal(cells["packed_case_class_counts"][visited], want.cell_words[visited, 0])
+            check_offsets(ex.offsets_buffer(), ex.blocks_buffer(), want.cell_ranges, 42, "e64")
     ex.close()
 
 
@@ -193,10 +225,11 @@ def test_batch_of_mixed_chunks(edge):
     """N chunks per dispatch: every chunk's slot equals its single-chunk oracle result."""
     specs = [(O.FIELD_SPHERE, [0, 0, 0]), (O.FIELD_PLANE, [0, 1, 0]), (O.FIELD_PLANE, [0, -1, 0]),
              (O.FIELD_TERRAIN_FBM, [0, -1, 0]), (O.FIELD_CAVE, [-1, -1, -1]), (O.FIELD_PLANE, [5, -3, 2]),
-             (O.FIELD_TERRAIN_FBM, [2, -1, 1]), (O.FIELD_SHARP_CORNER, [0, 0, 0])] * 40  # 320 chunks > 148 SMs
+             (O.FIELD_TERRAIN_FBM, [2, -1, 1]), (O.FIELD_SHARP_CORNER, [0, 0, 0]), (O.FIELD_THIN_SLAB, [0, -1, 0]),
+             (O.FIELD_MATERIAL_SEAM, [0, -1, 0])] * 40  # 400 chunks > 148 SMs
     n = len(specs)
     batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=40_000, max_indices=60_000)
-    samples = np.concatenate([O.fixture_fill(k, p, edge=edge) for k, p in specs[:8]] * 40)
+    samples = np.concatenate([O.fixture_fill(k, p, edge=edge) for k, p in specs[:10]] * 40)
     masks = [(i * 7) % 64 for i in range(n)]
     gens = [100 + i for i in range(n)]
     batch.extract_regular(samples, n, generation=gens, transition_mask=masks)
@@ -204,9 +237,9 @@ def test_batch_of_mixed_chunks(edge):
     ranges = batch.ranges(n)
     wants = {}
     for i in range(n):
-        key = (i % 8, masks[i])
+        key = (i % 10, masks[i])
         if key not in wants:
-            wants[key] = O.extract_regular(samples[(i % 8) * (edge + 2) ** 3:(i % 8 + 1) * (edge + 2) ** 3], edge=edge,
+            wants[key] = O.extract_regular(samples[(i % 10) * (edge + 2) ** 3:(i % 10 + 1) * (edge + 2) ** 3], edge=edge,
                                            transition_mask=masks[i], debug=False)
         want = wants[key]
         assert counters["completed"][i] == 1 and counters["required_vertices"][i] == len(want.vertices), i
@@ -215,7 +248,7 @@ def test_batch_of_mixed_chunks(edge):
     # spot-check full meshes, and the packed readback of the whole batch
     verts, idx, packed = batch.ctx.read_meshes(0, 0, n)
     for i in list(range(0, n, 37)) + [n - 1]:
-        want = wants[(i % 8, masks[i])]
+        want = wants[(i % 10, masks[i])]
         r = packed[i]
         assert_vertices_equal(verts[r["first_vertex"]:r["first_vertex"] + r["vertex_count"]], want.vertices, f"chunk {i}")
         assert np.array_equal(idx[r["first_index"]:r["first_index"] + r["index_count"]], want.indices), i
@@ -226,12 +259,12 @@ def test_batch_of_mixed_chunks(edge):
 
 
 @pytest.mark.parametrize("edge,n,all_surface", [(64, 592, False), (32, 1184, False), (64, 1184, True), (32, 2368, True)])
-def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, n, all_surface, monkeypatch):
+def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, n, all_surface):
     """Race detector for the asynchronous (decoupled) kernel at a size where every SM walks several chunks.
 
     A terrain batch (surface and empty chunks mixed, random transition masks, a few partially dirty
     chunks) is extracted three times with the default kernel and once with the first-generation
-    kernel (CTA-wide barriers, HVX_REGULAR_VARIANT=1): counters, ranges and every mesh byte must be
+    kernel (CTA-wide barriers, a second context with HVX_CFG_FIRST_GENERATION): counters, ranges and every mesh byte must be
     identical, and a sample of chunks must equal the oracle.  ``all_surface`` puts every chunk on the
     surface layer: the emission warps are the bottleneck throughout, the work queue stays full and the
     front end is throttled by the slab ring -- the opposite regime of the headline batch.
@@ -249,10 +282,10 @@ def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, 
         dirty[i] = int(rng.integers(1, 1 << 62))
     gens = [1000 + i for i in range(n)]
 
-    def run():
-        batch.extract_regular(None, n, generation=gens, transition_mask=masks, dirty_microbricks=dirty)
-        c, r = batch.counters(n).copy(), batch.ranges(n).copy()
-        v, i, packed = batch.ctx.read_meshes(0, 0, n)
+    def run(b=batch):
+        b.extract_regular(None, n, generation=gens, transition_mask=masks, dirty_microbricks=dirty)
+        c, r = b.counters(n).copy(), b.ranges(n).copy()
+        v, i, packed = b.ctx.read_meshes(0, 0, n)
         return c, r, v.copy(), i.copy(), packed.copy()
 
     first = run()
@@ -262,9 +295,11 @@ def test_large_batch_is_deterministic_and_equal_across_kernel_generations(edge, 
         again = run()
         for a, b in zip(first, again):
             assert a.tobytes() == b.tobytes()
-    monkeypatch.setenv("HVX_REGULAR_VARIANT", "1")
-    old = run()
-    monkeypatch.delenv("HVX_REGULAR_VARIANT")
+    gen1 = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=batch.ctx.max_vertices,
+                                 max_indices=batch.ctx.max_indices, first_generation=True)
+    gen1.fill_density(O.FIELD_TERRAIN_FBM, pages)   # the same (deterministic) samples in its own arena
+    old = run(gen1)
+    gen1.close()
     for a, b in zip(first, old):
         assert a.tobytes() == b.tobytes()
     # a sample of chunks against the oracle (surface chunks included)
@@ -302,3 +337,13 @@ def test_cost_hints_change_the_start_order_and_nothing_else():
         for a, b in zip(plain, again):
             assert a.tobytes() == b.tobytes()
     batch.close()
+
+
+def test_edge_parameter_division_is_exact():
+    """The decoupled kernel's branch-free d0 / (d0 - d1): all 2^32 pairs of i16 densities, bit for bit against
+    the reference formula with IEEE division (hvx_selftest_edge_parameter)."""
+    import ctypes as C
+    bad, witness = C.c_uint64(123), C.c_uint32()
+    rc = H._ffi.load().hvx_selftest_edge_parameter(0, C.byref(bad), C.byref(witness))
+    assert rc == 0
+    assert bad.value == 0, f"{bad.value} operand pairs differ, e.g. d0={(witness.value >> 16) - 32768} d1={(witness.value & 0xffff) - 32768}"
