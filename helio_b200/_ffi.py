@@ -45,6 +45,7 @@ HVX_E_DEVICE_BUFFER_LIMIT = -49
 
 HVX_CFG_DEBUG_RECORDS = 1
 HVX_CFG_FIRST_GENERATION = 2
+HVX_CHUNK_UNIFORM = 1
 (XPUB_VERTICES, XPUB_INDICES, XPUB_PAGE_RANGES, XPUB_COUNTERS) = range(4)
 (BRICK_VERTICES, BRICK_NORMALS, BRICK_INDICES, BRICK_DESCRIPTORS, BRICK_DRAWS, BRICK_REJECTED) = range(6)
 (PUB_REGULAR_VERTICES, PUB_REGULAR_INDICES, PUB_TRANSITION_VERTICES, PUB_TRANSITION_INDICES, PUB_STATES, PUB_REGULAR_DRAWS,
@@ -66,7 +67,18 @@ class Config(C.Structure):
 
 class ChunkDesc(C.Structure):
     _fields_ = [("generation", C.c_uint64), ("dirty_microbricks", C.c_uint64), ("transition_mask", C.c_uint32),
-                ("cost_hint", C.c_uint32)]
+                ("cost_hint", C.c_uint32), ("flags", C.c_uint32), ("_reserved", C.c_uint32)]
+
+
+class VoxelEdit(C.Structure):
+    """GpuVoxelEdit (crates/helio-voxel-core/src/gpu_types.rs:47-54)."""
+    _fields_ = [("volume_id", C.c_uint32), ("op_type", C.c_uint32), ("material", C.c_uint32), ("center", C.c_float * 3),
+                ("radius", C.c_float), ("_pad", C.c_uint32)]
+
+
+class EmissionCounters(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("required_vertices", "required_indices", "emitted_vertices", "emitted_indices",
+                                          "vertex_overflow", "index_overflow", "completed", "_pad")]
 
 
 class Range(C.Structure):
@@ -158,8 +170,8 @@ class ExtractionPublisherCounters(C.Structure):
 # every symbol include/hvx.h declares; tests assert the library exports all of them
 EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
-    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_selftest_edge_parameter",
-    "hvx_fill_density", "hvx_fill_slabs", "hvx_extract_regular", "hvx_classify_regular", "hvx_extract_transition",
+    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_selftest_edge_parameter", "hvx_selftest_inv_sqrt",
+    "hvx_fill_density", "hvx_fill_slabs", "hvx_apply_edit", "hvx_extract_regular", "hvx_extract_regular_to_host", "hvx_classify_regular", "hvx_extract_transition",
     "hvx_build_meshlets", "hvx_gather_surface", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
     "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
     "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
@@ -209,10 +221,14 @@ def load() -> C.CDLL:
     L.hvx_launch_count.restype = C.c_uint64
     L.hvx_debug_set_mode.argtypes = [vp, C.c_uint32]
     L.hvx_selftest_edge_parameter.argtypes = [C.c_int, u64p, u32p]
+    L.hvx_selftest_inv_sqrt.argtypes = [C.c_int, u64p, u32p]
     L.hvx_fill_density.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
     L.hvx_fill_slabs.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
+    L.hvx_apply_edit.argtypes = [vp, C.POINTER(VoxelEdit), i64p, u8p, C.c_uint32, vp, u64p, u32p]
     L.hvx_extract_regular.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
     L.hvx_classify_regular.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
+    L.hvx_extract_regular_to_host.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32, vp, C.c_uint64, vp,
+                                              C.c_uint64, C.POINTER(Range), vp, u64p, u64p]
     L.hvx_extract_transition.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
     L.hvx_build_meshlets.argtypes = [vp, C.c_int, C.c_uint32]
     L.hvx_gather_surface.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint32]

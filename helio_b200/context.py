@@ -65,12 +65,14 @@ def _input_pointer(array, expected_dtype=np.uint32):
     return C.c_void_p(arr.ctypes.data), arr.size, arr
 
 
-_DESC_DTYPE = np.dtype([("generation", "<u8"), ("dirty_microbricks", "<u8"), ("transition_mask", "<u4"), ("cost_hint", "<u4")])
+_DESC_DTYPE = np.dtype([("generation", "<u8"), ("dirty_microbricks", "<u8"), ("transition_mask", "<u4"), ("cost_hint", "<u4"),
+                        ("flags", "<u4"), ("_reserved", "<u4")])
 
 
-def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask=0, cost_hint=0):
+def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask=0, cost_hint=0, flags=0):
     """ctypes array of ``hvx_chunk_desc``; scalar arguments broadcast, sequences are per chunk.  ``cost_hint``
-    (e.g. each chunk's vertex count last time) makes the batch start its heaviest chunks first."""
+    (e.g. each chunk's vertex count last time) makes the batch start its heaviest chunks first; ``flags``:
+    ``HVX_CHUNK_UNIFORM`` marks chunks the producer knows to hold no surface (not uploaded, not read)."""
     arr = np.zeros(max(n, 1), dtype=_DESC_DTYPE)
 
     def column(value, mask):
@@ -82,6 +84,7 @@ def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask
     arr["dirty_microbricks"][:n] = column(dirty_microbricks, (1 << 64) - 1)
     arr["transition_mask"][:n] = column(transition_mask, 0xFFFFFFFF)
     arr["cost_hint"][:n] = column(cost_hint, 0xFFFFFFFF)
+    arr["flags"][:n] = column(flags, 0xFFFFFFFF)
     descs = (_ffi.ChunkDesc * max(n, 1)).from_buffer(arr)
     descs._keepalive = arr
     return descs
@@ -210,6 +213,19 @@ class Context:
             kind="transition")
         return n
 
+    def apply_edit(self, op, center, radius, page_xyz, lod=None, material=1, samples_ptr=None):
+        """hvx_apply_edit: one AddSphere (op 1) / SubtractSphere (op 2) edit on the resident samples of the chunks at
+        ``page_xyz``.  Returns (dirty_microbricks [n] uint64, number of chunks whose samples changed)."""
+        pages, lods, n = self._pages(page_xyz, lod)
+        edit = _ffi.VoxelEdit(0, int(op), int(material), (C.c_float * 3)(*[float(c) for c in center]), float(radius), 0)
+        dirty = np.zeros(n, dtype=np.uint64)
+        touched = C.c_uint32()
+        self._check(self._lib.hvx_apply_edit(
+            self._handle, C.byref(edit), pages.ctypes.data_as(C.POINTER(C.c_int64)),
+            None if lods is None else lods.ctypes.data_as(C.POINTER(C.c_uint8)), n, C.c_void_p(samples_ptr or 0),
+            dirty.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(touched)))
+        return dirty, touched.value
+
     # -- K2-K4 --------------------------------------------------------------------------------
     def extract_regular(self, samples, descs, n, sample_words=None, classify_only=False):
         ptr, count, keep = _input_pointer(samples)
@@ -218,6 +234,35 @@ class Context:
         fn = self._lib.hvx_classify_regular if classify_only else self._lib.hvx_extract_regular
         self._check(fn(self._handle, ptr, int(sample_words), descs, n), kind="regular")
         del keep
+
+    def extract_regular_to_host(self, samples, descs, n, vertices_out=None, indices_out=None, vertex_cap=None, index_cap=None):
+        """hvx_extract_regular_to_host: pipelined upload -> extraction -> packed read-back in one call.
+
+        ``vertices_out`` / ``indices_out``: numpy arrays or pinned torch tensors (32-byte vertices / u32 indices);
+        if omitted they are allocated with ``vertex_cap`` / ``index_cap`` elements (default: the slot capacities).
+        Returns (vertices, indices, ranges, counters) -- with caller-owned tensors the first two are the totals."""
+        ptr, count, keep = _input_pointer(samples)
+        sample_words = n * self.sample_words if count is None else count
+        own = vertices_out is None or indices_out is None
+        if own:
+            vertices_out = np.empty(vertex_cap if vertex_cap is not None else n * self.max_vertices, dtype=VERTEX_DTYPE)
+            indices_out = np.empty(index_cap if index_cap is not None else n * self.max_indices, dtype=np.uint32)
+        torchy = hasattr(vertices_out, "data_ptr")
+        vptr = vertices_out.data_ptr() if torchy else vertices_out.ctypes.data
+        iptr = indices_out.data_ptr() if torchy else indices_out.ctypes.data
+        vcap = vertices_out.numel() * vertices_out.element_size() // 32 if torchy else vertices_out.size
+        icap = indices_out.numel() if torchy else indices_out.size
+        ranges = np.zeros(n, dtype=RANGE_DTYPE)
+        counters = np.zeros(n, dtype=EMISSION_COUNTERS_DTYPE)
+        tv, ti = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.hvx_extract_regular_to_host(
+            self._handle, ptr, int(sample_words), descs, n, C.c_void_p(vptr), vcap, C.c_void_p(iptr), icap,
+            ranges.ctypes.data_as(C.POINTER(_ffi.Range)), C.c_void_p(counters.ctypes.data), C.byref(tv), C.byref(ti)),
+            kind="regular")
+        del keep
+        if torchy:
+            return tv.value, ti.value, ranges, counters
+        return vertices_out[:tv.value], indices_out[:ti.value], ranges, counters
 
     def extract_transition(self, slabs, descs, n, slab_words=None):
         ptr, count, keep = _input_pointer(slabs)

@@ -7,6 +7,7 @@
 // Ownership follows the reference: the ctx owns every device buffer, the caller borrows inputs
 // for the duration of the call, outputs are overwritten by the next dispatch.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdlib>
@@ -28,6 +29,11 @@ struct hvx_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t handover = nullptr;   // orders a new stream after the old one (hvx_set_stream)
+    cudaStream_t copy_stream = nullptr;  // host-sample dispatches: uploads of sub-batch k+1 beside the kernel of sub-batch k
+    cudaStream_t d2h_stream = nullptr;   // hvx_extract_regular_to_host: pack + read-back behind the kernels
+    std::vector<cudaEvent_t> events;     // [2 * sub-batches]: upload done, kernel done
+    hvx_range* h_ranges = nullptr;       // pinned, [max_chunks]: ranges on their way to the host
+    uint32_t* d_uniform = nullptr;       // [max_chunks] chunks flagged HVX_CHUNK_UNIFORM
     void* buf[HVX_BUF_COUNT] = {};
     uint64_t buf_bytes[HVX_BUF_COUNT] = {};
     ChunkDesc* d_descs = nullptr;     // [max_chunks] descriptors of the last REGULAR dispatch
@@ -210,54 +216,261 @@ int check_batch(hvx_ctx* ctx, const void* descs, uint32_t n) {
     return HVX_OK;
 }
 
+bool is_device_pointer(hvx_ctx* ctx, const void* ptr, int* status) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged) return false;
+    if (reinterpret_cast<uintptr_t>(ptr) % 16 != 0)
+        *status = fail(ctx, HVX_E_INVALID_ARGUMENT, "device sample pointer must be 16-byte aligned");
+    else if (attr.type == cudaMemoryTypeDevice && attr.device != ctx->device)
+        *status = fail(ctx, HVX_E_INVALID_ARGUMENT, "sample pointer lives on device %d, ctx is on device %d", attr.device, ctx->device);
+    return true;
+}
+
+int ensure_pipeline(hvx_ctx* ctx, size_t events) {
+    if (!ctx->copy_stream) HVX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->d2h_stream) HVX_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+    while (ctx->events.size() < events) {
+        cudaEvent_t e = nullptr;
+        HVX_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    return HVX_OK;
+}
+
+// Packed host destination of a pipelined dispatch (hvx_extract_regular_to_host).
+struct HostMeshOut {
+    hvx_vertex* vertices;
+    uint64_t vertex_cap;
+    uint32_t* indices;
+    uint64_t index_cap;
+    hvx_range* ranges;
+    hvx_emission_counters* counters;
+    uint64_t total_vertices = 0, total_indices = 0;
+};
+
+int grow_device(hvx_ctx* ctx, void** ptr, uint64_t* have, uint64_t need, cudaStream_t user) {
+    if (*have >= need) return HVX_OK;
+    if (*ptr) {
+        HVX_CUDA(ctx, cudaStreamSynchronize(user));
+        cudaFree(*ptr);
+        ctx->allocated -= *have;
+        *ptr = nullptr;
+        *have = 0;
+    }
+    const uint64_t bytes = need + need / 4 + 4096;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(pack staging)");
+    *have = bytes;
+    ctx->allocated += bytes;
+    return HVX_OK;
+}
+
+// One regular dispatch over n chunks.
+//   * device-resident samples (or the ctx arena): one launch.
+//   * HOST samples: the batch is cut into sub-batches of ~256 MiB.  Sub-batch k is copied on the copy stream
+//     while sub-batch k-1 is extracted on the ctx stream (one event per hand-off), so the call costs the upload
+//     and one sub-batch of kernel time instead of upload + kernel.  Chunks flagged HVX_CHUNK_UNIFORM are neither
+//     uploaded nor walked; one small launch writes their (empty) records.
+//   * `out` (hvx_extract_regular_to_host): each sub-batch's ranges come back through pinned staging as soon as
+//     its kernel is done; this thread places the sub-batch in the packed output and queues pack + D2H on a third
+//     stream, so the read-back of sub-batch k overlaps the upload of k+2 and the kernel of k+1.
 int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n,
-                uint32_t mode) {
+                uint32_t mode, HostMeshOut* out = nullptr) {
     int rc = check_batch(ctx, descs, n);
     if (rc) return rc;
-    const uint64_t expected = static_cast<uint64_t>(n) * sample_words(ctx->cfg.edge);
+    const uint64_t chunk_words = sample_words(ctx->cfg.edge);
+    const uint64_t expected = static_cast<uint64_t>(n) * chunk_words;
     if (words != expected)
         return fail(ctx, HVX_E_SAMPLE_COUNT, "Transvoxel classification received %llu samples; expected %llu",
                     static_cast<unsigned long long>(words), static_cast<unsigned long long>(expected));
     if (n == 0) return HVX_OK;
+    for (uint32_t i = 0; i < n; ++i)
+        if (descs[i].flags & ~HVX_CHUNK_UNIFORM) return fail(ctx, HVX_E_INVALID_ARGUMENT, "chunk %u: unknown descriptor flags %#x", i, descs[i].flags);
     DeviceGuard guard(ctx->device);
+
+    // ---- where the samples are -----------------------------------------------------------------------------
     const uint32_t* d_samples = nullptr;
-    if ((rc = resolve_input(ctx, samples, words, HVX_BUF_SAMPLES, &d_samples))) return rc;
+    bool from_host = false;
+    if (samples == nullptr) {
+        if ((rc = ensure_buffer(ctx, HVX_BUF_SAMPLES))) return rc;
+        d_samples = static_cast<const uint32_t*>(ctx->buf[HVX_BUF_SAMPLES]);
+    } else {
+        int status = HVX_OK;
+        if (is_device_pointer(ctx, samples, &status)) {
+            if (status) return status;
+            d_samples = samples;
+        } else {
+            if ((rc = ensure_buffer(ctx, HVX_BUF_SAMPLES))) return rc;
+            d_samples = static_cast<const uint32_t*>(ctx->buf[HVX_BUF_SAMPLES]);
+            from_host = true;
+        }
+    }
+
+    // ---- sub-batches, work lists (heaviest first, uniform chunks left out) -----------------------------------
+    const uint32_t sub = from_host ? static_cast<uint32_t>(std::max<uint64_t>(1, (256ull << 20) / (chunk_words * 4))) : n;
+    const uint32_t n_sub = (n + sub - 1) / sub;
+    if ((from_host || out) && (rc = ensure_pipeline(ctx, 2ull * n_sub))) return rc;
+    bool hinted = false, any_uniform = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        hinted |= descs[i].cost_hint != 0u;
+        any_uniform |= (descs[i].flags & HVX_CHUNK_UNIFORM) != 0u;
+    }
+    std::vector<uint32_t> order, uniform, n_work(n_sub);
+    if (hinted || any_uniform) order.resize(n);
+    for (uint32_t k = 0; k < n_sub; ++k) {
+        const uint32_t first = k * sub, count = std::min(sub, n - first);
+        if (order.empty()) {
+            n_work[k] = count;
+            continue;
+        }
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < count; ++i) {
+            if (descs[first + i].flags & HVX_CHUNK_UNIFORM) uniform.push_back(first + i);
+            else order[first + m++] = i;  // ids are relative to the sub-batch
+        }
+        n_work[k] = m;
+        // descending hint, ties in chunk order (the scheduler's LPT rule)
+        if (hinted)
+            std::stable_sort(order.begin() + first, order.begin() + first + m,
+                             [&](uint32_t a, uint32_t b) { return descs[first + a].cost_hint > descs[first + b].cost_hint; });
+    }
     if ((rc = upload_descs(ctx, ctx->d_descs, descs, n))) return rc;
     ctx->n_regular = n;
-    RegularParams p{};
-    p.samples = d_samples;
-    p.descs = ctx->d_descs;
-    p.n_chunks = n;
-    p.mode = mode;
-    for (uint32_t i = 0; i < n && !p.any_partial; ++i) p.any_partial = descs[i].dirty_microbricks != ~0ull;
-    // cost hints -> start order: descending hint, ties in chunk order (the scheduler's LPT rule)
-    bool hinted = false;
-    for (uint32_t i = 0; i < n && !hinted; ++i) hinted = descs[i].cost_hint != 0u;
-    if (hinted) {
-        std::vector<uint32_t> order(n);
-        for (uint32_t i = 0; i < n; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return descs[a].cost_hint > descs[b].cost_hint; });
-        // pageable source: cudaMemcpyAsync returns once it is staged, so the temporary may go out of scope
+    // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope
+    if (!order.empty())
         HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, order.data(), static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        p.order = ctx->d_order;
+
+    RegularParams base{};
+    base.mode = mode;
+    if (ctx->debug_mode == 1) base.mode = MODE_STREAM_ONLY;  // hvx_debug_set_mode: roofline probes, no compute
+    else if (ctx->debug_mode == 2) base.mode = MODE_BITS_ONLY;
+    base.first_generation = (ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) ? 1u : 0u;
+    base.max_vertices = ctx->cfg.max_vertices;
+    base.max_indices = ctx->cfg.max_indices;
+    base.work_counter = ctx->d_work;
+    const uint64_t cell_count = cells(ctx->cfg.edge);
+    auto* const all_vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);
+    auto* const all_indices = static_cast<uint32_t*>(ctx->buf[HVX_BUF_REGULAR_INDICES]);
+    auto* const all_counters = static_cast<hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
+    auto* const all_classify = static_cast<hvx_classify_counters*>(ctx->buf[HVX_BUF_REGULAR_CLASSIFY]);
+    auto* const all_ranges = static_cast<hvx_range*>(ctx->buf[HVX_BUF_REGULAR_RANGES]);
+    auto* const all_cells = static_cast<hvx_cell_record*>(ctx->buf[HVX_BUF_REGULAR_CELLS]);
+    auto* const all_offsets = static_cast<hvx_cell_offset*>(ctx->buf[HVX_BUF_REGULAR_OFFSETS]);
+    auto* const all_blocks = static_cast<hvx_scan_block*>(ctx->buf[HVX_BUF_REGULAR_BLOCKS]);
+
+    if (out && !ctx->h_ranges) {
+        HVX_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_ranges), static_cast<size_t>(ctx->cfg.max_chunks) * sizeof(hvx_range), cudaHostAllocDefault));
     }
-    if (ctx->debug_mode == 1) p.mode = MODE_STREAM_ONLY;  // hvx_debug_set_mode: roofline probes, no compute
-    else if (ctx->debug_mode == 2) p.mode = MODE_BITS_ONLY;
-    p.first_generation = (ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) ? 1u : 0u;
-    p.max_vertices = ctx->cfg.max_vertices;
-    p.max_indices = ctx->cfg.max_indices;
-    p.vertices = static_cast<hvx_vertex*>(ctx->buf[HVX_BUF_REGULAR_VERTICES]);
-    p.indices = static_cast<uint32_t*>(ctx->buf[HVX_BUF_REGULAR_INDICES]);
-    p.counters = static_cast<hvx_emission_counters*>(ctx->buf[HVX_BUF_REGULAR_COUNTERS]);
-    p.classify = static_cast<hvx_classify_counters*>(ctx->buf[HVX_BUF_REGULAR_CLASSIFY]);
-    p.ranges = static_cast<hvx_range*>(ctx->buf[HVX_BUF_REGULAR_RANGES]);
-    p.cells = static_cast<hvx_cell_record*>(ctx->buf[HVX_BUF_REGULAR_CELLS]);
-    p.offsets = static_cast<hvx_cell_offset*>(ctx->buf[HVX_BUF_REGULAR_OFFSETS]);
-    p.blocks = static_cast<hvx_scan_block*>(ctx->buf[HVX_BUF_REGULAR_BLOCKS]);
-    p.work_counter = ctx->d_work;
-    cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
-    ctx->launches += (p.cells != nullptr && !p.first_generation) ? 3 : 1;  // + the two record kernels
+    if (from_host) {
+        // the arena may still be read by work queued earlier on the ctx stream
+        HVX_CUDA(ctx, cudaEventRecord(ctx->handover, ctx->stream));
+        HVX_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->handover, 0));
+    }
+    for (uint32_t k = 0; k < n_sub; ++k) {
+        const uint32_t first = k * sub, count = std::min(sub, n - first);
+        if (from_host) {
+            // runs of consecutive chunks that are not flagged uniform, one copy each
+            uint32_t i = 0;
+            while (i < count) {
+                while (i < count && (descs[first + i].flags & HVX_CHUNK_UNIFORM)) ++i;
+                uint32_t j = i;
+                while (j < count && !(descs[first + j].flags & HVX_CHUNK_UNIFORM)) ++j;
+                if (j > i) {
+                    const uint64_t off = (static_cast<uint64_t>(first) + i) * chunk_words;
+                    HVX_CUDA(ctx, cudaMemcpyAsync(static_cast<uint32_t*>(ctx->buf[HVX_BUF_SAMPLES]) + off, samples + off,
+                                                  static_cast<uint64_t>(j - i) * chunk_words * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+                }
+                i = j;
+            }
+            HVX_CUDA(ctx, cudaEventRecord(ctx->events[2 * k], ctx->copy_stream));
+            HVX_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->events[2 * k], 0));
+        }
+        RegularParams p = base;
+        p.samples = d_samples + static_cast<uint64_t>(first) * chunk_words;
+        p.descs = ctx->d_descs + first;
+        p.order = order.empty() ? nullptr : ctx->d_order + first;
+        p.n_chunks = count;
+        p.n_work = n_work[k];
+        p.chunk_base = first;
+        for (uint32_t i = 0; i < count && !p.any_partial; ++i)
+            p.any_partial = descs[first + i].dirty_microbricks != ~0ull && !(descs[first + i].flags & HVX_CHUNK_UNIFORM);
+        p.vertices = all_vertices + static_cast<uint64_t>(first) * ctx->cfg.max_vertices;
+        p.indices = all_indices + static_cast<uint64_t>(first) * ctx->cfg.max_indices;
+        p.counters = all_counters + first;
+        p.classify = all_classify + first;
+        p.ranges = all_ranges + first;
+        p.cells = all_cells ? all_cells + static_cast<uint64_t>(first) * cell_count : nullptr;
+        p.offsets = all_offsets ? all_offsets + static_cast<uint64_t>(first) * cell_count : nullptr;
+        p.blocks = all_blocks ? all_blocks + static_cast<uint64_t>(first) * (cell_count / 256) : nullptr;
+        if (p.n_work != 0) {
+            cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
+            ctx->launches += (p.cells != nullptr && !p.first_generation) ? 3 : 1;  // + the two record kernels
+        }
+        if (k + 1 == n_sub && !uniform.empty()) {
+            HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_uniform, uniform.data(), uniform.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+            RegularParams q = base;
+            q.descs = ctx->d_descs;
+            q.counters = all_counters;
+            q.classify = all_classify;
+            q.ranges = all_ranges;
+            cudaError_t e = launch_uniform_records(static_cast<int>(ctx->cfg.edge), q, ctx->d_uniform, static_cast<uint32_t>(uniform.size()), ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_uniform_records");
+            ctx->launches += 1;
+        }
+        if (out) {
+            HVX_CUDA(ctx, cudaMemcpyAsync(ctx->h_ranges + first, all_ranges + first, static_cast<size_t>(count) * sizeof(hvx_range),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            HVX_CUDA(ctx, cudaEventRecord(ctx->events[2 * k + 1], ctx->stream));
+        }
+    }
+    if (!out) return HVX_OK;
+
+    // ---- packed read-back, sub-batch by sub-batch, behind the kernels ------------------------------------------
+    uint64_t tv = 0, ti = 0;
+    bool fits = true;
+    std::vector<hvx_range> local(std::min(sub, n));
+    for (uint32_t k = 0; k < n_sub; ++k) {
+        const uint32_t first = k * sub, count = std::min(sub, n - first);
+        HVX_CUDA(ctx, cudaEventSynchronize(ctx->events[2 * k + 1]));
+        uint64_t sv = 0, si = 0;
+        for (uint32_t i = 0; i < count; ++i) {
+            const hvx_range r = ctx->h_ranges[first + i];
+            out->ranges[first + i] = {static_cast<uint32_t>(tv + sv), r.vertex_count, static_cast<uint32_t>(ti + si), r.index_count};
+            local[i] = {static_cast<uint32_t>(sv), r.vertex_count, static_cast<uint32_t>(si), r.index_count};
+            sv += r.vertex_count;
+            si += r.index_count;
+        }
+        fits = fits && tv + sv <= out->vertex_cap && ti + si <= out->index_cap && tv + sv <= 0xffffffffull && ti + si <= 0xffffffffull &&
+               (sv == 0 || out->vertices) && (si == 0 || out->indices);
+        if (fits && (sv || si)) {
+            if ((rc = grow_device(ctx, &ctx->pack_v, &ctx->pack_v_bytes, sv * sizeof(hvx_vertex), ctx->d2h_stream))) return rc;
+            if ((rc = grow_device(ctx, &ctx->pack_i, &ctx->pack_i_bytes, si * 4, ctx->d2h_stream))) return rc;
+            HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_packed + first, local.data(), static_cast<size_t>(count) * sizeof(hvx_range), cudaMemcpyHostToDevice, ctx->d2h_stream));
+            cudaError_t e = launch_pack(all_vertices, all_indices, all_ranges + first, ctx->d_packed + first, count,
+                                        static_cast<hvx_vertex*>(ctx->pack_v), static_cast<uint32_t*>(ctx->pack_i), ctx->dev, ctx->d2h_stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_pack");
+            ctx->launches += 1;
+            if (sv) HVX_CUDA(ctx, cudaMemcpyAsync(out->vertices + tv, ctx->pack_v, sv * sizeof(hvx_vertex), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            if (si) HVX_CUDA(ctx, cudaMemcpyAsync(out->indices + ti, ctx->pack_i, si * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+        }
+        tv += sv;
+        ti += si;
+    }
+    // every kernel of the dispatch has finished (the last event was waited for)
+    if (out->counters)
+        HVX_CUDA(ctx, cudaMemcpyAsync(out->counters, all_counters, static_cast<size_t>(n) * sizeof(hvx_emission_counters), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+    out->total_vertices = tv;
+    out->total_indices = ti;
+    if (tv > 0xffffffffull || ti > 0xffffffffull) return fail(ctx, HVX_E_DEVICE_LIMIT, "DeviceLimit: packed mesh exceeds 32-bit ranges");
+    if (!fits)
+        return fail(ctx, HVX_E_INVALID_CAPACITY, "output capacity too small: need %llu vertices / %llu indices",
+                    static_cast<unsigned long long>(tv), static_cast<unsigned long long>(ti));
     return HVX_OK;
 }
 
@@ -468,6 +681,7 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((rc = small_alloc(ctx, &ctx->d_descs, c.max_chunks))) return bail(rc);
     if (c.max_transition_vertices != 0 && (rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_order, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_uniform, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_index, c.max_chunks))) return bail(rc);
@@ -502,6 +716,13 @@ void hvx_destroy(hvx_ctx* ctx) {
     cudaFree(ctx->d_packed);
     cudaFree(ctx->pack_v);
     cudaFree(ctx->pack_i);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+    cudaFree(ctx->d_uniform);
+    if (ctx->h_ranges) cudaFreeHost(ctx->h_ranges);
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->handover) cudaEventDestroy(ctx->handover);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -555,12 +776,104 @@ int hvx_fill_slabs(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const u
     return run_fill(ctx, kind, page_xyz, lod, n, d_slabs, true);
 }
 
+int hvx_apply_edit(hvx_ctx* ctx, const hvx_voxel_edit* edit, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
+                   uint32_t* d_samples, uint64_t* dirty_out, uint32_t* touched_out) {
+    static_assert(sizeof(hvx_voxel_edit) == 32, "GpuVoxelEdit layout");
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (touched_out) *touched_out = 0;
+    if (!edit || (n != 0 && (!page_xyz || !dirty_out))) return fail(ctx, HVX_E_INVALID_ARGUMENT, "hvx_apply_edit: NULL argument");
+    if (n > ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
+    if (edit->op_type != 1u && edit->op_type != 2u)
+        return fail(ctx, HVX_E_INVALID_ARGUMENT, "edit op %u is not a sphere edit (1 AddSphere, 2 SubtractSphere)", edit->op_type);
+    if (!(edit->radius > 0.0f) || !std::isfinite(edit->radius) || !std::isfinite(edit->center[0]) ||
+        !std::isfinite(edit->center[1]) || !std::isfinite(edit->center[2]))
+        return fail(ctx, HVX_E_INVALID_ARGUMENT, "edit centre and radius must be finite, radius positive");
+    if (n == 0) return HVX_OK;
+    int rc = validate_pages(ctx, page_xyz, lod, n, false);
+    if (rc) return rc;
+    // the octree rule (octree.rs:139-173), in float like the reference: a box is untouched when the centre is further
+    // from the box centre than half the box plus the radius on any axis
+    const int E = static_cast<int>(ctx->cfg.edge), Q = E / 4;
+    auto overlaps = [&](const float lo[3], const float hi[3], float r) {
+        for (int a = 0; a < 3; ++a) {
+            const float c = (lo[a] + hi[a]) * 0.5f, h = (hi[a] - lo[a]) * 0.5f;
+            if (std::fabs(edit->center[a] - c) > h + r) return false;
+        }
+        return true;
+    };
+    std::vector<uint32_t> touched;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t l = lod ? lod[i] : 0;
+        const float cell_m = 0.1f * static_cast<float>(1ull << (l > 30 ? 30 : l));
+        float lo[3], hi[3];
+        for (int a = 0; a < 3; ++a) {  // the sample block, halo included
+            lo[a] = static_cast<float>(page_xyz[3 * i + a] * E - 1) * cell_m;
+            hi[a] = static_cast<float>(page_xyz[3 * i + a] * E + E) * cell_m;
+        }
+        dirty_out[i] = 0;
+        if (!overlaps(lo, hi, edit->radius)) continue;
+        touched.push_back(i);
+        const float reach = edit->radius + 2.0f * cell_m;
+        uint64_t bits = 0;
+        for (int mz = 0; mz < 4; ++mz)
+            for (int my = 0; my < 4; ++my)
+                for (int mx = 0; mx < 4; ++mx) {
+                    const int m[3] = {mx, my, mz};
+                    for (int a = 0; a < 3; ++a) {
+                        lo[a] = static_cast<float>(page_xyz[3 * i + a] * E + m[a] * Q) * cell_m;
+                        hi[a] = static_cast<float>(page_xyz[3 * i + a] * E + (m[a] + 1) * Q) * cell_m;
+                    }
+                    if (overlaps(lo, hi, reach)) bits |= 1ull << (mx + 4 * my + 16 * mz);
+                }
+        dirty_out[i] = bits;
+    }
+    if (touched_out) *touched_out = static_cast<uint32_t>(touched.size());
+    if (touched.empty()) return HVX_OK;
+    DeviceGuard guard(ctx->device);
+    if (!d_samples) {
+        if ((rc = ensure_buffer(ctx, HVX_BUF_SAMPLES))) return rc;
+        d_samples = static_cast<uint32_t*>(ctx->buf[HVX_BUF_SAMPLES]);
+    }
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pages, page_xyz, static_cast<size_t>(n) * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (lod) HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_lod, lod, n, cudaMemcpyHostToDevice, ctx->stream));
+    else HVX_CUDA(ctx, cudaMemsetAsync(ctx->d_lod, 0, n, ctx->stream));
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_uniform, touched.data(), touched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    EditParams p{};
+    p.op = edit->op_type;
+    p.material = edit->material;
+    for (int a = 0; a < 3; ++a) p.center[a] = edit->center[a];
+    p.radius = edit->radius;
+    p.n_touched = static_cast<uint32_t>(touched.size());
+    p.ids = ctx->d_uniform;
+    p.page_xyz = ctx->d_pages;
+    p.lod = ctx->d_lod;
+    p.samples = d_samples;
+    cudaError_t e = launch_edit_sphere(E, p, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_edit_sphere");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
 int hvx_extract_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n) {
     return run_regular(ctx, samples, words, descs, n, MODE_EXTRACT);
 }
 
 int hvx_classify_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n) {
     return run_regular(ctx, samples, words, descs, n, MODE_CLASSIFY);
+}
+
+int hvx_extract_regular_to_host(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx_chunk_desc* descs, uint32_t n,
+                                hvx_vertex* vertices_out, uint64_t vertex_cap, uint32_t* indices_out, uint64_t index_cap,
+                                hvx_range* ranges_out, hvx_emission_counters* counters_out, uint64_t* total_vertices,
+                                uint64_t* total_indices) {
+    if (total_vertices) *total_vertices = 0;
+    if (total_indices) *total_indices = 0;
+    if (ctx && n != 0 && !ranges_out) return fail(ctx, HVX_E_INVALID_ARGUMENT, "ranges_out is NULL");
+    HostMeshOut out{vertices_out, vertex_cap, indices_out, index_cap, ranges_out, counters_out};
+    const int rc = run_regular(ctx, samples, words, descs, n, MODE_EXTRACT, &out);
+    if (total_vertices) *total_vertices = out.total_vertices;
+    if (total_indices) *total_indices = out.total_indices;
+    return rc;
 }
 
 int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t words, const hvx_chunk_desc* descs, uint32_t n) {

@@ -14,6 +14,8 @@ struct ChunkDesc {
     uint64_t dirty_microbricks;
     uint32_t transition_mask;
     uint32_t cost_hint;
+    uint32_t flags;
+    uint32_t _reserved;
 };
 
 enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1, MODE_STREAM_ONLY = 2, MODE_BITS_ONLY = 3 };
@@ -21,8 +23,12 @@ enum : uint32_t { MODE_EXTRACT = 0, MODE_CLASSIFY = 1, MODE_STREAM_ONLY = 2, MOD
 struct RegularParams {
     const uint32_t* samples;  // [n][(E+2)^3]
     const ChunkDesc* descs;   // [n] device
-    const uint32_t* order;    // nullable, [n] device: the k-th chunk to start (descending cost hints)
-    uint32_t n_chunks;
+    const uint32_t* order;    // nullable, [n_work] device: the k-th chunk to start (descending cost hints; chunks flagged
+                              // uniform are left out)
+    uint32_t n_chunks;        // chunks addressed by this launch (ids are < n_chunks)
+    uint32_t n_work;          // chunks it actually walks (== n_chunks when order is NULL)
+    uint32_t chunk_base;      // batch index of this launch's chunk 0 (a sub-batch of a pipelined dispatch); every pointer
+                              // below is already offset, only the ranges record absolute slots
     uint32_t mode;
     uint32_t debug_flags;  // diagnostics: bit 0 disables the classification fast-reject
     uint32_t any_partial;  // some chunk of the batch is partially dirty (picks the slab-skipping instantiation)
@@ -64,6 +70,18 @@ struct FillParams {
     // columns, heights[col][(E+2)][(E+2)], and each chunk's column; NULL = compute per chunk
     const float* heights;
     const uint32_t* col_index;
+};
+
+struct EditParams {
+    uint32_t op;              // 1 AddSphere, 2 SubtractSphere (GpuVoxelEdit::op_type)
+    uint32_t material;
+    float center[3];          // metres
+    float radius;             // metres
+    uint32_t n_touched;
+    const uint32_t* ids;      // [n_touched] device: chunks whose sample block meets the sphere
+    const int64_t* page_xyz;  // [n][3] device
+    const uint8_t* lod;       // [n] device
+    uint32_t* samples;        // [n][(E+2)^3]
 };
 
 struct GatherParams {
@@ -166,8 +184,11 @@ struct DeviceInfo {
 cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream);
 // per-cell records, block-relative offsets and scan blocks (HVX_CFG_DEBUG_RECORDS), after the extraction
 cudaError_t launch_regular_records(int edge, const RegularParams& p, cudaStream_t stream);
+// empty, completed records for chunks flagged HVX_CHUNK_UNIFORM (ids = batch indices)
+cudaError_t launch_uniform_records(int edge, const RegularParams& p, const uint32_t* ids, uint32_t n, cudaStream_t stream);
 cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_samples(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_edit_sphere(int edge, const EditParams& p, cudaStream_t stream);
 cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_terrain_heights(int edge, const long long* col_xz, const uint8_t* col_lod, uint32_t n_cols, float* heights,
                                    cudaStream_t stream);

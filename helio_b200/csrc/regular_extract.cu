@@ -348,7 +348,8 @@ __global__ void __launch_bounds__(C::NT_ALL, C::E == 32 ? 2 : 1) regular_extract
             int slot = 0;
             uint32_t round = 0;  // how many times the ring has wrapped
             for (uint32_t k = 0;; ++k) {
-                const uint32_t id = atomicAdd(p.work_counter, 1u);
+                const uint32_t ticket = atomicAdd(p.work_counter, 1u);
+                const uint32_t id = ticket < p.n_work ? (p.order != nullptr ? p.order[ticket] : ticket) : 0xffffffffu;
                 // chunk_ids[k & 3] was last read for local chunk k - 4, long retired (RS < NSLAB)
                 sm.chunk_ids[k & 3] = id;
                 if (id >= p.n_chunks) {
@@ -722,9 +723,9 @@ __global__ void __launch_bounds__(C::NT_ALL, C::E == 32 ? 2 : 1) regular_extract
             cc.triangles = i_base / 3u;
             p.classify[chunk] = cc;
             hvx_range rg;
-            rg.first_vertex = chunk * p.max_vertices;
+            rg.first_vertex = (p.chunk_base + chunk) * p.max_vertices;
             rg.vertex_count = ok ? v_base : 0u;
-            rg.first_index = chunk * p.max_indices;
+            rg.first_index = (p.chunk_base + chunk) * p.max_indices;
             rg.index_count = ok ? i_base : 0u;
             p.ranges[chunk] = rg;
         }
@@ -971,8 +972,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             uint32_t round = 0;
             for (uint32_t k = 0;; ++k) {
                 const uint32_t ticket = atomicAdd(p.work_counter, 1u);
-                // heaviest chunks first when the caller supplied cost hints (a chunk's slot does not depend on when it runs)
-                const uint32_t id = (ticket < p.n_chunks && p.order != nullptr) ? p.order[ticket] : ticket;
+                // the work list: every chunk in index order, or the caller's list -- heaviest chunks first when the batch
+                // carries cost hints, chunks flagged uniform left out (a chunk's slot does not depend on when it runs)
+                const uint32_t id = ticket < p.n_work ? (p.order != nullptr ? p.order[ticket] : ticket) : 0xffffffffu;
                 sm.chunk_ids[k & 3] = id;
                 if (id >= p.n_chunks) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
@@ -1231,9 +1233,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 cc.triangles = i_tot / 3u;
                 p.classify[chunk] = cc;
                 hvx_range rg;
-                rg.first_vertex = chunk * p.max_vertices;
+                rg.first_vertex = (p.chunk_base + chunk) * p.max_vertices;
                 rg.vertex_count = ok ? v_tot : 0u;
-                rg.first_index = chunk * p.max_indices;
+                rg.first_index = (p.chunk_base + chunk) * p.max_indices;
                 rg.index_count = ok ? i_tot : 0u;
                 p.ranges[chunk] = rg;
             }
@@ -1247,7 +1249,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             // "are there tiles left" must be ONE decision per warp: the counter moves while the lanes look at it, and
             // a warp whose lanes disagreed would meet itself in the collectives below from two different entries
             // (lane 0 reads, the shuffle makes the warp converge and agree)
-#ifdef HVX_LEGACY_PROTOCOL  // stress builds: the round-1 form (every lane reads for itself)
+#if defined(HVX_LEGACY_PROTOCOL) || defined(HVX_LEGACY_LANE_READ)  // stress builds: the round-1 form (every lane reads for itself)
             const uint32_t pulled = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]);
 #else
             uint32_t pulled = 0;
@@ -1342,7 +1344,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     // tiles -- tile q can only overwrite word q & 31 after tile q - 31 has read tile q - 32's totals.
                     HVX_JIT(4);
                     uint64_t base = 0;
-#ifdef HVX_LEGACY_PROTOCOL  // stress builds: the round-1 form (a chunk's first tile does not wait)
+#if defined(HVX_LEGACY_PROTOCOL) || defined(HVX_LEGACY_FIRST_TILE)  // stress builds: the round-1 form (a chunk's first tile does not wait)
                     if (!first)
 #endif
                     {
@@ -1399,7 +1401,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             if (on && v_base + v < p.max_vertices) {
                                 const int x = cr & 63, rw = (cr >> 8) & 255;
                                 const int zl = rw / E, y = rw % E;
+#ifdef HVX_SELFCHECK  // a broken invariant is logged above; stay inside the table so the log can be read
+                                const uint32_t code = sm.vertex_packed[min((cvv >> 9) + (v - (cvv & 511u)), 1535u)];
+#else
                                 const uint32_t code = sm.vertex_packed[(cvv >> 9) + (v - (cvv & 511u))];
+#endif
                                 emit_regular_vertex_fast<C>(ring_flat, wl, x, y, zl, z0 + zl, code, tmask, out_v + v_base + v);
                             }
                         }
@@ -1440,7 +1446,7 @@ cudaError_t launch_persistent(Kernel* kernel, int* ctas_cache, int threads, size
         if (dev.ordinal >= 0 && dev.ordinal < 64) __atomic_store_n(&ctas_cache[dev.ordinal], ctas_per_sm, __ATOMIC_RELEASE);
     }
     const uint32_t grid = static_cast<uint32_t>(
-        min(static_cast<long long>(p.n_chunks), static_cast<long long>(dev.sm_count) * ctas_per_sm));
+        min(static_cast<long long>(p.n_work), static_cast<long long>(dev.sm_count) * ctas_per_sm));
     kernel<<<grid, threads, smem, stream>>>(p);
     return cudaGetLastError();
 }
@@ -1468,7 +1474,7 @@ size_t regular_smem_bytes(int edge) {
 }
 
 cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
-    if (p.n_chunks == 0) return cudaSuccess;
+    if (p.n_chunks == 0 || p.n_work == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
     if (e != cudaSuccess) return e;
     // The decoupled kernel is the product.  The first-generation kernel (CTA-wide barriers; writes the debug records

@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) cell_records_kernel(const RegularParams p
     const ChunkDesc desc = p.descs[chunk];
     const uint32_t lin = block * 256u + static_cast<uint32_t>(tid);
     const int x = lin % E, y = (lin / E) % E, z = lin / (E * E);
-    const bool visited = (desc.dirty_microbricks >> ((x / QW) + 4 * (y / QW) + 16 * (z / QW))) & 1ull;
+    // a chunk flagged uniform was not uploaded: its cells keep their old records, its blocks report nothing
+    const bool visited = ((desc.dirty_microbricks >> ((x / QW) + 4 * (y / QW) + 16 * (z / QW))) & 1ull) && !(desc.flags & HVX_CHUNK_UNIFORM);
     uint32_t c = 0, nv = 0, nt = 0, cls = 0;
     if (visited) {
         const uint32_t* s0 = p.samples + static_cast<size_t>(chunk) * S * S * S + (static_cast<size_t>(z + 1) * S + (y + 1)) * S + (x + 1);
@@ -87,7 +88,31 @@ __global__ void __launch_bounds__(256) block_prefix_kernel(const RegularParams p
         }
 }
 
+// chunks the caller flagged HVX_CHUNK_UNIFORM: nothing was read, the slot reports an empty, completed mesh
+__global__ void __launch_bounds__(128) uniform_records_kernel(const RegularParams p, const uint32_t* __restrict__ ids, uint32_t n, uint32_t microbrick_cells) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t chunk = ids[i];
+    hvx_emission_counters ec{};
+    ec.completed = 1u;
+    p.counters[chunk] = ec;
+    hvx_classify_counters cc{};
+    cc.visited_cells = static_cast<uint32_t>(__popcll(p.descs[chunk].dirty_microbricks)) * microbrick_cells;
+    p.classify[chunk] = cc;
+    hvx_range rg{};
+    rg.first_vertex = chunk * p.max_vertices;
+    rg.first_index = chunk * p.max_indices;
+    p.ranges[chunk] = rg;
+}
+
 }  // namespace
+
+cudaError_t launch_uniform_records(int edge, const RegularParams& p, const uint32_t* ids, uint32_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const uint32_t q = static_cast<uint32_t>(edge) / 4u;
+    uniform_records_kernel<<<(n + 127u) / 128u, 128, 0, stream>>>(p, ids, n, q * q * q);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_regular_records(int edge, const RegularParams& p, cudaStream_t stream) {
     if (p.n_chunks == 0 || p.cells == nullptr) return cudaSuccess;

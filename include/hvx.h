@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HVX_ABI_VERSION 1u
+#define HVX_ABI_VERSION 2u /* 2: hvx_chunk_desc grew flags (32 bytes) */
 
 /* Errors.  -1..-4 mirror PV/src/transvoxel_gpu.rs:445-459 TransvoxelGpuError and
  * PV/src/transvoxel_transition_gpu.rs:712-732 TransvoxelTransitionGpuError. */
@@ -155,7 +155,16 @@ typedef struct {
                                    count at its last extraction.  When any chunk of a batch carries a hint, the
                                    batch is STARTED in descending hint order (longest first, so the kernel does not
                                    end on a lone heavy chunk); slots, ranges and meshes do not depend on it. */
+    uint32_t flags;             /* HVX_CHUNK_* */
+    uint32_t _reserved;
 } hvx_chunk_desc;
+
+/* The producer of the samples knows this chunk holds no surface (e.g. an octree node that is all air or all rock:
+ * every sample has the same sign).  Its samples are then neither uploaded (host input) nor read (device input): the
+ * chunk's slot reports an empty, completed mesh.  For host input its part of the sample array need not be
+ * populated.  A flag on a chunk that does cross the surface makes that chunk's mesh silently empty -- the caller's
+ * contract, like the dirty mask. */
+#define HVX_CHUNK_UNIFORM 1u
 
 /* PV/src/transvoxel_emit.rs:57-85 TransvoxelGpuExtractorConfig +
  * PV/src/transvoxel_transition_gpu.rs:154-181, widened to a batch of chunks. */
@@ -204,6 +213,9 @@ int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode);
  * with __fdiv_rn; *mismatches_out = pairs whose result bits differ (must be 0), *witness_out = (d0+32768)<<16 | (d1+32768)
  * of one of them. */
 int hvx_selftest_edge_parameter(int device, uint64_t* mismatches_out, uint32_t* witness_out);
+/* Same for the normal's 1 / sqrt(s) (inv_sqrt_rn_normal against IEEE sqrt then divide): every float s from 1e-12 (the
+ * kernel's guard) to 2^40 (s is a sum of three squared i16 differences, < 2^35).  *witness_out = bits of one bad s. */
+int hvx_selftest_inv_sqrt(int device, uint64_t* mismatches_out, uint32_t* witness_out);
 
 /* ---- K1: density / SDF fill -------------------------------------------------------- */
 /* ExtractionFixture::new (PV/src/fixture.rs:95-124) on the device.
@@ -218,6 +230,33 @@ int hvx_fill_density(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const
 int hvx_fill_slabs(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
                    uint32_t* d_slabs);
 
+/* ---- edits on resident samples (BASELINE config 5: the incremental-edit path) -------------------------- */
+/* GpuVoxelEdit (crates/helio-voxel-core/src/gpu_types.rs:47-54), 32 bytes. */
+typedef struct {
+    uint32_t volume_id;
+    uint32_t op_type;     /* VoxelOp (edit.rs:5-10): 1 AddSphere, 2 SubtractSphere; 0 SetBox and 3 Paint are not handled */
+    uint32_t material;
+    float center[3];      /* metres, in the frame of the pages' LOD0 cell grid (cell c spans [0.1 c, 0.1 (c+1)) m) */
+    float radius;         /* metres */
+    uint32_t _pad;
+} hvx_voxel_edit;
+
+/* Apply one sphere edit to the device-resident samples of chunks [0, n) (d_samples NULL = the ctx sample arena,
+ * page_xyz / lod as in hvx_fill_density) and derive what must be re-extracted.
+ *   samples:  every sample within `radius` of the centre -- halo samples included, so neighbouring chunks stay
+ *             consistent -- gets  carve = clamp_i16(rint((radius - distance) / cell_m * 256)),
+ *             SubtractSphere: density = max(density, carve), material 0 where the sample becomes air;
+ *             AddSphere: density = min(density, -carve), material = edit.material where it becomes solid.
+ *             (The reference queues edits and marks its octree, crates/helio/src/scene/voxel.rs:81-115, but has no
+ *             kernel that applies them to planetary pages; this rule is ours, restated in oracle/edit.py.)
+ *   dirty_out[n]: per chunk, the microbricks to re-extract: the legacy octree's sphere-vs-box rule
+ *             |centre_a - box_centre_a| > half_a + r  =>  untouched  (crates/helio-voxel-core/src/octree.rs:139-173)
+ *             at microbrick granularity, with r = radius + 2 cells (a vertex also reads the gradient neighbours of
+ *             its cell's corners).  0 = chunk untouched.  Feed it to hvx_chunk_desc.dirty_microbricks.
+ *   *touched_out: chunks whose samples were modified. */
+int hvx_apply_edit(hvx_ctx* ctx, const hvx_voxel_edit* edit, const int64_t* page_xyz, const uint8_t* lod, uint32_t n,
+                   uint32_t* d_samples, uint64_t* dirty_out, uint32_t* touched_out);
+
 /* ---- K2-K4: regular cells ---------------------------------------------------------- */
 /* TransvoxelGpuExtractor::dispatch (PV/src/transvoxel_emit.rs:233-254) over n chunks.
  * samples: HOST or DEVICE pointer (detected), n*(edge+2)^3 CellWords, 16-byte aligned;
@@ -229,6 +268,16 @@ int hvx_extract_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t sample_w
  * classify counters (+ cell records when HVX_CFG_DEBUG_RECORDS), no emission. */
 int hvx_classify_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t sample_words,
                          const hvx_chunk_desc* descs, uint32_t n);
+/* dispatch + the read-back the reference's callers do afterwards (map counters, copy the emitted ranges;
+ * PV/tests/gpu_transvoxel_emission.rs:59-101), as ONE pipelined call: host samples are uploaded in sub-batches of
+ * ~256 MiB on a copy stream while the previous sub-batch is extracted, and every sub-batch's mesh is packed and copied
+ * to the host behind the kernels on a third stream.  Outputs as hvx_read_meshes (tightly packed in chunk order,
+ * indices chunk-local, ranges_out[n] = packed placement) plus counters_out[n] (nullable).  Returns
+ * HVX_E_INVALID_CAPACITY if the host arrays are too small (totals and ranges_out are still filled). */
+int hvx_extract_regular_to_host(hvx_ctx* ctx, const uint32_t* samples, uint64_t sample_words,
+                                const hvx_chunk_desc* descs, uint32_t n, hvx_vertex* vertices_out, uint64_t vertex_cap,
+                                uint32_t* indices_out, uint64_t index_cap, hvx_range* ranges_out,
+                                hvx_emission_counters* counters_out, uint64_t* total_vertices, uint64_t* total_indices);
 
 /* ---- K2-K4 (T): transition cells ---------------------------------------------------- */
 /* TransvoxelGpuTransitionExtractor::dispatch (PV/src/transvoxel_transition_gpu.rs:366-380).

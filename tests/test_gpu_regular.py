@@ -347,3 +347,84 @@ def test_edge_parameter_division_is_exact():
     rc = H._ffi.load().hvx_selftest_edge_parameter(0, C.byref(bad), C.byref(witness))
     assert rc == 0
     assert bad.value == 0, f"{bad.value} operand pairs differ, e.g. d0={(witness.value >> 16) - 32768} d1={(witness.value & 0xffff) - 32768}"
+
+
+def test_inverse_square_root_is_exact():
+    """The normal's branch-free 1 / sqrt(s): every float from the kernel's guard 1e-12 to 2^40, bit for bit against
+    IEEE sqrt followed by IEEE division (hvx_selftest_inv_sqrt)."""
+    import ctypes as C
+    bad, witness = C.c_uint64(123), C.c_uint32()
+    assert H._ffi.load().hvx_selftest_inv_sqrt(0, C.byref(bad), C.byref(witness)) == 0
+    assert bad.value == 0, f"{bad.value} operands differ, e.g. s = float bits {witness.value:#x}"
+
+
+@pytest.mark.parametrize("edge,n", [(64, 520), (32, 3600)])
+def test_host_sample_pipeline_and_packed_readback(edge, n):
+    """Host samples go up in ~256 MiB sub-batches beside the kernels (hvx_extract_regular), and
+    hvx_extract_regular_to_host also brings the packed meshes back behind them: both must equal the
+    single-launch device-resident dispatch byte for byte -- with cost hints, partially dirty chunks and
+    chunks flagged HVX_CHUNK_UNIFORM (whose samples are never uploaded: the host array holds garbage there)."""
+    rng = np.random.default_rng(5)
+    side = int(round(n ** 0.5)) + 1
+    pages = np.array([[x - side // 2, (-1, 0, 1)[(x + 2 * z) % 3], z - side // 2] for z in range(side) for x in range(side)][:n],
+                     dtype=np.int64)
+    mv, mi = (49_152, 73_728) if edge == 64 else (12_288, 18_432)
+    words = (edge + 2) ** 3
+    assert n * words * 4 > 2 * (256 << 20)          # at least three sub-batches
+    batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=mv, max_indices=mi)
+    batch.fill_density(O.FIELD_TERRAIN_FBM, pages)
+    masks = [int(m) for m in rng.integers(0, 64, n)]
+    dirty = [ALL] * n
+    for i in range(3, n, 29):
+        dirty[i] = int(rng.integers(1, 1 << 62))
+
+    def snapshot():
+        c, r, k = batch.counters(n).copy(), batch.ranges(n).copy(), batch.classify_counters(n).copy()
+        v, i, packed = batch.ctx.read_meshes(0, 0, n)
+        return c, r, k, v.copy(), i.copy(), packed.copy()
+
+    batch.ctx.extract_regular(None, H.make_descs(n, 7, dirty, masks), n)
+    want = snapshot()
+    surface = want[0]["required_vertices"] > 0
+    assert 0 < surface.sum() < n
+    host = batch.ctx.read(H._ffi.BUF_SAMPLES, 0, n * words)
+    hints = [int(v) for v in want[0]["required_vertices"]]
+    # chunks without a surface are flagged uniform (every third of them, so runs of both kinds occur) and scribbled over
+    flags = np.zeros(n, dtype=np.uint32)
+    flags[np.nonzero(~surface)[0][::3]] = H._ffi.HVX_CHUNK_UNIFORM
+    for i in np.nonzero(flags)[0]:
+        host[i * words:(i + 1) * words] = 0xDEAD0001
+    descs = H.make_descs(n, 7, dirty, masks, cost_hint=hints, flags=[int(f) for f in flags])
+    # 1. sub-batched upload, outputs stay on the device
+    batch.ctx.write(H._ffi.BUF_SAMPLES, np.zeros(words, dtype=np.uint32), 0)   # the arena really is overwritten by the upload
+    batch.ctx.extract_regular(host, descs, n)
+    got = snapshot()
+    for a, b in zip(want, got):
+        assert a.tobytes() == b.tobytes()
+    # 2. upload + extraction + packed read-back in one call
+    v, i, ranges, counters = batch.ctx.extract_regular_to_host(host, descs, n, vertex_cap=len(want[3]) + 7, index_cap=len(want[4]))
+    assert v.tobytes() == want[3].tobytes() and i.tobytes() == want[4].tobytes()
+    assert ranges.tobytes() == want[5].tobytes() and counters.tobytes() == want[0].tobytes()
+    # 3. too small a destination: totals and placement are still reported
+    with pytest.raises(H.InvalidExtractionCapacity):
+        batch.ctx.extract_regular_to_host(host, descs, n, vertex_cap=len(want[3]) - 1, index_cap=len(want[4]))
+    # 4. device-resident input through the same entry point (one launch, then the read-back)
+    batch.ctx.extract_regular(host, H.make_descs(n, 7, dirty, masks), n)      # refill the arena (uniform chunks hold the scribble)
+    v, i, ranges, counters = batch.ctx.extract_regular_to_host(None, descs, n, vertex_cap=len(want[3]), index_cap=len(want[4]))
+    assert v.tobytes() == want[3].tobytes() and i.tobytes() == want[4].tobytes() and counters.tobytes() == want[0].tobytes()
+    batch.close()
+
+
+def test_uniform_flag_on_a_surface_chunk_empties_it():
+    """HVX_CHUNK_UNIFORM is the caller's promise: a flagged chunk reports an empty, completed mesh whatever it holds."""
+    pages = np.array([[0, -1, 0], [1, -1, 0], [0, 5, 0]], dtype=np.int64)
+    batch = H.ChunkBatchExtractor(0, edge=64, max_chunks=3)
+    batch.fill_density(O.FIELD_TERRAIN_FBM, pages)
+    batch.ctx.extract_regular(None, H.make_descs(3, flags=[0, H._ffi.HVX_CHUNK_UNIFORM, H._ffi.HVX_CHUNK_UNIFORM]), 3)
+    c, r, k = batch.counters(3), batch.ranges(3), batch.classify_counters(3)
+    assert c["required_vertices"][0] > 0 and list(c["required_vertices"][1:]) == [0, 0] and list(c["completed"]) == [1, 1, 1]
+    assert list(r["first_vertex"]) == [0, 49_152, 98_304] and list(r["vertex_count"][1:]) == [0, 0]
+    assert list(k["visited_cells"]) == [64 ** 3] * 3 and list(k["active_cells"][1:]) == [0, 0]
+    with pytest.raises(H.HvxError, match="unknown descriptor flags"):
+        batch.ctx.extract_regular(None, H.make_descs(3, flags=[0, 2, 0]), 3)
+    batch.close()

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [name for name in sorted(declared) if not hasattr(lib, name)]
     assert not missing, missing
     assert set(_ffi.EXPORTS) == declared
-    assert lib.hvx_abi_version() == 1
+    assert lib.hvx_abi_version() == 2
     assert lib.hvx_status_name(-1).decode() == "HVX_E_SAMPLE_COUNT" and lib.hvx_status_name(0).decode() == "HVX_OK"
 
 
@@ -34,7 +34,7 @@ def test_struct_layouts_match_the_reference_pods():
     assert H.CLASSIFY_COUNTERS_DTYPE.itemsize == 16
     assert H.TRANSITION_COUNTERS_DTYPE.itemsize == 48 and H.TRANSITION_COUNTERS_DTYPE.fields["completed"][1] == 32
     assert H.CELL_RECORD_DTYPE.itemsize == H.CELL_OFFSET_DTYPE.itemsize == H.SCAN_BLOCK_DTYPE.itemsize == H.RANGE_DTYPE.itemsize == 16
-    assert C.sizeof(_ffi.ChunkDesc) == 24 and C.sizeof(_ffi.Config) == 32 and C.sizeof(_ffi.Page) == 32
+    assert C.sizeof(_ffi.ChunkDesc) == 32 and C.sizeof(_ffi.Config) == 32 and C.sizeof(_ffi.Page) == 32
 
 
 def test_no_gpu_means_a_loud_error_not_a_fallback():
