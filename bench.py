@@ -6,8 +6,15 @@ fBm terrain (helio-pass-sdf `terrain_sdf`, TerrainConfig::rolling(), 0.1 m voxel
 4.71 GB of CellWord samples.  One "step" = one regular-cell extraction pass over the whole batch.
 
   value        cells/s with the samples already resident in HBM (CUDA events on the launch stream)
-  e2e          the same metric through the C-ABI call with HOST buffers: pinned host samples ->
-               H2D -> extraction -> packed mesh + counters -> D2H into pinned host memory
+  e2e          the same metric through ONE C-ABI call with HOST buffers (hvx_extract_regular_to_host): pinned
+               host samples -> H2D in sub-batches beside the kernels -> packed mesh + counters -> D2H behind
+               them.  h2d_gbs_peak is the raw pinned upload bandwidth of this box measured in the same run
+               (all ranks at once), so h2d_frac says how much of the link the call uses.
+  e2e_variants fill_extract_readback (procedural density on the device, no sample upload), sparse_upload
+               (chunks the producer knows to be empty are flagged HVX_CHUNK_UNIFORM and not uploaded),
+               unpipelined (round 1's path: monolithic copy, kernel, read-back, counters)
+  configs      BASELINE configs[2..4] as sub-records: the planet-scale page set (STRONG scaling at the launched
+               N), the three-level LOD seam path, the incremental-edit latency path, the whole per-page pass
   roofline     algorithmic bytes (4*(E+2)^3 + 32*V + 4*I per chunk) / kernel time vs measured HBM peak
   cpu_baseline the CPU oracle (restating the reference's Rust CPU extractor) on this box's cores,
                on a bounded sample of the same chunks
@@ -88,13 +95,16 @@ def bind_to_gpu_numa_node(local_rank):
 
 
 def profiled_traffic(alg_bytes):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture
-    (profiles/r01_traffic.json), scaled by nothing: only reported when it was taken on this exact workload."""
-    path = ROOT / "profiles" / "r01_traffic.json"
-    if not path.exists():
-        return None
-    rec = json.loads(path.read_text())
-    return rec["dram_bytes_per_launch"] if rec.get("algorithmic_bytes_per_launch") == alg_bytes else None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch.  ncu cannot run inside the timed process, so this
+    is an OFFLINE number: the committed ncu --set full capture of this same command (profiles/r02_traffic.json, or
+    round 1's), reported only when it was taken on exactly this workload (same algorithmic bytes).  -> (bytes, source)"""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        path = ROOT / "profiles" / name
+        if path.exists():
+            rec = json.loads(path.read_text())
+            if rec.get("algorithmic_bytes_per_launch") == alg_bytes:
+                return rec["dram_bytes_per_launch"], f"offline ncu --set full capture, profiles/{name}"
+    return None, None
 
 
 def measured_peak_gbs():
@@ -257,15 +267,16 @@ def run_ours(args):
     launches0 = ctx.launch_count
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            starts[k].record(stream)
-            ctx.extract_regular(None, descs, n)
-            stops[k].record(stream)
-        barrier()
-        wall = time.perf_counter() - t0
+    clocks = ClockSampler(local_rank)       # sampled from here to the end of the e2e legs (stopped before the CPU baseline)
+    clocks.__enter__()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        starts[k].record(stream)
+        ctx.extract_regular(None, descs, n)
+        stops[k].record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
     launches = ctx.launch_count - launches0
     kernel_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     total_ms = starts[0].elapsed_time(stops[-1])
@@ -287,43 +298,98 @@ def run_ours(args):
     achieved = alg_bytes / avg_kernel_s / 1e9
 
     # ---- e2e through the C ABI with HOST buffers ------------------------------------------------
-    e2e = None
+    e2e, e2e_variants = None, {}
     if not args.no_e2e:
+        import ctypes as C
         host_samples = torch.empty(n * words, dtype=torch.int32, pin_memory=True)
         ctx.synchronize()
         # one-time (untimed) copy of the generated samples to the pinned host buffer
-        import ctypes as C
         rc = _ffi.load().hvx_read(ctx._handle, _ffi.BUF_SAMPLES, 0, n * words * 4, C.c_void_p(host_samples.data_ptr()))
         assert rc == 0
         host_v = torch.empty((total_v + 1024) * 8, dtype=torch.int32, pin_memory=True)
         host_i = torch.empty(total_i + 1024, dtype=torch.int32, pin_memory=True)
-
-        def e2e_step():
-            ctx.extract_regular(host_samples, descs, n)                       # H2D + kernel
-            tv, ti, _ = ctx.read_meshes(0, 0, n, vertices_out=host_v, indices_out=host_i)  # pack + D2H
-            c = batch.counters(n)                                             # D2H counters
-            return tv, ti, c
-
-        for _ in range(max(1, min(args.warmup, 2))):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        for _ in range(e2e_steps):
-            tv, ti, c = e2e_step()
-        barrier()
-        e2e_s = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        assert tv == total_v and ti == total_i
-        e2e = {"value": world * cells_per_step * e2e_steps / e2e_s, "unit": "cells/s",
-               "h2d_bytes_per_step": n * words * 4 + n * 24 + n * 16,
-               "d2h_bytes_per_step": 32 * total_v + 4 * total_i + n * 16 + n * 32,
-               "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps,
-               "path": "hvx_extract_regular(host samples) + hvx_read_meshes + counters, pinned host memory",
+        h2d_bytes = n * words * 4 + n * 32
+        d2h_bytes = 32 * total_v + 4 * total_i + n * 16 + n * 32
+
+        def timed_e2e(step, warm=2):
+            """wall clock over e2e_steps calls, barrier + device sync on both sides, max over ranks"""
+            for _ in range(warm):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                out = step()
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt / e2e_steps, out
+
+        def check(out):
+            tv, ti, _ranges, c = out
+            assert tv == total_v and ti == total_i and int(c["emitted_vertices"].astype(np.int64).sum()) == total_v
+
+        # the raw link: the same 4.71 GB pinned buffer into the sample arena with plain async copies, all ranks at once
+
+        def raw_upload():
+            rc = _ffi.load().hvx_write(ctx._handle, _ffi.BUF_SAMPLES, 0, n * words * 4, C.c_void_p(host_samples.data_ptr()))
+            assert rc == 0
+        raw_s, _ = timed_e2e(raw_upload, warm=1)
+        h2d_peak = n * words * 4 / raw_s / 1e9
+
+        # headline: ONE call, pipelined upload -> extraction -> packed read-back
+        step_s, out = timed_e2e(lambda: ctx.extract_regular_to_host(host_samples, descs, n, host_v, host_i))
+        check(out)
+        e2e = {"value": world * cells_per_step / step_s, "unit": "cells/s", "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": step_s * 1e3, "steps": e2e_steps,
+               "path": "hvx_extract_regular_to_host(pinned host samples): sub-batched H2D beside the kernels, packed meshes + counters D2H behind them",
+               "h2d_gbs_achieved": h2d_bytes / step_s / 1e9, "h2d_gbs_peak": h2d_peak,
+               "h2d_frac": (h2d_bytes / step_s / 1e9) / h2d_peak,
+               "h2d_peak_how": f"hvx_write of the same {n * words * 4 / 1e9:.2f} GB pinned buffer, {world} rank(s) at once, same run",
                "numa_node": numa_node}
+
+        # round 1's path for comparison: monolithic copy, kernel, read-back, counters
+        def unpipelined():
+            raw_upload()
+            ctx.extract_regular(None, descs, n)
+            tv, ti, r = ctx.read_meshes(0, 0, n, vertices_out=host_v, indices_out=host_i)
+            return tv, ti, r, batch.counters(n)
+        step_s, out = timed_e2e(unpipelined, warm=1)
+        check(out)
+        e2e_variants["unpipelined"] = {"value": world * cells_per_step / step_s, "unit": "cells/s", "ms_per_step": step_s * 1e3,
+                                       "path": "hvx_write(samples) + hvx_extract_regular + hvx_read_meshes + counters (round 1's sequence)"}
+
+        # production flow 1: procedural density on the device -> extraction -> packed read-back (no sample upload)
+        def fill_extract_readback():
+            ctx.fill_density(FIELD_TERRAIN_FBM, pages)
+            return ctx.extract_regular_to_host(None, descs, n, host_v, host_i)
+        step_s, out = timed_e2e(fill_extract_readback, warm=1)
+        check(out)
+        e2e_variants["fill_extract_readback"] = {
+            "value": world * cells_per_step / step_s, "unit": "cells/s", "ms_per_step": step_s * 1e3,
+            "h2d_bytes_per_step": n * 24 + n * 32, "d2h_bytes_per_step": d2h_bytes,
+            "path": "hvx_fill_density(page list) + hvx_extract_regular_to_host(arena): host sends page coordinates, gets packed meshes"}
+
+        # sparse upload: the producer (an octree that keeps min / max density per node) knows which chunks hold no
+        # surface; they are flagged HVX_CHUNK_UNIFORM and neither uploaded nor walked
+        empty = counters["required_vertices"] == 0
+        sparse = H.make_descs(n, cost_hint=[int(v) for v in counters["required_vertices"]],
+                              flags=[_ffi.HVX_CHUNK_UNIFORM if e else 0 for e in empty])
+        step_s, out = timed_e2e(lambda: ctx.extract_regular_to_host(host_samples, sparse, n, host_v, host_i), warm=1)
+        check(out)
+        e2e_variants["sparse_upload"] = {
+            "value": world * cells_per_step / step_s, "unit": "cells/s", "ms_per_step": step_s * 1e3,
+            "h2d_bytes_per_step": int((~empty).sum()) * words * 4 + n * 32, "d2h_bytes_per_step": d2h_bytes,
+            "uploaded_chunks": int((~empty).sum()),
+            "path": "hvx_extract_regular_to_host with HVX_CHUNK_UNIFORM on the chunks that produced no vertex on the previous pass"}
+        ctx.extract_regular(host_samples, descs, n)      # leave the arena whole again
+        ctx.synchronize()
+        del host_samples, host_v, host_i
+
+    clocks.__exit__(None, None, None)
 
     # ---- CPU baseline on this box's cores (rank 0, N=1 only) ------------------------------------
     cpu = None
@@ -342,9 +408,25 @@ def run_ours(args):
         assert totals[0] == int(counters["required_vertices"][idx].astype(np.int64).sum()), "CPU/GPU vertex totals differ"
         cpu = {"value": cells / dt, "unit": "cells/s", "cores": threads, "kind": "port",
                "sample": f"{len(idx)} of {n} chunks (every {args.cpu_stride}th), {dt:.2f} s wall, samples resident in host RAM"}
+        del host
+
+    kernel_name = ctx.regular_kernel_name()
+    batch.close()
+
+    # ---- the other BASELINE configurations, as sub-records --------------------------------------
+    configs = {}
+    if not args.no_configs and WORKLOAD == "terrain":
+        sys.path.insert(0, str(ROOT / "tools"))
+        import bench_cases as BC
+        configs["planet"] = BC.planet_case(H, torch, dist, device, local_rank, rank, world, steps=args.steps, warmup=args.warmup)
+        if world == 1:
+            configs["lod_seam"] = BC.lod_seam_case(H, torch, device, local_rank)
+            configs["edit_latency"] = BC.edit_latency_case(H, torch, device, local_rank)
+            configs["page_pass"] = BC.page_pass_case(H, torch, device, local_rank)
 
     if rank == 0:
         clk = clocks.summary()
+        traffic, traffic_src = profiled_traffic(alg_bytes) if WORKLOAD == "terrain" and world == 1 else (None, None)
         print(json.dumps({
             "metric": "voxel_cells_per_sec", "value": value, "unit": "cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -358,14 +440,15 @@ def run_ours(args):
                        "partition": "LPT static, no data-path collective",
                        "chunk_order": "identity" if args.no_hints or not args.warmup else "heaviest first by the previous pass's vertex counts (hvx_chunk_desc.cost_hint)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profiled_traffic(alg_bytes) if WORKLOAD == "terrain" and world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel": "regular_extract_decoupled_kernel<64>", "kernel_ms": float(np.mean(kernel_ms)),
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel": kernel_name, "kernel_ms": float(np.mean(kernel_ms)),
                          "frac_of_8TBps_nominal": achieved / 8000.0},
             "fill_kernel": {"ms": fill_ms, "GB/s": n * words * 4 / (fill_ms * 1e-3) / 1e9},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_variants": e2e_variants, "configs": configs,
+            "gpu_launches": launches, "clocks": clk,
             "wall_s_timed_region": wall,
         }))
-    batch.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -395,9 +478,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     ap.add_argument("--no-hints", action="store_true", help="do not feed the previous pass's vertex counts back as cost hints")
     ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (N > 1)")
-    ap.add_argument("--cpu-stride", type=int, default=2, help="CPU baseline runs every k-th chunk of the workload")
+    ap.add_argument("--cpu-stride", type=int, default=1, help="CPU baseline runs every k-th chunk of the workload (default: all of them)")
     ap.add_argument("--cpu-offset", type=int, default=0)
     ap.add_argument("--workload", choices=["terrain", "surface", "empty"], default="terrain")
     args = ap.parse_args()

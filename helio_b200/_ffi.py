@@ -170,12 +170,12 @@ class ExtractionPublisherCounters(C.Structure):
 # every symbol include/hvx.h declares; tests assert the library exports all of them
 EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
-    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_selftest_edge_parameter", "hvx_selftest_inv_sqrt",
+    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_regular_kernel_name", "hvx_selftest_edge_parameter", "hvx_selftest_inv_sqrt",
     "hvx_fill_density", "hvx_fill_slabs", "hvx_apply_edit", "hvx_extract_regular", "hvx_extract_regular_to_host", "hvx_classify_regular", "hvx_extract_transition",
     "hvx_build_meshlets", "hvx_gather_surface", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
     "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
     "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
-    "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost",
+    "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost", "hvx_copy_segments",
     "hvx_extraction_request_new", "hvx_extraction_limits_plan", "hvx_extraction_limits_validate_device",
     "hvx_extraction_gpu_range", "hvx_extraction_publisher_create", "hvx_extraction_publisher_destroy",
     "hvx_extraction_reserve", "hvx_extraction_publish", "hvx_extraction_cancel_pending", "hvx_extraction_evict",
@@ -220,6 +220,8 @@ def load() -> C.CDLL:
     L.hvx_launch_count.argtypes = [vp]
     L.hvx_launch_count.restype = C.c_uint64
     L.hvx_debug_set_mode.argtypes = [vp, C.c_uint32]
+    L.hvx_regular_kernel_name.argtypes = [vp, C.c_int]
+    L.hvx_regular_kernel_name.restype = C.c_char_p
     L.hvx_selftest_edge_parameter.argtypes = [C.c_int, u64p, u32p]
     L.hvx_selftest_inv_sqrt.argtypes = [C.c_int, u64p, u32p]
     L.hvx_fill_density.argtypes = [vp, C.c_uint32, i64p, u8p, C.c_uint32, vp]
@@ -255,6 +257,7 @@ def load() -> C.CDLL:
     L.hvx_horizon_plan.argtypes = [i64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Page), u32p,
                                    C.POINTER(Page), C.POINTER(LodStats)]
     L.hvx_partition_chunks.argtypes = [u64p, C.c_uint32, C.c_uint32, u32p]
+    L.hvx_copy_segments.argtypes = [C.c_int, vp, vp, vp, u64p, C.c_uint32]
     L.hvx_chunk_cost.argtypes = [C.c_uint32, C.c_uint32]
     L.hvx_chunk_cost.restype = C.c_uint64
     L.hvx_extraction_request_new.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(ExtractionRequest)]

@@ -151,6 +151,9 @@ class Context:
     def synchronize(self):
         self._check(self._lib.hvx_synchronize(self._handle))
 
+    def regular_kernel_name(self, partial=False):
+        return self._lib.hvx_regular_kernel_name(self._handle, int(bool(partial))).decode()
+
     def debug_set_mode(self, mode):
         """Roofline probes of the regular kernel: 0 normal, 1 stream only, 2 stream + sign bits (no meshes)."""
         self._check(self._lib.hvx_debug_set_mode(self._handle, int(mode)))

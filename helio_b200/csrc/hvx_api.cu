@@ -317,7 +317,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     bool hinted = false, any_uniform = false;
     for (uint32_t i = 0; i < n; ++i) {
         hinted |= descs[i].cost_hint != 0u;
-        any_uniform |= (descs[i].flags & HVX_CHUNK_UNIFORM) != 0u;
+        any_uniform |= (descs[i].flags & HVX_CHUNK_UNIFORM) != 0u || descs[i].dirty_microbricks == 0;
     }
     std::vector<uint32_t> order, uniform, n_work(n_sub);
     if (hinted || any_uniform) order.resize(n);
@@ -329,7 +329,8 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         }
         uint32_t m = 0;
         for (uint32_t i = 0; i < count; ++i) {
-            if (descs[first + i].flags & HVX_CHUNK_UNIFORM) uniform.push_back(first + i);
+            // nothing to walk: flagged uniform, or no dirty microbrick (an edit frame re-submits every resident chunk)
+            if ((descs[first + i].flags & HVX_CHUNK_UNIFORM) || descs[first + i].dirty_microbricks == 0) uniform.push_back(first + i);
             else order[first + m++] = i;  // ids are relative to the sub-batch
         }
         n_work[k] = m;
@@ -397,7 +398,8 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         p.n_work = n_work[k];
         p.chunk_base = first;
         for (uint32_t i = 0; i < count && !p.any_partial; ++i)
-            p.any_partial = descs[first + i].dirty_microbricks != ~0ull && !(descs[first + i].flags & HVX_CHUNK_UNIFORM);
+            p.any_partial = descs[first + i].dirty_microbricks != ~0ull && descs[first + i].dirty_microbricks != 0 &&
+                            !(descs[first + i].flags & HVX_CHUNK_UNIFORM);
         p.vertices = all_vertices + static_cast<uint64_t>(first) * ctx->cfg.max_vertices;
         p.indices = all_indices + static_cast<uint64_t>(first) * ctx->cfg.max_indices;
         p.counters = all_counters + first;
@@ -410,6 +412,10 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
             cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
             ctx->launches += (p.cells != nullptr && !p.first_generation) ? 3 : 1;  // + the two record kernels
+        } else if (p.cells != nullptr) {  // nothing to extract, but the scan blocks of the sub-batch still report it
+            cudaError_t e = launch_regular_records(static_cast<int>(ctx->cfg.edge), p, ctx->stream);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular_records");
+            ctx->launches += 2;
         }
         if (k + 1 == n_sub && !uniform.empty()) {
             HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_uniform, uniform.data(), uniform.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -736,6 +742,11 @@ int hvx_get_config(const hvx_ctx* ctx, hvx_config* out) {
 
 uint64_t hvx_allocated_bytes(const hvx_ctx* ctx) { return ctx ? ctx->allocated : 0; }
 uint64_t hvx_launch_count(const hvx_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+const char* hvx_regular_kernel_name(const hvx_ctx* ctx, int partial) {
+    if (!ctx) return "";
+    return regular_kernel_name(static_cast<int>(ctx->cfg.edge), (ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) != 0, partial != 0);
+}
 
 int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
@@ -1463,6 +1474,22 @@ int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n) {
     cudaError_t e = launch_meshlets(p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_meshlets");
     ctx->launches += 1;
+    return HVX_OK;
+}
+
+int hvx_copy_segments(int device, void* cuda_stream, const uint32_t* d_src, uint32_t* d_dst, const uint64_t* segments, uint32_t n) {
+    if (n == 0) return HVX_OK;
+    if (!d_src || !d_dst || !segments) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "hvx_copy_segments: NULL argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "device %d cannot be selected", device);
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    uint64_t* d_seg = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_seg), 24ull * n, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_seg, segments, 24ull * n, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = launch_copy_segments(d_src, d_dst, d_seg, n, stream);
+    if (d_seg) cudaFreeAsync(d_seg, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // `segments` is the caller's host memory
+    if (e != cudaSuccess) return cuda_fail(nullptr, e, "hvx_copy_segments");
     return HVX_OK;
 }
 

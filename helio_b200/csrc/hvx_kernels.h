@@ -188,6 +188,7 @@ cudaError_t launch_regular_records(int edge, const RegularParams& p, cudaStream_
 cudaError_t launch_uniform_records(int edge, const RegularParams& p, const uint32_t* ids, uint32_t n, cudaStream_t stream);
 cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_fill_samples(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_copy_segments(const uint32_t* src, uint32_t* dst, const uint64_t* d_segments, uint32_t n, cudaStream_t stream);
 cudaError_t launch_edit_sphere(int edge, const EditParams& p, cudaStream_t stream);
 cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_terrain_heights(int edge, const long long* col_xz, const uint8_t* col_lod, uint32_t n_cols, float* heights,
@@ -203,6 +204,7 @@ cudaError_t launch_pack(const hvx_vertex* vertices, const uint32_t* indices, con
                         const hvx_range* packed_ranges, uint32_t n, hvx_vertex* out_vertices,
                         uint32_t* out_indices, const DeviceInfo& dev, cudaStream_t stream);
 
+const char* regular_kernel_name(int edge, bool first_generation, bool partial);
 // shared-memory footprint of the regular kernel (for resource reporting / tests)
 size_t regular_smem_bytes(int edge);
 

@@ -1354,6 +1354,10 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         do {
                             got = *prev;
                         } while ((got >> 44) != want);
+                        // all lanes poll (a lane-0 spin leaves the warp split, and everything after it is issued twice),
+                        // but the word can be overwritten 32 tiles later: the warp takes lane 0's copy, so a lane that
+                        // looked late cannot carry a different prefix into the collectives below
+                        got = __shfl_sync(0xffffffffu, got, 0);
                         if (!first) base = got & ((1ull << 44) - 1ull);
                     }
                     HVX_CHECK((base & FIELD) + tot_v <= FIELD && ((base >> 22) & FIELD) + tot_i <= FIELD, 5u, chunk, st | (slot << 8), seq,
@@ -1468,6 +1472,15 @@ cudaError_t launch_decoupled(const RegularParams& p, const DeviceInfo& dev, cuda
 }
 
 }  // namespace
+
+#define HVX_STR2(x) #x
+#define HVX_STR(x) HVX_STR2(x)
+const char* regular_kernel_name(int edge, bool first_generation, bool partial) {
+    if (first_generation) return edge == 64 ? "regular_extract_kernel<Cfg<64,2,6,16>>" : "regular_extract_kernel<Cfg<32,2,10,8>>";
+    if (edge == 64) return partial ? "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,true>" : "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,false>";
+    return partial ? "regular_extract_decoupled_kernel<Cfg<32,1," HVX_STR(HVX_E32_RS) "," HVX_STR(HVX_E32_NW) ">,true>"
+                   : "regular_extract_decoupled_kernel<Cfg<32,1," HVX_STR(HVX_E32_RS) "," HVX_STR(HVX_E32_NW) ">,false>";
+}
 
 size_t regular_smem_bytes(int edge) {
     return edge == 64 ? max(sizeof(Smem<Cfg64>), sizeof(SmemD<Cfg64D>)) : max(sizeof(Smem<Cfg32>), sizeof(SmemD<Cfg32D>));

@@ -84,22 +84,44 @@ def gather_meshes(vertices, indices, ranges, shard: Shard, dst=0, group=None):
             req.wait()
     if rank != dst:
         return None
-    # 3. interleave back into global chunk order
+    # 3. interleave back into global chunk order: every rank's ranges come to the host in ONE copy, the placement is
+    #    computed there, and each arena is rearranged by ONE device launch (hvx_copy_segments) -- no per-chunk sync
     n_global = shard.owner.size
-    local_pos = np.zeros(world, dtype=np.int64)
+    all_r = torch.cat([recv_r[src] for src in range(world)]).cpu().numpy()        # [sum nr, 4]
+    row0 = np.concatenate([[0], np.cumsum(all_sizes[:, 2])])[:world]              # first range row of each rank
+    v0 = np.concatenate([[0], np.cumsum(all_sizes[:, 0])])[:world]                # first word of each rank in the concatenation
+    i0 = np.concatenate([[0], np.cumsum(all_sizes[:, 1])])[:world]
+    owner = shard.owner.astype(np.int64)
+    local = np.zeros(n_global, dtype=np.int64)                                   # position of chunk g in its owner's list
+    for src in range(world):
+        mask = owner == src
+        local[mask] = np.arange(int(mask.sum()))
+    rows = all_r[row0[owner] + local]
+    nv, ni = rows[:, 1], rows[:, 3]
     out_ranges = np.zeros((n_global, 4), dtype=np.int64)
-    v_parts, i_parts = [], []
-    tv = ti = 0
-    for g in range(n_global):
-        src = int(shard.owner[g])
-        fr = recv_r[src][int(local_pos[src])].cpu().numpy()
-        local_pos[src] += 1
-        fv, nv, fi, ni = (int(x) for x in fr)
-        v_parts.append(recv_v[src][fv * 8:(fv + nv) * 8])
-        i_parts.append(recv_i[src][fi:fi + ni])
-        out_ranges[g] = (tv, nv, ti, ni)
-        tv += nv
-        ti += ni
-    vertices_out = torch.cat(v_parts) if v_parts else torch.empty(0, dtype=torch.int32, device=device)
-    indices_out = torch.cat(i_parts) if i_parts else torch.empty(0, dtype=torch.int32, device=device)
+    out_ranges[:, 1], out_ranges[:, 3] = nv, ni
+    out_ranges[:, 0] = np.cumsum(nv) - nv
+    out_ranges[:, 2] = np.cumsum(ni) - ni
+    cat_v = torch.cat([recv_v[src] for src in range(world)])
+    cat_i = torch.cat([recv_i[src] for src in range(world)])
+    vertices_out, indices_out = torch.empty_like(cat_v), torch.empty_like(cat_i)
+    seg_v = np.stack([v0[owner] + rows[:, 0] * 8, out_ranges[:, 0] * 8, nv * 8], axis=1).astype(np.uint64)
+    seg_i = np.stack([i0[owner] + rows[:, 2], out_ranges[:, 2], ni], axis=1).astype(np.uint64)
+    if device.type == "cuda":
+        import ctypes as C
+        from . import _ffi
+        lib = _ffi.load()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        for seg, src_t, dst_t in ((seg_v, cat_v, vertices_out), (seg_i, cat_i, indices_out)):
+            seg = np.ascontiguousarray(seg[seg[:, 2] != 0])
+            if len(seg):
+                status = lib.hvx_copy_segments(device.index or 0, C.c_void_p(stream), C.c_void_p(src_t.data_ptr()), C.c_void_p(dst_t.data_ptr()),
+                                               seg.ctypes.data_as(C.POINTER(C.c_uint64)), len(seg))
+                if status != _ffi.HVX_OK:
+                    raise RuntimeError(f"hvx_copy_segments failed: {lib.hvx_last_error(None).decode()}")
+    else:   # gloo / CPU tensors: the host-logic tests; plain slice copies
+        sv, dv, si, di = cat_v.numpy(), vertices_out.numpy(), cat_i.numpy(), indices_out.numpy()
+        for (a0, b0, n0), (a1, b1, n1) in zip(seg_v.astype(np.int64), seg_i.astype(np.int64)):
+            dv[b0:b0 + n0] = sv[a0:a0 + n0]
+            di[b1:b1 + n1] = si[a1:a1 + n1]
     return vertices_out, indices_out, out_ranges

@@ -202,6 +202,10 @@ uint64_t hvx_allocated_bytes(const hvx_ctx* ctx);
 int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream);
 void* hvx_get_stream(const hvx_ctx* ctx);
 int hvx_synchronize(hvx_ctx* ctx);
+/* The kernel hvx_extract_regular launches for this ctx (as ncu / cuobjdump print it, without the namespace), e.g.
+ * "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,false>"; `partial` != 0: the instantiation for batches that hold
+ * partially dirty chunks.  bench.py copies it into roofline.kernel. */
+const char* hvx_regular_kernel_name(const hvx_ctx* ctx, int partial);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t hvx_launch_count(const hvx_ctx* ctx);
 /* Roofline probes for the regular kernel (bench tools only): 0 = normal, 1 = stream the samples and do nothing else,
@@ -664,6 +668,11 @@ int hvx_lod_topology(hvx_page* pages, uint32_t n, uint32_t edge, hvx_lod_stats* 
 int hvx_horizon_plan(const int64_t focus_lod0_cell[3], uint32_t root_lod, uint32_t minimum_lod,
                      uint32_t max_pages, uint32_t edge, hvx_page* out, uint32_t* n_out, hvx_page* root_out,
                      hvx_lod_stats* stats);
+/* The interleave step of the optional multi-GPU mesh gather (helio_b200/distributed.py): n independent
+ * device-to-device segment copies in ONE launch on `cuda_stream` of `device`.  segments: HOST, n triples
+ * (source word, destination word, words) of 32-bit words into src / dst.  Segments must not overlap in dst. */
+int hvx_copy_segments(int device, void* cuda_stream, const uint32_t* d_src, uint32_t* d_dst, const uint64_t* segments,
+                      uint32_t n);
 /* Static multi-GPU partition: LPT-greedy assignment of chunks to ranks by cost;
  * owner[i] in [0, ranks).  Deterministic (ties -> lower chunk index, lower rank). */
 int hvx_partition_chunks(const uint64_t* cost, uint32_t n, uint32_t ranks, uint32_t* owner);
