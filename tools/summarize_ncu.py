@@ -15,7 +15,41 @@ KEYS = [
 ]
 
 
+def multi(rep, out):
+    """A capture with many kernels: one metric block per distinct kernel name (its slowest launch)."""
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    kn, dur = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+    best = {}
+    for r in data:
+        if len(r) <= dur:
+            continue
+        name = r[kn]
+        if name not in best or float(r[dur] or 0) > float(best[name][dur] or 0):
+            best[name] = r
+    lines = [f"# ncu --set full, one block per kernel (slowest launch of each) of {rep}", ""]
+    for name, vals in sorted(best.items()):
+        lines.append(f"kernel: {name}")
+        grid_i, block_i = hdr.index("Grid Size") if "Grid Size" in hdr else None, hdr.index("Block Size") if "Block Size" in hdr else None
+        if grid_i is not None:
+            lines.append(f"  grid {vals[grid_i]}  block {vals[block_i]}")
+        for i, h in enumerate(hdr):
+            if h in KEYS:
+                lines.append(f"  {h:73s} {vals[i]:>18s} {units[i]}")
+        stalls = []
+        for i, h in enumerate(hdr):
+            if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and float(vals[i] or 0) >= 0.3:
+                stalls.append((float(vals[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+        lines.append("  stalls: " + ", ".join(f"{n} {v:.2f}" for v, n in sorted(stalls, reverse=True)[:6]))
+        lines.append("")
+    open(out, "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines[:60]))
+
+
 def main():
+    if sys.argv[1] == "--multi":
+        return multi(sys.argv[2], sys.argv[3])
     rep, out = sys.argv[1], sys.argv[2]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
