@@ -34,12 +34,15 @@ struct hvx_ctx {
     std::vector<cudaEvent_t> events;     // [2 * sub-batches]: upload done, kernel done
     hvx_range* h_ranges = nullptr;       // pinned, [max_chunks]: ranges on their way to the host
     uint32_t* d_uniform = nullptr;       // [max_chunks] chunks flagged HVX_CHUNK_UNIFORM
+    SplitItem* d_items = nullptr;        // [MAX_SPLIT_ITEMS] z-ranges of chunks, when a dispatch is too small to fill the machine
+    uint4* d_item_totals = nullptr;      // [MAX_SPLIT_ITEMS] per-part totals (the look-back state of the split walk)
     void* buf[HVX_BUF_COUNT] = {};
     uint64_t buf_bytes[HVX_BUF_COUNT] = {};
     ChunkDesc* d_descs = nullptr;     // [max_chunks] descriptors of the last REGULAR dispatch
     ChunkDesc* d_tdescs = nullptr;    // [max_chunks] descriptors of the last TRANSITION dispatch
     uint32_t n_regular = 0, n_transition = 0;  // sizes of those dispatches (hvx_build_meshlets reads the generations)
     uint32_t debug_mode = 0;          // hvx_debug_set_mode
+    bool no_split = false;            // hvx_debug_set_mode bit 8: never split chunks across CTAs (A/B measurements, tests)
     uint32_t* d_order = nullptr;      // [max_chunks] start order of a batch with cost hints
     int64_t* d_pages = nullptr;
     uint8_t* d_lod = nullptr;
@@ -62,6 +65,9 @@ struct hvx_ctx {
 };
 
 namespace {
+
+constexpr uint32_t MAX_SPLIT_ITEMS = 4096;  // a dispatch is only split while it has fewer chunks than resident CTAs (<= 444)
+constexpr uint32_t MAX_PARTS = 8;
 
 thread_local std::string g_create_error;
 
@@ -339,9 +345,38 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
             std::stable_sort(order.begin() + first, order.begin() + first + m,
                              [&](uint32_t a, uint32_t b) { return descs[first + a].cost_hint > descs[first + b].cost_hint; });
     }
+    // ---- too few chunks to fill the machine (one page, an edit frame): walk z-ranges of chunks instead -----------
+    // Each chunk of the work list becomes up to MAX_PARTS consecutive items over the steps that can hold a dirty cell;
+    // a counting launch leaves every part's totals, the extraction launch looks back over them (regular_extract.cu).
+    std::vector<SplitItem> items;
+    const uint32_t resident = static_cast<uint32_t>(ctx->dev.sm_count) * (ctx->cfg.edge == 32 ? 3u : 1u);
+    if (n_sub == 1 && n_work[0] != 0 && n_work[0] < resident && mode == MODE_EXTRACT && ctx->debug_mode == 0 &&
+        !(ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) && !ctx->no_split) {
+        const uint32_t steps_per_chunk = (ctx->cfg.edge + 2) / 2 - 1, steps_per_brick = ctx->cfg.edge / 8;
+        const uint32_t parts_wanted = std::min(MAX_PARTS, std::max(1u, 2u * resident / n_work[0]));
+        if (parts_wanted >= 2) {
+            for (uint32_t w = 0; w < n_work[0]; ++w) {
+                const uint32_t chunk = order.empty() ? w : order[w];
+                const uint64_t dirty = descs[chunk].dirty_microbricks;
+                uint32_t lo = steps_per_chunk, hi = 1;   // first / last step that can hold a dirty cell
+                for (uint32_t mz = 0; mz < 4; ++mz)
+                    if ((dirty >> (16 * mz)) & 0xffffull) {
+                        lo = std::min(lo, mz * steps_per_brick + 1);
+                        hi = std::max(hi, (mz + 1) * steps_per_brick);
+                    }
+                const uint32_t span = hi - lo + 1, parts = std::min(parts_wanted, span);
+                for (uint32_t q = 0; q < parts; ++q)
+                    items.push_back({chunk, static_cast<uint8_t>(lo + span * q / parts), static_cast<uint8_t>(lo + span * (q + 1) / parts - 1),
+                                     static_cast<uint8_t>(q), static_cast<uint8_t>(parts)});
+            }
+            if (items.size() > MAX_SPLIT_ITEMS) items.clear();
+        }
+    }
     if ((rc = upload_descs(ctx, ctx->d_descs, descs, n))) return rc;
     ctx->n_regular = n;
     // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope
+    if (!items.empty())
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(SplitItem), cudaMemcpyHostToDevice, ctx->stream));
     if (!order.empty())
         HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, order.data(), static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 
@@ -396,6 +431,12 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         p.order = order.empty() ? nullptr : ctx->d_order + first;
         p.n_chunks = count;
         p.n_work = n_work[k];
+        if (!items.empty()) {   // the items are already in start order
+            p.order = nullptr;
+            p.items = ctx->d_items;
+            p.item_totals = ctx->d_item_totals;
+            p.n_work = static_cast<uint32_t>(items.size());
+        }
         p.chunk_base = first;
         for (uint32_t i = 0; i < count && !p.any_partial; ++i)
             p.any_partial = descs[first + i].dirty_microbricks != ~0ull && descs[first + i].dirty_microbricks != 0 &&
@@ -411,7 +452,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         if (p.n_work != 0) {
             cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
-            ctx->launches += (p.cells != nullptr && !p.first_generation) ? 3 : 1;  // + the two record kernels
+            ctx->launches += ((p.cells != nullptr && !p.first_generation) ? 3 : 1) + (p.items != nullptr ? 1 : 0);  // + record kernels, + counting walk
         } else if (p.cells != nullptr) {  // nothing to extract, but the scan blocks of the sub-batch still report it
             cudaError_t e = launch_regular_records(static_cast<int>(ctx->cfg.edge), p, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular_records");
@@ -688,6 +729,8 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if (c.max_transition_vertices != 0 && (rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_order, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_uniform, c.max_chunks))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_items, MAX_SPLIT_ITEMS))) return bail(rc);
+    if ((rc = small_alloc(ctx, &ctx->d_item_totals, MAX_SPLIT_ITEMS))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_index, c.max_chunks))) return bail(rc);
@@ -725,6 +768,8 @@ void hvx_destroy(hvx_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
     cudaFree(ctx->d_uniform);
+    cudaFree(ctx->d_items);
+    cudaFree(ctx->d_item_totals);
     if (ctx->h_ranges) cudaFreeHost(ctx->h_ranges);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -763,8 +808,10 @@ int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
 
 int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
-    if (mode > 2) return fail(ctx, HVX_E_INVALID_ARGUMENT, "debug mode must be 0 (off), 1 (stream only) or 2 (stream + sign bits)");
-    ctx->debug_mode = mode;
+    if ((mode & 0xffu) > 2 || (mode & ~0x1ffu))
+        return fail(ctx, HVX_E_INVALID_ARGUMENT, "debug mode must be 0 (off), 1 (stream only) or 2 (stream + sign bits), optionally | 0x100 (no split walk)");
+    ctx->debug_mode = mode & 0xffu;
+    ctx->no_split = (mode & 0x100u) != 0;
     return HVX_OK;
 }
 

@@ -897,13 +897,15 @@ struct SmemD {
     uint64_t q_free[NQ];
     uint64_t active[C::RS][C::STEP_ROWS];  // per step (ring slot of its newest slab): active-cell bits per row
     uint64_t tile_prefix[32];              // chained tile totals: vertices | indices<<22 | tag<<44
-    uint64_t chunk_total[4];               // totals after the last tile of the newest finished step, same packing
+    uint64_t chunk_total[16];              // totals after the last tile of the newest finished step of work item kc & 15
+                                           // (the queue is 16 deep, so an item 16 later cannot be published before every
+                                           // warp has left this item's CHUNK_END entry)
     uint32_t bits[3][C::BW];               // solid bits of the last three slabs (front warps only)
     uint32_t q_ctr[NQ];                    // next tile of the entry
     uint32_t q_done[NQ];                   // finished tiles of the entry
     uint32_t wtot[C::RS][C::PWS];          // active cells per classifying warp
     uint32_t wlayer[C::NW][8];             // per emission warp: ring word offset of sample layer z0 + d
-    uint32_t chunk_ids[4];
+    uint32_t chunk_ids[8];                 // work item of the CTA's k-th walk, k & 7 (an item is at least three slabs, the ring six)
     uint16_t rowrank[C::RS][C::STEP_ROWS]; // first cell rank of a row, relative to its classifying warp
     uint16_t case_info[256];
     alignas(16) uint8_t class_index[16 * 16];
@@ -928,10 +930,31 @@ struct DecoupledCfg {
     static_assert(CW <= 4 && C::RS <= 15 && C::NSLAB <= 255, "queue entry packing");
 };
 
+// One walk of a CTA: a whole chunk, or (SPLIT) one z-range of a chunk.  Steps [j0 + 1, s_last] are classified and
+// emitted; slabs [j0, j1] are streamed (j1 = s_last + 1 only lends its first layer to the +z gradient of step s_last).
+struct WorkItem {
+    uint32_t chunk;
+    int j0, j1, s_last;
+    uint32_t tag;  // SPLIT: item index | part << 24 | is-last-part << 28
+};
+template <class C, bool SPLIT>
+__device__ __forceinline__ WorkItem work_item(const RegularParams& p, uint32_t id) {
+    if (!SPLIT) return {id, 0, C::NSLAB - 1, C::NSLAB - 1, 0u};
+    const SplitItem it = p.items[id];
+    const int s_last = it.s_last;
+    return {it.chunk, static_cast<int>(it.s_first) - 1, min(s_last + 1, C::NSLAB - 1), s_last,
+            id | (static_cast<uint32_t>(it.part) << 24) | ((it.part + 1u == it.parts ? 1u : 0u) << 28)};
+}
+
 // PARTIAL: the batch holds partially dirty chunks (incremental edits): slabs no dirty step reads are neither
 // fetched nor balloted nor classified.  A separate instantiation, so the fully dirty batches (the headline) keep
 // the front-end loop free of the per-slab test and its registers (measured: 0.804 vs 0.814 ms with it compiled in).
-template <class C, bool PARTIAL>
+// SPLIT: the work list names z-ranges of chunks (SplitItem) instead of chunks, so that a few chunks still fill the
+// machine (the latency configurations: one page, an edit frame).  Placement across the parts of a chunk is a
+// look-back over per-part totals in global memory: a first launch in MODE_COUNT walks every part without emitting
+// and leaves its totals in item_totals; the extraction launch starts part q at the sum of parts 0 .. q-1, and the
+// chunk's last part writes the chunk's records.  Output is byte-identical to the unsplit walk.
+template <class C, bool PARTIAL, bool SPLIT>
 __global__ void __launch_bounds__(DecoupledCfg<C>::NT_ALL, C::E == 32 ? HVX_E32_CTAS : 1)
 regular_extract_decoupled_kernel(const RegularParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -950,7 +973,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     for (int i = tid; i < 256; i += D::NT_ALL) sm.class_index[i] = HVX_REGULAR_CLASS_INDEX[i / 16][i % 16];
     for (int i = tid; i < 3 * C::BW; i += D::NT_ALL) sm.bits[i / C::BW][i % C::BW] = 0u;  // incl. zero padding
     if (tid < 32) sm.tile_prefix[tid] = ~0ull;                                            // no tile has this tag yet
-    if (tid < 4) sm.chunk_total[tid] = ~0ull;
+    if (tid < 16) sm.chunk_total[tid] = ~0ull;
     if (tid == 0) {
         for (int i = 0; i < RS; ++i) {
             mbar_init(&sm.full_bar[i], 1);
@@ -975,15 +998,16 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 // the work list: every chunk in index order, or the caller's list -- heaviest chunks first when the batch
                 // carries cost hints, chunks flagged uniform left out (a chunk's slot does not depend on when it runs)
                 const uint32_t id = ticket < p.n_work ? (p.order != nullptr ? p.order[ticket] : ticket) : 0xffffffffu;
-                sm.chunk_ids[k & 3] = id;
-                if (id >= p.n_chunks) {
+                sm.chunk_ids[k & 7] = id;
+                if (id == 0xffffffffu) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     mbar_arrive(&sm.full_bar[slot]);
                     break;
                 }
-                const uint32_t* src = p.samples + static_cast<size_t>(id) * chunk_words;
-                const uint64_t need = PARTIAL ? slabs_of_steps(dirty_steps<C>(p.descs[id].dirty_microbricks)) : ~0ull;
-                for (int j = 0; j < C::NSLAB; ++j) {
+                const WorkItem it = work_item<C, SPLIT>(p, id);
+                const uint32_t* src = p.samples + static_cast<size_t>(it.chunk) * chunk_words;
+                const uint64_t need = PARTIAL ? slabs_of_steps(dirty_steps<C>(p.descs[it.chunk].dirty_microbricks)) : ~0ull;
+                for (int j = it.j0; j <= it.j1; ++j) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     HVX_JIT(30);
                     if ((need >> j) & 1ull) {
@@ -1010,18 +1034,19 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         int bcur = 0, bprev = 2;  // bits ring: slab j in bits[bcur], slab j-1 in bits[bprev]
         for (uint32_t kc = 0;; ++kc) {
             uint64_t dirty = 0, need = ~0ull;
-            for (int j = 0; j < C::NSLAB; ++j) {
-                mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+            // the first wait of a walk is for its first slab (or the sentinel): only then is the work item known
+            mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+            const uint32_t id = sm.chunk_ids[kc & 7];
+            if (id == 0xffffffffu) return;
+            const WorkItem it = work_item<C, SPLIT>(p, id);
+            dirty = p.descs[it.chunk].dirty_microbricks;
+            if (PARTIAL) need = slabs_of_steps(dirty_steps<C>(dirty));
+            for (int j = it.j0; j <= it.j1; ++j) {
+                if (j != it.j0) mbar_wait_parked(&sm.full_bar[slot], round & 1u);
                 HVX_JIT(20);
-                if (j == 0) {
-                    const uint32_t chunk = sm.chunk_ids[kc & 3];
-                    if (chunk >= p.n_chunks) return;
-                    dirty = p.descs[chunk].dirty_microbricks;
-                    if (PARTIAL) need = slabs_of_steps(dirty_steps<C>(dirty));
-                }
                 // a slab no dirty step reads was not fetched: no ballots, and its own step (not dirty) has no cells
                 const bool live = !PARTIAL || ((need >> j) & 1ull);
-                const bool classify = j >= 1 && live && p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY;
+                const bool classify = j > it.j0 && j <= it.s_last && live && p.mode != MODE_STREAM_ONLY && p.mode != MODE_BITS_ONLY;
                 if (live && p.mode != MODE_STREAM_ONLY) {
                     // P1: LDS, sign test, VOTE, STS for this warp's ballot blocks.  The warps that classify afterwards
                     // take one block of every group of GB, the others three, so the classifying warps (the critical
@@ -1125,23 +1150,25 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         };
         for (uint32_t kc = 0;; ++kc) {
             mbar_wait_parked(&sm.full_bar[slot], round & 1u);
-            const uint32_t chunk = sm.chunk_ids[kc & 3];
-            if (chunk >= p.n_chunks) {
+            const uint32_t id = sm.chunk_ids[kc & 7];
+            if (id == 0xffffffffu) {
                 publish(QK_EXIT << 30, 0, 0, 0, 0, 0, 0, 0);
                 return;
             }
+            const WorkItem it = work_item<C, SPLIT>(p, id);
+            const uint32_t chunk = it.chunk;
             const ChunkDesc desc = p.descs[chunk];
             const uint64_t dirty = desc.dirty_microbricks;
             const uint32_t tmask = desc.transition_mask & 0x3fu;
             const uint32_t chunk_first_tile = tile_total;
             uint32_t chunk_cells = 0;
             bool prev_empty = false;
-            for (int j = 0; j < C::NSLAB; ++j) {
+            for (int j = it.j0; j <= it.j1; ++j) {
                 mbar_wait_parked(&sm.rec_bar[slot], round & 1u);
                 HVX_JIT(10);
                 const int prev_slot = slot == 0 ? RS - 1 : slot - 1;
-                if (j == 0) {
-                    // slab 0 has no steps -1 and 0: make their arrivals; slab 1 gets "step 0 done" next round
+                if (j == it.j0) {
+                    // the walk's first slab has no steps j0 - 1 and j0: make their arrivals; the next slab gets "step j0 done" next round
                     mbar_arrive(&sm.empty_bar[slot]);
                     mbar_arrive(&sm.empty_bar[slot]);
                     prev_empty = true;
@@ -1161,18 +1188,18 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     } else {
                         const uint32_t next_parity = (slot + 1 == RS ? round + 1u : round) & 1u;
                         const uint32_t w0 = static_cast<uint32_t>(slot) | (static_cast<uint32_t>(j) << 4) | (tmask << 12) |
-                                            ((kc & 3u) << 18) | ((tile_total == chunk_first_tile ? 1u : 0u) << 20) |
-                                            (next_parity << 21) | (QK_STEP << 30);
-                        publish(w0, chunk, n, tile_total, cum[0], cum[1], cum[2], 0u);
+                                            ((kc & 15u) << 18) | ((tile_total == chunk_first_tile ? 1u : 0u) << 22) |
+                                            (next_parity << 23) | (QK_STEP << 30);
+                        publish(w0, chunk, n, tile_total, cum[0], cum[1], cum[2], it.tag);
                         tile_total += (n + D::TC - 1u) / D::TC;
                         chunk_cells += n;
                         prev_empty = false;
                     }
                 }
-                if (j == C::NSLAB - 1) {
-                    mbar_arrive(&sm.empty_bar[slot]);  // the last slab has no step NSLAB
-                    publish((QK_CHUNK_END << 30) | ((kc & 3u) << 18), chunk, chunk_cells, tile_total - 1u,
-                            static_cast<uint32_t>(dirty), static_cast<uint32_t>(dirty >> 32), 0u,
+                if (j == it.j1) {
+                    mbar_arrive(&sm.empty_bar[slot]);  // the walk's last slab has no step j1 + 1
+                    publish((QK_CHUNK_END << 30) | ((kc & 15u) << 18), chunk, chunk_cells, tile_total - 1u,
+                            static_cast<uint32_t>(dirty), static_cast<uint32_t>(dirty >> 32), it.tag,
                             tile_total != chunk_first_tile ? 1u : 0u);
                 }
                 if (++slot == RS) {
@@ -1198,11 +1225,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         const uint4 e1 = *reinterpret_cast<const uint4*>(&sm.queue[qi][4]);
         const uint32_t kind = e0.x >> 30;
         if (kind == QK_EXIT) return;
-        const uint32_t chunk = e0.y, kcpar = (e0.x >> 18) & 3u;
+        const uint32_t chunk = e0.y, kcpar = (e0.x >> 18) & 15u;
         if (kind == QK_CHUNK_END) {
             // ---- chunk epilogue: one warp waits for the chain's final totals and writes the records ----
             if (static_cast<int>(k % NW) == ew && lane == 0) {
-                uint32_t v_tot = 0, i_tot = 0;
+                uint32_t v_tot = 0, i_tot = 0, cells = e0.z;
                 if (e1.w != 0u) {
                     const volatile uint64_t* tot = &sm.chunk_total[kcpar];
                     const uint64_t want = static_cast<uint64_t>(e0.w & 0xfffffu);
@@ -1213,6 +1240,26 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     v_tot = static_cast<uint32_t>(got & FIELD);
                     i_tot = static_cast<uint32_t>((got >> 22) & FIELD);
                 }
+                bool records = true;
+                if (SPLIT) {
+                    const uint32_t item = e1.z & 0xffffffu, part = (e1.z >> 24) & 15u;
+                    if (p.mode == MODE_COUNT) {
+                        // look-back state of this part: what it adds to the chunk (the counting walk starts every part at zero)
+                        p.item_totals[item] = make_uint4(v_tot, i_tot, cells, 1u);
+                        records = false;
+                    } else if (!((e1.z >> 28) & 1u)) {
+                        records = false;  // the chunk's last part reports for the chunk
+                    } else {
+                        v_tot = i_tot = cells = 0u;
+                        for (uint32_t q = 0; q <= part; ++q) {
+                            const uint4 t = p.item_totals[item - part + q];
+                            v_tot += t.x;
+                            i_tot += t.y;
+                            cells += t.z;
+                        }
+                    }
+                }
+                if (records) {
                 const uint64_t dirty = static_cast<uint64_t>(e1.x) | (static_cast<uint64_t>(e1.y) << 32);
                 const uint32_t vo = v_tot > p.max_vertices ? 1u : 0u, io = i_tot > p.max_indices ? 1u : 0u;
                 const bool ok = !(vo | io) && do_emit;
@@ -1228,7 +1275,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 p.counters[chunk] = ec;
                 hvx_classify_counters cc;
                 cc.visited_cells = static_cast<uint32_t>(__popcll(dirty)) * (C::QW * C::QW * C::QW);
-                cc.active_cells = e0.z;
+                cc.active_cells = cells;
                 cc.vertices = v_tot;
                 cc.triangles = i_tot / 3u;
                 p.classify[chunk] = cc;
@@ -1238,10 +1285,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 rg.first_index = (p.chunk_base + chunk) * p.max_indices;
                 rg.index_count = ok ? i_tot : 0u;
                 p.ranges[chunk] = rg;
+                }
             }
         } else {
             const int slot = e0.x & 15u, st = (e0.x >> 4) & 255u;
-            const uint32_t tmask = (e0.x >> 12) & 63u, first_of_chunk = (e0.x >> 20) & 1u, next_parity = (e0.x >> 21) & 1u;
+            const uint32_t tmask = (e0.x >> 12) & 63u, first_of_chunk = (e0.x >> 22) & 1u, next_parity = (e0.x >> 23) & 1u;
             const uint32_t n_cells = e0.z, tile_base = e0.w;
             const uint32_t cum[3] = {e1.x, e1.y, e1.z};
             const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
@@ -1360,6 +1408,18 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         got = __shfl_sync(0xffffffffu, got, 0);
                         if (!first) base = got & ((1ull << 44) - 1ull);
                     }
+                    if (SPLIT && first && p.mode != MODE_COUNT) {
+                        // look-back across the parts of the chunk: this part starts where parts 0 .. q-1 end (their totals
+                        // were left by the counting launch)
+                        const uint32_t item = e1.w & 0xffffffu, part = (e1.w >> 24) & 15u;
+                        uint64_t bv = 0, bi = 0;
+                        for (uint32_t q = 0; q < part; ++q) {
+                            const uint4 t = p.item_totals[item - part + q];
+                            bv += t.x;
+                            bi += t.y;
+                        }
+                        base = bv | (bi << 22);
+                    }
                     HVX_CHECK((base & FIELD) + tot_v <= FIELD && ((base >> 22) & FIELD) + tot_i <= FIELD, 5u, chunk, st | (slot << 8), seq,
                               static_cast<uint32_t>(base), static_cast<uint32_t>(base >> 32));
                     HVX_JIT(5);
@@ -1465,10 +1525,14 @@ cudaError_t launch_first_generation(const RegularParams& p, const DeviceInfo& de
 template <class C>
 cudaError_t launch_decoupled(const RegularParams& p, const DeviceInfo& dev, cudaStream_t stream) {
     static_assert(sizeof(SmemD<C>) <= 232448, "shared memory budget (227 KB per CTA)");
-    static int ctas[2][64];
-    if (p.any_partial)
-        return launch_persistent(regular_extract_decoupled_kernel<C, true>, ctas[1], DecoupledCfg<C>::NT_ALL, sizeof(SmemD<C>), p, dev, stream);
-    return launch_persistent(regular_extract_decoupled_kernel<C, false>, ctas[0], DecoupledCfg<C>::NT_ALL, sizeof(SmemD<C>), p, dev, stream);
+    static int ctas[4][64];
+    constexpr int NT = DecoupledCfg<C>::NT_ALL;
+    if (p.items != nullptr) {
+        if (p.any_partial) return launch_persistent(regular_extract_decoupled_kernel<C, true, true>, ctas[3], NT, sizeof(SmemD<C>), p, dev, stream);
+        return launch_persistent(regular_extract_decoupled_kernel<C, false, true>, ctas[2], NT, sizeof(SmemD<C>), p, dev, stream);
+    }
+    if (p.any_partial) return launch_persistent(regular_extract_decoupled_kernel<C, true, false>, ctas[1], NT, sizeof(SmemD<C>), p, dev, stream);
+    return launch_persistent(regular_extract_decoupled_kernel<C, false, false>, ctas[0], NT, sizeof(SmemD<C>), p, dev, stream);
 }
 
 }  // namespace
@@ -1477,9 +1541,9 @@ cudaError_t launch_decoupled(const RegularParams& p, const DeviceInfo& dev, cuda
 #define HVX_STR(x) HVX_STR2(x)
 const char* regular_kernel_name(int edge, bool first_generation, bool partial) {
     if (first_generation) return edge == 64 ? "regular_extract_kernel<Cfg<64,2,6,16>>" : "regular_extract_kernel<Cfg<32,2,10,8>>";
-    if (edge == 64) return partial ? "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,true>" : "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,false>";
-    return partial ? "regular_extract_decoupled_kernel<Cfg<32,1," HVX_STR(HVX_E32_RS) "," HVX_STR(HVX_E32_NW) ">,true>"
-                   : "regular_extract_decoupled_kernel<Cfg<32,1," HVX_STR(HVX_E32_RS) "," HVX_STR(HVX_E32_NW) ">,false>";
+    if (edge == 64) return partial ? "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,true,false>" : "regular_extract_decoupled_kernel<Cfg<64,1,6,20>,false,false>";
+    return partial ? "regular_extract_decoupled_kernel<Cfg<32,1," HVX_STR(HVX_E32_RS) "," HVX_STR(HVX_E32_NW) ">,true,false>"
+                   : "regular_extract_decoupled_kernel<Cfg<32,1," HVX_STR(HVX_E32_RS) "," HVX_STR(HVX_E32_NW) ">,false,false>";
 }
 
 size_t regular_smem_bytes(int edge) {
@@ -1501,10 +1565,21 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     q.cells = nullptr;  // per-cell records come from regular_records.cu
     q.offsets = nullptr;
     q.blocks = nullptr;
-    if (edge == 64) e = launch_decoupled<Cfg64D>(q, dev, stream);
-    else if (edge == 32) e = launch_decoupled<Cfg32D>(q, dev, stream);
-    else return cudaErrorInvalidValue;
-    if (e != cudaSuccess) return e;
+    // split walk: the counting launch leaves every part's totals, the extraction launch looks back over them
+    for (int pass = q.items != nullptr ? 0 : 1; pass < 2; ++pass) {
+        RegularParams r = q;
+        if (pass == 0) {
+            if (q.mode != MODE_EXTRACT) continue;  // classify-only dispatches are never split (hvx_api.cu)
+            r.mode = MODE_COUNT;
+        } else if (q.items != nullptr) {
+            e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
+            if (e != cudaSuccess) return e;
+        }
+        if (edge == 64) e = launch_decoupled<Cfg64D>(r, dev, stream);
+        else if (edge == 32) e = launch_decoupled<Cfg32D>(r, dev, stream);
+        else return cudaErrorInvalidValue;
+        if (e != cudaSuccess) return e;
+    }
     return launch_regular_records(edge, p, stream);
 }
 

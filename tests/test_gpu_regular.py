@@ -428,3 +428,73 @@ def test_uniform_flag_on_a_surface_chunk_empties_it():
     with pytest.raises(H.HvxError, match="unknown descriptor flags"):
         batch.ctx.extract_regular(None, H.make_descs(3, flags=[0, 2, 0]), 3)
     batch.close()
+
+
+@pytest.mark.parametrize("edge,n", [(32, 1), (32, 7), (32, 60), (64, 1), (64, 5), (64, 40), (64, 147)])
+def test_split_walk_equals_the_whole_chunk_walk(edge, n):
+    """A dispatch with fewer chunks than resident CTAs walks z-ranges of chunks (counting launch + look-back over
+    per-part totals).  Counters, classify counters, ranges and every mesh byte must equal the unsplit walk
+    (hvx_debug_set_mode 0x100) -- with transition masks, partially dirty and empty-dirty chunks, cost hints, uniform
+    flags -- and the oracle."""
+    rng = np.random.default_rng(100 * edge + n)
+    side = int(np.ceil(n ** 0.5))
+    pages = np.array([[x - 1, (-1, -1, 0, -2)[(x + z) % 4] if edge == 64 else (-2, -1, -2, -3)[(x + z) % 4], z - 2]
+                      for z in range(side) for x in range(side)][:n], dtype=np.int64)
+    mv, mi = (49_152, 73_728) if edge == 64 else (12_288, 18_432)
+    batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=mv, max_indices=mi)
+    batch.fill_density(O.FIELD_TERRAIN_FBM, pages)
+    masks = [int(m) for m in rng.integers(0, 64, n)]
+    dirty = [ALL] * n
+    for i in range(1, n, 3):
+        dirty[i] = int(rng.integers(1, 1 << 62)) if i % 2 else 0xFFFF << (16 * int(rng.integers(0, 4)))
+    if n > 4:
+        dirty[4] = 0
+    hints = [int(h) for h in rng.integers(0, 1000, n)]
+    flags = [H._ffi.HVX_CHUNK_UNIFORM if (i % 11 == 10) else 0 for i in range(n)]
+    descs = H.make_descs(n, 5, dirty, masks, cost_hint=hints, flags=flags)
+
+    def run():
+        batch.ctx.extract_regular(None, descs, n)
+        c, r, k = batch.counters(n).copy(), batch.ranges(n).copy(), batch.classify_counters(n).copy()
+        v, i, packed = batch.ctx.read_meshes(0, 0, n)
+        return c, r, k, v.copy(), i.copy(), packed.copy()
+
+    launches0 = batch.ctx.launch_count
+    split = run()
+    split_launches = batch.ctx.launch_count - launches0
+    batch.ctx.debug_set_mode(0x100)
+    launches0 = batch.ctx.launch_count
+    whole = run()
+    whole_launches = batch.ctx.launch_count - launches0
+    batch.ctx.debug_set_mode(0)
+    assert split_launches == whole_launches + 1, "the split walk adds exactly the counting launch"
+    for a, b in zip(split, whole):
+        assert a.tobytes() == b.tobytes()
+    again = run()
+    for a, b in zip(split, again):
+        assert a.tobytes() == b.tobytes()
+    assert int(split[0]["emitted_vertices"].astype(np.int64).sum()) > 1000
+    words = (edge + 2) ** 3
+    for k in sorted({0, n // 2, n - 1}):
+        if flags[k]:
+            continue
+        s = batch.ctx.read(H._ffi.BUF_SAMPLES, k * words, words)
+        want = O.extract_regular(s, edge=edge, transition_mask=masks[k], dirty_microbricks=dirty[k], generation=5, debug=False)
+        r = split[5][k]
+        assert r["vertex_count"] == len(want.vertices) and r["index_count"] == len(want.indices), k
+        assert_vertices_equal(split[3][r["first_vertex"]:r["first_vertex"] + r["vertex_count"]], want.vertices, f"chunk {k}")
+        assert np.array_equal(split[4][r["first_index"]:r["first_index"] + r["index_count"]], want.indices), k
+    batch.close()
+
+
+def test_split_walk_overflow_is_reported_for_the_chunk():
+    """Capacity is a property of the chunk, not of a part: one element short anywhere suppresses the whole emission."""
+    samples = O.fixture_fill(O.FIELD_PLANE, [0, -1, 0])
+    for capacity in [(4095, 6144), (4096, 6143), (2000, 100_000)]:
+        ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig.new(*capacity), debug_records=False)
+        ex.dispatch(samples, 9, ALL, 0)
+        c = ex.counters_buffer()
+        assert c["completed"] == 1 and c["required_vertices"] == 4096 and c["required_indices"] == 6144
+        assert c["emitted_vertices"] == 0 and c["emitted_indices"] == 0
+        assert (c["vertex_overflow"] != 0) == (capacity[0] < 4096) and (c["index_overflow"] != 0) == (capacity[1] < 6144)
+        ex.close()
