@@ -284,12 +284,21 @@ class Context:
         residency / table / jobs: numpy structured arrays (helio_b200.gather dtypes); atlas: numpy uint32
         array or a torch tensor (host or device) of 32^3-word tiles in linear order."""
         residency = np.ascontiguousarray(residency)
-        table = np.ascontiguousarray(table)
+        table = None if table is None else np.ascontiguousarray(table)     # None: the table bound with bind_page_table
         jobs = np.ascontiguousarray(jobs)
         aptr, awords, keep = _input_pointer(atlas)
-        self._check(self._lib.hvx_gather_surface(self._handle, C.c_void_p(residency.ctypes.data), C.c_void_p(table.ctypes.data),
+        self._check(self._lib.hvx_gather_surface(self._handle, C.c_void_p(residency.ctypes.data),
+                                                 C.c_void_p(table.ctypes.data if table is not None else 0),
                                                  aptr, awords, C.c_void_p(jobs.ctypes.data), len(jobs)))
         del keep
+
+    def bind_page_table(self, table):
+        """hvx_gather_bind_table: keep the page table resident on the device (``None`` unbinds)."""
+        if table is None:
+            self._check(self._lib.hvx_gather_bind_table(self._handle, None, 0))
+            return
+        table = np.ascontiguousarray(table)
+        self._check(self._lib.hvx_gather_bind_table(self._handle, C.c_void_p(table.ctypes.data), len(table)))
 
     def read_meshlets(self, chunk, kind=0):
         """Host copy of one chunk's (descriptors, bounds) after build_meshlets."""

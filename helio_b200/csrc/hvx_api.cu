@@ -54,6 +54,8 @@ struct hvx_ctx {
     uint64_t heights_cols = 0;
     void* stage[3] = {nullptr, nullptr, nullptr};  // gather inputs staged from the host: table, atlas, jobs
     uint64_t stage_bytes[3] = {0, 0, 0};
+    void* bound_table = nullptr;      // hvx_gather_bind_table: the page table, resident until the next bind
+    uint64_t bound_table_bytes = 0;
     uint32_t* d_work = nullptr;       // [2] work counters (regular, transition)
     hvx_range* d_packed = nullptr;    // [max_chunks] packed placement for hvx_read_meshes
     void* pack_v = nullptr;           // staging for hvx_read_meshes
@@ -761,6 +763,7 @@ void hvx_destroy(hvx_ctx* ctx) {
     cudaFree(ctx->d_col_lod);
     cudaFree(ctx->d_heights);
     for (void* b : ctx->stage) cudaFree(b);
+    cudaFree(ctx->bound_table);
     cudaFree(ctx->d_work);
     cudaFree(ctx->d_packed);
     cudaFree(ctx->pack_v);
@@ -1015,7 +1018,8 @@ int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_p
     if (ctx->cfg.edge != 32) return fail(ctx, HVX_E_INVALID_ARGUMENT, "surface gather needs edge 32 (the residency page edge), ctx has %u", ctx->cfg.edge);
     if (n > ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
     if (n == 0) return HVX_OK;
-    if (!residency || !table || !atlas || !jobs) return fail(ctx, HVX_E_INVALID_ARGUMENT, "residency, table, atlas and jobs must be non-NULL");
+    if (!residency || !atlas || !jobs) return fail(ctx, HVX_E_INVALID_ARGUMENT, "residency, atlas and jobs must be non-NULL");
+    if (!table && !ctx->bound_table) return fail(ctx, HVX_E_INVALID_ARGUMENT, "table is NULL and no table is bound (hvx_gather_bind_table)");
     const hvx_residency& r = *residency;
     if ((r.table_mask & (r.table_mask + 1u)) != 0u) return fail(ctx, HVX_E_INVALID_ARGUMENT, "page table capacity must be a power of two (mask %#x)", r.table_mask);
     if (r.max_probe == 0u || r.max_probe > r.table_mask + 1u) return fail(ctx, HVX_E_INVALID_ARGUMENT, "max_probe %u must be in [1, capacity %u]", r.max_probe, r.table_mask + 1u);
@@ -1040,7 +1044,15 @@ int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_p
     if ((rc = ensure_buffer(ctx, HVX_BUF_GATHER_COUNTERS))) return rc;
     if ((rc = ensure_buffer(ctx, HVX_BUF_GATHER_INDIRECT))) return rc;
     const void *d_table = nullptr, *d_atlas = nullptr, *d_jobs = nullptr;
-    if ((rc = stage_input(ctx, 0, table, (static_cast<uint64_t>(r.table_mask) + 1) * sizeof(hvx_page_table_entry), &d_table))) return rc;
+    const uint64_t table_bytes = (static_cast<uint64_t>(r.table_mask) + 1) * sizeof(hvx_page_table_entry);
+    if (table == nullptr) {
+        if (ctx->bound_table_bytes != table_bytes)
+            return fail(ctx, HVX_E_INVALID_ARGUMENT, "table is NULL and the bound table holds %llu bytes, the residency uniform needs %llu",
+                        static_cast<unsigned long long>(ctx->bound_table_bytes), static_cast<unsigned long long>(table_bytes));
+        d_table = ctx->bound_table;
+    } else if ((rc = stage_input(ctx, 0, table, table_bytes, &d_table))) {
+        return rc;
+    }
     if ((rc = stage_input(ctx, 1, atlas, atlas_words * 4, &d_atlas))) return rc;
     if ((rc = stage_input(ctx, 2, jobs, static_cast<uint64_t>(n) * sizeof(hvx_gather_job), &d_jobs))) return rc;
     HVX_CUDA(ctx, cudaMemsetAsync(ctx->buf[HVX_BUF_GATHER_COUNTERS], 0, static_cast<size_t>(n) * sizeof(hvx_gather_counters), ctx->stream));
@@ -1058,6 +1070,29 @@ int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_p
     cudaError_t e = launch_gather(p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_gather");
     ctx->launches += 2;
+    return HVX_OK;
+}
+
+int hvx_gather_bind_table(hvx_ctx* ctx, const hvx_page_table_entry* table, uint32_t entries) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    DeviceGuard guard(ctx->device);
+    if (ctx->bound_table) {
+        HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->bound_table);
+        ctx->allocated -= ctx->bound_table_bytes;
+        ctx->bound_table = nullptr;
+        ctx->bound_table_bytes = 0;
+    }
+    if (!table || entries == 0) return HVX_OK;  // unbind
+    if ((entries & (entries - 1)) != 0) return fail(ctx, HVX_E_INVALID_ARGUMENT, "page table capacity must be a power of two, got %u", entries);
+    const uint64_t bytes = static_cast<uint64_t>(entries) * sizeof(hvx_page_table_entry);
+    cudaError_t e = cudaMalloc(&ctx->bound_table, bytes);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(page table)");
+    ctx->bound_table_bytes = bytes;
+    ctx->allocated += bytes;
+    // host or device source; the caller's array may change as soon as this returns
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->bound_table, table, bytes, cudaMemcpyDefault, ctx->stream));
+    HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HVX_OK;
 }
 

@@ -157,11 +157,17 @@ class GpuSurfaceSampler:
         self._ctx = context
         self._jobs = None
 
+    def bind_table(self, table) -> None:
+        """Upload the page table once; later ``dispatch(residency, None, ...)`` calls use the resident copy."""
+        table_entries = table.entries() if isinstance(table, PageTable) else table
+        self._ctx.bind_page_table(None if table_entries is None else np.ascontiguousarray(table_entries, dtype=PAGE_TABLE_ENTRY_DTYPE))
+
     def dispatch(self, residency, table, atlas, jobs) -> None:
         table_entries = table.entries() if isinstance(table, PageTable) else table
         self._jobs = np.ascontiguousarray(jobs, dtype=GATHER_JOB_DTYPE).copy()
         self._ctx.gather_surface(np.ascontiguousarray(residency, dtype=RESIDENCY_UNIFORM_DTYPE),
-                                 np.ascontiguousarray(table_entries, dtype=PAGE_TABLE_ENTRY_DTYPE), atlas, self._jobs)
+                                 None if table_entries is None else np.ascontiguousarray(table_entries, dtype=PAGE_TABLE_ENTRY_DTYPE),
+                                 atlas, self._jobs)
 
     def counters_buffer(self, n=None) -> np.ndarray:
         n = len(self._jobs) if n is None else n

@@ -344,7 +344,8 @@ typedef struct {
  * Counters have the reference's values (table_probes counts one lookup per gathered sample);
  * HVX_BUF_GATHER_INDIRECT[k] holds the eight DispatchIndirectArgs finalize_gather publishes.
  * A job whose residency epoch does not match the uniform gathers nothing, like the shader.
- *   table:  HOST or DEVICE, table_mask + 1 entries.
+ *   table:  HOST or DEVICE, table_mask + 1 entries; NULL = the table bound with hvx_gather_bind_table (a host table is
+ *           otherwise staged on every call).
  *   atlas:  HOST or DEVICE, R32Uint texels of the 3-D atlas in linear order, x fastest:
  *           (32 tiles_x) x (32 tiles_y) x (32 tiles_z) words; page slot s occupies the 32^3 tile at
  *           tile coordinates (s % tiles_x, (s / tiles_x) % tiles_y, s / (tiles_x tiles_y)).
@@ -353,6 +354,11 @@ typedef struct {
  * (samples = NULL), with no host round trip of the 480 KB per page. */
 int hvx_gather_surface(hvx_ctx* ctx, const hvx_residency* residency, const hvx_page_table_entry* table,
                        const uint32_t* atlas, uint64_t atlas_words, const hvx_gather_job* jobs, uint32_t n);
+/* Keep the open-addressed page table resident on the ctx's device: copied once (HOST or DEVICE source, `entries` a power
+ * of two), used by every later hvx_gather_surface that passes table = NULL, until the next bind.  The residency layer
+ * republishes its table when the publication epoch advances (PV/src/table.rs:62-72): bind then, not per dispatch.
+ * table = NULL or entries = 0 unbinds. */
+int hvx_gather_bind_table(hvx_ctx* ctx, const hvx_page_table_entry* table, uint32_t entries);
 
 /* ---- surface publication (the step after extraction in the reference's pass) -------- */
 /* GpuSurfaceJob (PV/src/render.rs:466-480) */

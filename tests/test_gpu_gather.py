@@ -121,6 +121,29 @@ def test_gather_then_extract_equals_extracting_the_canonical_block():
     ctx.close()
 
 
+def test_bound_page_table_stays_resident():
+    """hvx_gather_bind_table: the table is uploaded once, dispatches with table = NULL use it; rebinding replaces it."""
+    atlas, job, _ = reference_scene()
+    ctx = make_ctx()
+    sampler = H.GpuSurfaceSampler(ctx)
+    with pytest.raises(H.HvxError, match="no table is bound"):
+        sampler.dispatch(atlas.residency(), None, atlas.words, job)
+    sampler.bind_table(atlas.table.entries)
+    for _ in range(2):
+        ctx.write(_ffi.BUF_SAMPLES, np.zeros(34 ** 3, dtype=np.uint32))
+        sampler.dispatch(atlas.residency(), None, atlas.words, job)
+        assert np.array_equal(sampler.regular_samples(0), R.expected_regular(2, (-1, -2, 1)))
+        assert check_job(sampler, 0, atlas, job[0:1], 0x3F)["completed"] == 1
+    dropped, job2, _ = reference_scene(drop=(2, (-2, -2, 1)))
+    sampler.bind_table(dropped.table.entries)       # a new publication: one more upload
+    sampler.dispatch(dropped.residency(), None, dropped.words, job2)
+    assert check_job(sampler, 0, dropped, job2, 0x3F)["page_misses"] > 0
+    sampler.bind_table(None)
+    with pytest.raises(H.HvxError, match="no table is bound"):
+        sampler.dispatch(atlas.residency(), None, atlas.words, job)
+    ctx.close()
+
+
 def test_errors():
     atlas, job, _ = reference_scene(mask=0)
     with pytest.raises(ValueError):
