@@ -35,7 +35,8 @@ struct hvx_ctx {
     hvx_range* h_ranges = nullptr;       // pinned, [max_chunks]: ranges on their way to the host
     uint32_t* d_uniform = nullptr;       // [max_chunks] chunks flagged HVX_CHUNK_UNIFORM
     SplitItem* d_items = nullptr;        // [MAX_SPLIT_ITEMS] z-ranges of chunks, when a dispatch is too small to fill the machine
-    uint4* d_item_totals = nullptr;      // [MAX_SPLIT_ITEMS] per-part totals (the look-back state of the split walk)
+    uint4* d_item_totals = nullptr;      // [MAX_SPLIT_ITEMS] per-part totals (the look-back state of the split walk), zeroed once
+    uint32_t split_generation = 0;       // tag of the newest split dispatch
     void* buf[HVX_BUF_COUNT] = {};
     uint64_t buf_bytes[HVX_BUF_COUNT] = {};
     ChunkDesc* d_descs = nullptr;     // [max_chunks] descriptors of the last REGULAR dispatch
@@ -437,6 +438,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
             p.order = nullptr;
             p.items = ctx->d_items;
             p.item_totals = ctx->d_item_totals;
+            p.split_generation = ++ctx->split_generation;
             p.n_work = static_cast<uint32_t>(items.size());
         }
         p.chunk_base = first;
@@ -454,7 +456,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         if (p.n_work != 0) {
             cudaError_t e = launch_regular(static_cast<int>(ctx->cfg.edge), p, ctx->dev, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular");
-            ctx->launches += ((p.cells != nullptr && !p.first_generation) ? 3 : 1) + (p.items != nullptr ? 1 : 0);  // + record kernels, + counting walk
+            ctx->launches += ((p.cells != nullptr && !p.first_generation) ? 3 : 1) ;  // + the two record kernels
         } else if (p.cells != nullptr) {  // nothing to extract, but the scan blocks of the sub-batch still report it
             cudaError_t e = launch_regular_records(static_cast<int>(ctx->cfg.edge), p, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular_records");
@@ -733,6 +735,8 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((rc = small_alloc(ctx, &ctx->d_uniform, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_items, MAX_SPLIT_ITEMS))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_item_totals, MAX_SPLIT_ITEMS))) return bail(rc);
+    if ((e = cudaMemsetAsync(ctx->d_item_totals, 0, MAX_SPLIT_ITEMS * sizeof(uint4), ctx->stream)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
     if ((rc = small_alloc(ctx, &ctx->d_pages, 3ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_index, c.max_chunks))) return bail(rc);

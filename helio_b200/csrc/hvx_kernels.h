@@ -23,7 +23,6 @@ enum : uint32_t {
     MODE_CLASSIFY = 1,
     MODE_STREAM_ONLY = 2,
     MODE_BITS_ONLY = 3,
-    MODE_COUNT = 4,  // split walks only: classify and count, leave each part's totals in item_totals (no chunk records)
 };
 
 // One z-range of a chunk (a work item of the split walk): steps [s_first, s_last] of the chunk's NSLAB - 1 steps,
@@ -39,7 +38,8 @@ struct RegularParams {
     const uint32_t* order;    // nullable, [n_work] device: the k-th chunk (split walk: item) to start (descending cost hints;
                               // chunks flagged uniform are left out)
     const SplitItem* items;   // nullable, device: the split walk's work items; ids in `order` / tickets then name items
-    uint4* item_totals;       // [items] device: (vertices, indices, active cells, 1) of every part, written by MODE_COUNT
+    uint4* item_totals;       // [items] device: (vertices, indices, active cells, generation) of every part: the look-back state
+    uint32_t split_generation;  // tag of this dispatch's look-back entries (never 0, never repeated while the ctx lives)
     uint32_t n_chunks;        // chunks addressed by this launch (ids are < n_chunks)
     uint32_t n_work;          // chunks it actually walks (== n_chunks when order is NULL)
     uint32_t chunk_base;      // batch index of this launch's chunk 0 (a sub-batch of a pipelined dispatch); every pointer

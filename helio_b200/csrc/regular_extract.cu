@@ -946,14 +946,36 @@ __device__ __forceinline__ WorkItem work_item(const RegularParams& p, uint32_t i
             id | (static_cast<uint32_t>(it.part) << 24) | ((it.part + 1u == it.parts ? 1u : 0u) << 28)};
 }
 
+// Look-back state of the split walk: item_totals[i] = (vertices, indices, active cells, generation).  A part's counting
+// walk stores the three totals, fences, then stores the dispatch's generation; readers spin on the generation (parts
+// are claimed in ascending order, so a part's predecessors are always running or done: no dead-lock) and fence before
+// they read the totals.
+__device__ __forceinline__ void publish_part(uint4* totals, uint32_t v, uint32_t i, uint32_t cells, uint32_t generation) {
+    volatile uint32_t* w = reinterpret_cast<volatile uint32_t*>(totals);
+    w[0] = v;
+    w[1] = i;
+    w[2] = cells;
+    __threadfence();
+    w[3] = generation;
+}
+__device__ __forceinline__ uint4 wait_part(const uint4* totals, uint32_t generation) {
+    const volatile uint32_t* w = reinterpret_cast<const volatile uint32_t*>(totals);
+    while (w[3] != generation) {
+    }
+    __threadfence();
+    return make_uint4(w[0], w[1], w[2], generation);
+}
+
 // PARTIAL: the batch holds partially dirty chunks (incremental edits): slabs no dirty step reads are neither
 // fetched nor balloted nor classified.  A separate instantiation, so the fully dirty batches (the headline) keep
 // the front-end loop free of the per-slab test and its registers (measured: 0.804 vs 0.814 ms with it compiled in).
 // SPLIT: the work list names z-ranges of chunks (SplitItem) instead of chunks, so that a few chunks still fill the
-// machine (the latency configurations: one page, an edit frame).  Placement across the parts of a chunk is a
-// look-back over per-part totals in global memory: a first launch in MODE_COUNT walks every part without emitting
-// and leaves its totals in item_totals; the extraction launch starts part q at the sum of parts 0 .. q-1, and the
-// chunk's last part writes the chunk's records.  Output is byte-identical to the unsplit walk.
+// machine (the latency configurations: one page, an edit frame).  Placement across the parts of a chunk is a decoupled
+// look-back over per-part totals in global memory: every part is walked twice by its CTA -- the counting walk
+// classifies, counts and publishes (vertices, indices, cells) tagged with the dispatch's generation; the emitting walk
+// starts at the sum of the parts before it, spinning on their tags if they are not there yet (parts are claimed in
+// ascending order, so predecessors are running or done) -- and the chunk's last part writes the chunk's records.
+// Output is byte-identical to the unsplit walk.
 template <class C, bool PARTIAL, bool SPLIT>
 __global__ void __launch_bounds__(DecoupledCfg<C>::NT_ALL, C::E == 32 ? HVX_E32_CTAS : 1)
 regular_extract_decoupled_kernel(const RegularParams p) {
@@ -992,14 +1014,14 @@ regular_extract_decoupled_kernel(const RegularParams p) {
     if (warp == FW + NW) {
         if (lane == 0) {
             int slot = 0;
-            uint32_t round = 0;
-            for (uint32_t k = 0;; ++k) {
+            uint32_t round = 0, k = 0;  // k: walks of this CTA so far
+            for (;;) {
                 const uint32_t ticket = atomicAdd(p.work_counter, 1u);
                 // the work list: every chunk in index order, or the caller's list -- heaviest chunks first when the batch
                 // carries cost hints, chunks flagged uniform left out (a chunk's slot does not depend on when it runs)
                 const uint32_t id = ticket < p.n_work ? (p.order != nullptr ? p.order[ticket] : ticket) : 0xffffffffu;
-                sm.chunk_ids[k & 7] = id;
                 if (id == 0xffffffffu) {
+                    sm.chunk_ids[k & 7] = id;
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     mbar_arrive(&sm.full_bar[slot]);
                     break;
@@ -1007,6 +1029,10 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 const WorkItem it = work_item<C, SPLIT>(p, id);
                 const uint32_t* src = p.samples + static_cast<size_t>(it.chunk) * chunk_words;
                 const uint64_t need = PARTIAL ? slabs_of_steps(dirty_steps<C>(p.descs[it.chunk].dirty_microbricks)) : ~0ull;
+                // SPLIT: a part is walked twice -- the counting walk publishes its totals, the emitting walk looks back over
+                // the parts before it (the second stream of its few slabs comes out of L2)
+                for (uint32_t pass = SPLIT ? 0u : 1u; pass < 2u; ++pass, ++k) {
+                sm.chunk_ids[k & 7] = id | (SPLIT ? pass << 30 : 0u);
                 for (int j = it.j0; j <= it.j1; ++j) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
                     HVX_JIT(30);
@@ -1022,6 +1048,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         ++round;
                     }
                 }
+                }
             }
         }
         return;
@@ -1036,9 +1063,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             uint64_t dirty = 0, need = ~0ull;
             // the first wait of a walk is for its first slab (or the sentinel): only then is the work item known
             mbar_wait_parked(&sm.full_bar[slot], round & 1u);
-            const uint32_t id = sm.chunk_ids[kc & 7];
-            if (id == 0xffffffffu) return;
-            const WorkItem it = work_item<C, SPLIT>(p, id);
+            const uint32_t idw = sm.chunk_ids[kc & 7];
+            if (idw == 0xffffffffu) return;
+            const WorkItem it = work_item<C, SPLIT>(p, idw & 0x3fffffffu);
             dirty = p.descs[it.chunk].dirty_microbricks;
             if (PARTIAL) need = slabs_of_steps(dirty_steps<C>(dirty));
             for (int j = it.j0; j <= it.j1; ++j) {
@@ -1150,12 +1177,13 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         };
         for (uint32_t kc = 0;; ++kc) {
             mbar_wait_parked(&sm.full_bar[slot], round & 1u);
-            const uint32_t id = sm.chunk_ids[kc & 7];
-            if (id == 0xffffffffu) {
+            const uint32_t idw = sm.chunk_ids[kc & 7];
+            if (idw == 0xffffffffu) {
                 publish(QK_EXIT << 30, 0, 0, 0, 0, 0, 0, 0);
                 return;
             }
-            const WorkItem it = work_item<C, SPLIT>(p, id);
+            WorkItem it = work_item<C, SPLIT>(p, idw & 0x3fffffffu);
+            it.tag |= (idw >> 30) << 29;  // SPLIT: bit 29 = the emitting walk
             const uint32_t chunk = it.chunk;
             const ChunkDesc desc = p.descs[chunk];
             const uint64_t dirty = desc.dirty_microbricks;
@@ -1243,16 +1271,16 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 bool records = true;
                 if (SPLIT) {
                     const uint32_t item = e1.z & 0xffffffu, part = (e1.z >> 24) & 15u;
-                    if (p.mode == MODE_COUNT) {
-                        // look-back state of this part: what it adds to the chunk (the counting walk starts every part at zero)
-                        p.item_totals[item] = make_uint4(v_tot, i_tot, cells, 1u);
+                    if (!((e1.z >> 29) & 1u)) {
+                        // counting walk: what this part adds to the chunk (every part counts from zero)
+                        publish_part(&p.item_totals[item], v_tot, i_tot, cells, p.split_generation);
                         records = false;
                     } else if (!((e1.z >> 28) & 1u)) {
                         records = false;  // the chunk's last part reports for the chunk
                     } else {
                         v_tot = i_tot = cells = 0u;
                         for (uint32_t q = 0; q <= part; ++q) {
-                            const uint4 t = p.item_totals[item - part + q];
+                            const uint4 t = wait_part(&p.item_totals[item - part + q], p.split_generation);
                             v_tot += t.x;
                             i_tot += t.y;
                             cells += t.z;
@@ -1292,6 +1320,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             const uint32_t tmask = (e0.x >> 12) & 63u, first_of_chunk = (e0.x >> 22) & 1u, next_parity = (e0.x >> 23) & 1u;
             const uint32_t n_cells = e0.z, tile_base = e0.w;
             const uint32_t cum[3] = {e1.x, e1.y, e1.z};
+            const bool emit = do_emit && (!SPLIT || ((e1.w >> 29) & 1u));  // SPLIT: the counting walk writes no mesh
             const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
             HVX_JIT(2);
             // "are there tiles left" must be ONE decision per warp: the counter moves while the lanes look at it, and
@@ -1408,13 +1437,13 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         got = __shfl_sync(0xffffffffu, got, 0);
                         if (!first) base = got & ((1ull << 44) - 1ull);
                     }
-                    if (SPLIT && first && p.mode != MODE_COUNT) {
-                        // look-back across the parts of the chunk: this part starts where parts 0 .. q-1 end (their totals
-                        // were left by the counting launch)
+                    if (SPLIT && first && emit) {
+                        // look-back across the parts of the chunk: this part starts where parts 0 .. q-1 end (their counting
+                        // walks publish the totals; every lane polls the same words)
                         const uint32_t item = e1.w & 0xffffffu, part = (e1.w >> 24) & 15u;
                         uint64_t bv = 0, bi = 0;
                         for (uint32_t q = 0; q < part; ++q) {
-                            const uint4 t = p.item_totals[item - part + q];
+                            const uint4 t = wait_part(&p.item_totals[item - part + q], p.split_generation);
                             bv += t.x;
                             bi += t.y;
                         }
@@ -1433,7 +1462,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         *const_cast<volatile uint64_t*>(&sm.tile_prefix[seq & 31u]) = mine;
                     }
                     __syncwarp();
-                    if (do_emit) {
+                    if (emit) {
                         const uint32_t v_base = static_cast<uint32_t>(base & FIELD);
                         const uint32_t i_base = static_cast<uint32_t>((base >> 22) & FIELD);
                         if (valid) {
@@ -1565,21 +1594,10 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     q.cells = nullptr;  // per-cell records come from regular_records.cu
     q.offsets = nullptr;
     q.blocks = nullptr;
-    // split walk: the counting launch leaves every part's totals, the extraction launch looks back over them
-    for (int pass = q.items != nullptr ? 0 : 1; pass < 2; ++pass) {
-        RegularParams r = q;
-        if (pass == 0) {
-            if (q.mode != MODE_EXTRACT) continue;  // classify-only dispatches are never split (hvx_api.cu)
-            r.mode = MODE_COUNT;
-        } else if (q.items != nullptr) {
-            e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
-            if (e != cudaSuccess) return e;
-        }
-        if (edge == 64) e = launch_decoupled<Cfg64D>(r, dev, stream);
-        else if (edge == 32) e = launch_decoupled<Cfg32D>(r, dev, stream);
-        else return cudaErrorInvalidValue;
-        if (e != cudaSuccess) return e;
-    }
+    if (edge == 64) e = launch_decoupled<Cfg64D>(q, dev, stream);
+    else if (edge == 32) e = launch_decoupled<Cfg32D>(q, dev, stream);
+    else return cudaErrorInvalidValue;
+    if (e != cudaSuccess) return e;
     return launch_regular_records(edge, p, stream);
 }
 

@@ -311,6 +311,9 @@ def page_pass_case(H, torch, device, local_rank, stream=None):
     gctx = H.Context(local_rank, edge=32, max_chunks=nj, max_vertices=12288, max_indices=18432)
     gctx.set_stream(stream.cuda_stream)
     sampler = H.GpuSurfaceSampler(gctx)
+    r_staged = timed(torch, stream, lambda: sampler.dispatch(res, table, atlas, jobs), 2, 10)   # page table staged from the host per call
+    sampler.bind_table(table)                                                                  # resident from here on (hvx_gather_bind_table)
+    table = None
     r_g = timed(torch, stream, lambda: sampler.dispatch(res, table, atlas, jobs), 2, 10)
     pub = H.SurfacePublisher(gctx, nj)
     meta = np.zeros(nj, dtype=H.PAGE_META_DTYPE)
@@ -335,7 +338,8 @@ def page_pass_case(H, torch, device, local_rank, stream=None):
     ec = gctx.read(H._ffi.BUF_REGULAR_COUNTERS, 0, nj)
     out = {
         "workload": f"{nj} pages of 32^3 gathered from a {n_pages}-page resident atlas", "jobs": nj,
-        "gather_ms": r_g["ms_median"], "gather_GBps_read_plus_write": 2 * nj * 34 ** 3 * 4 / (r_g["ms_median"] * 1e-3) / 1e9,
+        "gather_ms": r_g["ms_median"], "gather_ms_table_staged_per_call": r_staged["ms_median"],
+        "gather_GBps_read_plus_write": 2 * nj * 34 ** 3 * 4 / (r_g["ms_median"] * 1e-3) / 1e9,
         "whole_pass_ms": r_all["ms_median"], "pages_per_s": nj / (r_all["ms_median"] * 1e-3),
         "e2e_wall_ms": wall * 1e3, "e2e_pages_per_s": nj / wall,
         "e2e_h2d_bytes": int(jobs.nbytes + sjobs.nbytes + chunks.nbytes + meta.nbytes), "e2e_d2h_bytes": 32,
