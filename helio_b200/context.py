@@ -76,6 +76,8 @@ def make_descs(n, generation=1, dirty_microbricks=(1 << 64) - 1, transition_mask
     arr = np.zeros(max(n, 1), dtype=_DESC_DTYPE)
 
     def column(value, mask):
+        if isinstance(value, np.ndarray) and value.dtype.kind in "ui":   # fast path: no per-element Python
+            return value[:n].astype(np.uint64) & np.uint64(mask)
         if hasattr(value, "__len__"):
             return np.array([int(v) & mask for v in value[:n]], dtype=np.uint64)
         return np.uint64(int(value) & mask)

@@ -39,6 +39,17 @@ struct hvx_ctx {
     uint32_t split_generation = 0;       // tag of the newest split dispatch
     void* buf[HVX_BUF_COUNT] = {};
     uint64_t buf_bytes[HVX_BUF_COUNT] = {};
+    // The per-dispatch host inputs of the regular path (descriptors, start order, skipped chunks, split items) travel
+    // in ONE copy: they are packed back to back in a pinned staging buffer (two of them, alternating, each guarded by
+    // an event) and land in one device block; the four pointers below point into it.
+    unsigned char* d_batch = nullptr;
+    uint64_t batch_bytes = 0;
+    unsigned char* h_batch[2] = {nullptr, nullptr};
+    cudaEvent_t batch_done[2] = {nullptr, nullptr};
+    uint32_t batch_flip = 0;
+    uint32_t* d_touched = nullptr;    // [max_chunks] hvx_apply_edit: chunks whose samples the edit changes
+    std::vector<int64_t> edit_pages;  // page list / LODs hvx_apply_edit uploaded last (an edit frame repeats them)
+    std::vector<uint8_t> edit_lods;
     ChunkDesc* d_descs = nullptr;     // [max_chunks] descriptors of the last REGULAR dispatch
     ChunkDesc* d_tdescs = nullptr;    // [max_chunks] descriptors of the last TRANSITION dispatch
     uint32_t n_regular = 0, n_transition = 0;  // sizes of those dispatches (hvx_build_meshlets reads the generations)
@@ -375,13 +386,29 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
             if (items.size() > MAX_SPLIT_ITEMS) items.clear();
         }
     }
-    if ((rc = upload_descs(ctx, ctx->d_descs, descs, n))) return rc;
+    // ---- one upload for everything the host contributes to the dispatch -----------------------------------------
+    {
+        auto align16 = [](uint64_t v) { return (v + 15ull) & ~15ull; };
+        const uint64_t off_descs = 0, off_order = align16(off_descs + static_cast<uint64_t>(n) * sizeof(ChunkDesc));
+        const uint64_t off_uniform = align16(off_order + order.size() * sizeof(uint32_t));
+        const uint64_t off_items = align16(off_uniform + uniform.size() * sizeof(uint32_t));
+        const uint64_t bytes = align16(off_items + items.size() * sizeof(SplitItem));
+        const uint32_t flip = ctx->batch_flip ^= 1u;
+        HVX_CUDA(ctx, cudaEventSynchronize(ctx->batch_done[flip]));  // the copy that last read this staging buffer (two dispatches ago)
+        unsigned char* h = ctx->h_batch[flip];
+        static_assert(sizeof(hvx_chunk_desc) == sizeof(ChunkDesc), "desc layout");
+        memcpy(h + off_descs, descs, static_cast<size_t>(n) * sizeof(ChunkDesc));
+        if (!order.empty()) memcpy(h + off_order, order.data(), order.size() * sizeof(uint32_t));
+        if (!uniform.empty()) memcpy(h + off_uniform, uniform.data(), uniform.size() * sizeof(uint32_t));
+        if (!items.empty()) memcpy(h + off_items, items.data(), items.size() * sizeof(SplitItem));
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_batch, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        HVX_CUDA(ctx, cudaEventRecord(ctx->batch_done[flip], ctx->stream));
+        ctx->d_descs = reinterpret_cast<ChunkDesc*>(ctx->d_batch + off_descs);
+        ctx->d_order = reinterpret_cast<uint32_t*>(ctx->d_batch + off_order);
+        ctx->d_uniform = reinterpret_cast<uint32_t*>(ctx->d_batch + off_uniform);
+        ctx->d_items = reinterpret_cast<SplitItem*>(ctx->d_batch + off_items);
+    }
     ctx->n_regular = n;
-    // pageable sources: cudaMemcpyAsync returns once they are staged, so the vectors may go out of scope
-    if (!items.empty())
-        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_items, items.data(), items.size() * sizeof(SplitItem), cudaMemcpyHostToDevice, ctx->stream));
-    if (!order.empty())
-        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, order.data(), static_cast<size_t>(n) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 
     RegularParams base{};
     base.mode = mode;
@@ -463,7 +490,6 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
             ctx->launches += 2;
         }
         if (k + 1 == n_sub && !uniform.empty()) {
-            HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_uniform, uniform.data(), uniform.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
             RegularParams q = base;
             q.descs = ctx->d_descs;
             q.counters = all_counters;
@@ -560,6 +586,8 @@ int run_fill(hvx_ctx* ctx, uint32_t kind, const int64_t* page_xyz, const uint8_t
         if ((rc = ensure_buffer(ctx, arena))) return rc;
         out = static_cast<uint32_t*>(ctx->buf[arena]);
     }
+    ctx->edit_pages.clear();  // d_pages / d_lod are about to hold this fill's list
+    ctx->edit_lods.clear();
     HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pages, page_xyz, static_cast<size_t>(n) * 3 * sizeof(int64_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
     if (lod) HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_lod, lod, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -729,11 +757,17 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((e = cudaEventCreateWithFlags(&ctx->handover, cudaEventDisableTiming)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaEventCreate"));
     int rc;
-    if ((rc = small_alloc(ctx, &ctx->d_descs, c.max_chunks))) return bail(rc);
+    ctx->batch_bytes = static_cast<uint64_t>(c.max_chunks) * (sizeof(ChunkDesc) + 8) + MAX_SPLIT_ITEMS * sizeof(SplitItem) + 64;
+    if ((rc = small_alloc(ctx, &ctx->d_batch, ctx->batch_bytes))) return bail(rc);
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_batch[i]), ctx->batch_bytes, cudaHostAllocDefault)) != cudaSuccess)
+            return bail(cuda_fail(ctx, e, "cudaHostAlloc"));
+        if ((e = cudaEventCreateWithFlags(&ctx->batch_done[i], cudaEventDisableTiming)) != cudaSuccess)
+            return bail(cuda_fail(ctx, e, "cudaEventCreate"));
+    }
+    if ((rc = small_alloc(ctx, &ctx->d_touched, c.max_chunks))) return bail(rc);
     if (c.max_transition_vertices != 0 && (rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
-    if ((rc = small_alloc(ctx, &ctx->d_order, c.max_chunks))) return bail(rc);
-    if ((rc = small_alloc(ctx, &ctx->d_uniform, c.max_chunks))) return bail(rc);
-    if ((rc = small_alloc(ctx, &ctx->d_items, MAX_SPLIT_ITEMS))) return bail(rc);
+
     if ((rc = small_alloc(ctx, &ctx->d_item_totals, MAX_SPLIT_ITEMS))) return bail(rc);
     if ((e = cudaMemsetAsync(ctx->d_item_totals, 0, MAX_SPLIT_ITEMS * sizeof(uint4), ctx->stream)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
@@ -743,6 +777,7 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((rc = small_alloc(ctx, &ctx->d_col_xz, 2ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_lod, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_work, 4))) return bail(rc);
+    if ((e = cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(uint32_t), ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
     if ((rc = small_alloc(ctx, &ctx->d_packed, c.max_chunks))) return bail(rc);
     for (int id = HVX_BUF_REGULAR_VERTICES; id <= HVX_BUF_TRANSITION_BLOCKS; ++id)  // meshlet arenas stay lazy
         if (arena_bytes(c, id) != 0 && (rc = ensure_buffer(ctx, id))) return bail(rc);
@@ -757,9 +792,13 @@ void hvx_destroy(hvx_ctx* ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     for (void*& b : ctx->buf)
         if (b) cudaFree(b);
-    cudaFree(ctx->d_descs);
+    cudaFree(ctx->d_batch);
+    cudaFree(ctx->d_touched);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->h_batch[i]) cudaFreeHost(ctx->h_batch[i]);
+        if (ctx->batch_done[i]) cudaEventDestroy(ctx->batch_done[i]);
+    }
     cudaFree(ctx->d_tdescs);
-    cudaFree(ctx->d_order);
     cudaFree(ctx->d_pages);
     cudaFree(ctx->d_lod);
     cudaFree(ctx->d_col_index);
@@ -774,8 +813,6 @@ void hvx_destroy(hvx_ctx* ctx) {
     cudaFree(ctx->pack_i);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
-    cudaFree(ctx->d_uniform);
-    cudaFree(ctx->d_items);
     cudaFree(ctx->d_item_totals);
     if (ctx->h_ranges) cudaFreeHost(ctx->h_ranges);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -899,17 +936,26 @@ int hvx_apply_edit(hvx_ctx* ctx, const hvx_voxel_edit* edit, const int64_t* page
         if ((rc = ensure_buffer(ctx, HVX_BUF_SAMPLES))) return rc;
         d_samples = static_cast<uint32_t*>(ctx->buf[HVX_BUF_SAMPLES]);
     }
-    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pages, page_xyz, static_cast<size_t>(n) * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    if (lod) HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_lod, lod, n, cudaMemcpyHostToDevice, ctx->stream));
-    else HVX_CUDA(ctx, cudaMemsetAsync(ctx->d_lod, 0, n, ctx->stream));
-    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_uniform, touched.data(), touched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // an edit frame names the same resident pages as the frame before: they are uploaded again only when they changed
+    // (compared by content; hvx_fill_* use the same device arrays, so they drop the cache)
+    const bool same_pages = ctx->edit_pages.size() == 3ull * n && memcmp(ctx->edit_pages.data(), page_xyz, 3ull * n * sizeof(int64_t)) == 0 &&
+                            ctx->edit_lods.size() == n && (lod ? memcmp(ctx->edit_lods.data(), lod, n) == 0
+                                                               : std::all_of(ctx->edit_lods.begin(), ctx->edit_lods.end(), [](uint8_t l) { return l == 0; }));
+    if (!same_pages) {
+        HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_pages, page_xyz, static_cast<size_t>(n) * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        if (lod) HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_lod, lod, n, cudaMemcpyHostToDevice, ctx->stream));
+        else HVX_CUDA(ctx, cudaMemsetAsync(ctx->d_lod, 0, n, ctx->stream));
+        ctx->edit_pages.assign(page_xyz, page_xyz + 3ull * n);
+        if (lod) ctx->edit_lods.assign(lod, lod + n); else ctx->edit_lods.assign(n, 0);
+    }
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_touched, touched.data(), touched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     EditParams p{};
     p.op = edit->op_type;
     p.material = edit->material;
     for (int a = 0; a < 3; ++a) p.center[a] = edit->center[a];
     p.radius = edit->radius;
     p.n_touched = static_cast<uint32_t>(touched.size());
-    p.ids = ctx->d_uniform;
+    p.ids = ctx->d_touched;
     p.page_xyz = ctx->d_pages;
     p.lod = ctx->d_lod;
     p.samples = d_samples;

@@ -247,7 +247,7 @@ def edit_latency_case(H, torch, device, local_rank, frames=220, warm_frames=20, 
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         dirty, touched = ctx.apply_edit(2, (cx, cy, cz), 1.5, pages)
-        ctx.extract_regular(None, H.make_descs(n, 10 + f, [int(d) for d in dirty]), n)
+        ctx.extract_regular(None, H.make_descs(n, 10 + f, dirty), n)
         e.record(stream)
         e.synchronize()
         if f >= warm_frames:
