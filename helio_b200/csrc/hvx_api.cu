@@ -48,6 +48,8 @@ struct hvx_ctx {
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
     uint32_t batch_flip = 0;
     uint32_t* d_touched = nullptr;    // [max_chunks] hvx_apply_edit: chunks whose samples the edit changes
+    uint32_t* h_touched = nullptr;    // pinned twin (the list goes up with a truly asynchronous copy)
+    cudaEvent_t touched_done = nullptr;
     std::vector<int64_t> edit_pages;  // page list / LODs hvx_apply_edit uploaded last (an edit frame repeats them)
     std::vector<uint8_t> edit_lods;
     ChunkDesc* d_descs = nullptr;     // [max_chunks] descriptors of the last REGULAR dispatch
@@ -339,7 +341,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         hinted |= descs[i].cost_hint != 0u;
         any_uniform |= (descs[i].flags & HVX_CHUNK_UNIFORM) != 0u || descs[i].dirty_microbricks == 0;
     }
-    std::vector<uint32_t> order, uniform, n_work(n_sub);
+    std::vector<uint32_t> order, uniform, n_work(n_sub), skipped_begin(n_sub + 1, 0);  // uniform: ids relative to their sub-batch
     if (hinted || any_uniform) order.resize(n);
     for (uint32_t k = 0; k < n_sub; ++k) {
         const uint32_t first = k * sub, count = std::min(sub, n - first);
@@ -350,10 +352,11 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         uint32_t m = 0;
         for (uint32_t i = 0; i < count; ++i) {
             // nothing to walk: flagged uniform, or no dirty microbrick (an edit frame re-submits every resident chunk)
-            if ((descs[first + i].flags & HVX_CHUNK_UNIFORM) || descs[first + i].dirty_microbricks == 0) uniform.push_back(first + i);
+            if ((descs[first + i].flags & HVX_CHUNK_UNIFORM) || descs[first + i].dirty_microbricks == 0) uniform.push_back(i);
             else order[first + m++] = i;  // ids are relative to the sub-batch
         }
         n_work[k] = m;
+        skipped_begin[k + 1] = static_cast<uint32_t>(uniform.size());
         // descending hint, ties in chunk order (the scheduler's LPT rule)
         if (hinted)
             std::stable_sort(order.begin() + first, order.begin() + first + m,
@@ -461,6 +464,8 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         p.order = order.empty() ? nullptr : ctx->d_order + first;
         p.n_chunks = count;
         p.n_work = n_work[k];
+        p.skipped = ctx->d_uniform + skipped_begin[k];
+        p.n_skipped = skipped_begin[k + 1] - skipped_begin[k];
         if (!items.empty()) {   // the items are already in start order
             p.order = nullptr;
             p.items = ctx->d_items;
@@ -489,13 +494,9 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_regular_records");
             ctx->launches += 2;
         }
-        if (k + 1 == n_sub && !uniform.empty()) {
-            RegularParams q = base;
-            q.descs = ctx->d_descs;
-            q.counters = all_counters;
-            q.classify = all_classify;
-            q.ranges = all_ranges;
-            cudaError_t e = launch_uniform_records(static_cast<int>(ctx->cfg.edge), q, ctx->d_uniform, static_cast<uint32_t>(uniform.size()), ctx->stream);
+        if (p.n_skipped != 0 && (p.n_work == 0 || p.first_generation)) {
+            // no decoupled launch to write the skipped chunks' records on the side: a small launch of its own
+            cudaError_t e = launch_uniform_records(static_cast<int>(ctx->cfg.edge), p, p.skipped, p.n_skipped, ctx->stream);
             if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_uniform_records");
             ctx->launches += 1;
         }
@@ -766,6 +767,9 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
             return bail(cuda_fail(ctx, e, "cudaEventCreate"));
     }
     if ((rc = small_alloc(ctx, &ctx->d_touched, c.max_chunks))) return bail(rc);
+    if ((e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_touched), static_cast<size_t>(c.max_chunks) * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
+        return bail(cuda_fail(ctx, e, "cudaHostAlloc"));
+    if ((e = cudaEventCreateWithFlags(&ctx->touched_done, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaEventCreate"));
     if (c.max_transition_vertices != 0 && (rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
 
     if ((rc = small_alloc(ctx, &ctx->d_item_totals, MAX_SPLIT_ITEMS))) return bail(rc);
@@ -794,6 +798,8 @@ void hvx_destroy(hvx_ctx* ctx) {
         if (b) cudaFree(b);
     cudaFree(ctx->d_batch);
     cudaFree(ctx->d_touched);
+    if (ctx->h_touched) cudaFreeHost(ctx->h_touched);
+    if (ctx->touched_done) cudaEventDestroy(ctx->touched_done);
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_batch[i]) cudaFreeHost(ctx->h_batch[i]);
         if (ctx->batch_done[i]) cudaEventDestroy(ctx->batch_done[i]);
@@ -948,7 +954,10 @@ int hvx_apply_edit(hvx_ctx* ctx, const hvx_voxel_edit* edit, const int64_t* page
         ctx->edit_pages.assign(page_xyz, page_xyz + 3ull * n);
         if (lod) ctx->edit_lods.assign(lod, lod + n); else ctx->edit_lods.assign(n, 0);
     }
-    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_touched, touched.data(), touched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    HVX_CUDA(ctx, cudaEventSynchronize(ctx->touched_done));  // the previous edit's copy has left the pinned list
+    memcpy(ctx->h_touched, touched.data(), touched.size() * sizeof(uint32_t));
+    HVX_CUDA(ctx, cudaMemcpyAsync(ctx->d_touched, ctx->h_touched, touched.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    HVX_CUDA(ctx, cudaEventRecord(ctx->touched_done, ctx->stream));
     EditParams p{};
     p.op = edit->op_type;
     p.material = edit->material;

@@ -37,6 +37,8 @@ struct RegularParams {
     const ChunkDesc* descs;   // [n] device
     const uint32_t* order;    // nullable, [n_work] device: the k-th chunk (split walk: item) to start (descending cost hints;
                               // chunks flagged uniform are left out)
+    const uint32_t* skipped;  // [n_skipped] device: chunks of this launch that are not walked (uniform / nothing dirty); the
+    uint32_t n_skipped;       // decoupled kernel writes their empty records itself (ids relative to this launch)
     const SplitItem* items;   // nullable, device: the split walk's work items; ids in `order` / tickets then name items
     uint4* item_totals;       // [items] device: (vertices, indices, active cells, generation) of every part: the look-back state
     uint32_t split_generation;  // tag of this dispatch's look-back entries (never 0, never repeated while the ctx lives)

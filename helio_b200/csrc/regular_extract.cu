@@ -941,6 +941,21 @@ struct DecoupledCfg {
     static_assert(CW <= 4 && C::RS <= 15 && C::NSLAB <= 255, "queue entry packing");
 };
 
+// Records of a chunk that is not walked at all (HVX_CHUNK_UNIFORM, or an empty dirty mask).
+template <class C>
+__device__ __forceinline__ void write_empty_records(const RegularParams& p, uint32_t chunk) {
+    hvx_emission_counters ec{};
+    ec.completed = 1u;
+    p.counters[chunk] = ec;
+    hvx_classify_counters cc{};
+    cc.visited_cells = static_cast<uint32_t>(__popcll(p.descs[chunk].dirty_microbricks)) * (C::QW * C::QW * C::QW);
+    p.classify[chunk] = cc;
+    hvx_range rg{};
+    rg.first_vertex = (p.chunk_base + chunk) * p.max_vertices;
+    rg.first_index = (p.chunk_base + chunk) * p.max_indices;
+    p.ranges[chunk] = rg;
+}
+
 // One walk of a CTA: a whole chunk, or (SPLIT) one z-range of a chunk.  Steps [j0 + 1, s_last] are classified and
 // emitted; slabs [j0, j1] are streamed (j1 = s_last + 1 only lends its first layer to the +z gradient of step s_last).
 struct WorkItem {
@@ -1023,6 +1038,14 @@ regular_extract_decoupled_kernel(const RegularParams p) {
 
     // ---- PRODUCER warp ------------------------------------------------------------------------
     if (warp == FW + NW) {
+        if (lane != 0) {
+            // Lanes 1..31 have nothing to stream: they write the records of the chunks the work list leaves out (flagged
+            // uniform, or no dirty microbrick): an empty, completed mesh.  Off everybody's critical path, and one launch
+            // less for an edit frame that re-submits 256 resident chunks of which two are dirty.
+            for (uint32_t i = blockIdx.x * 31u + static_cast<uint32_t>(lane) - 1u; i < p.n_skipped; i += gridDim.x * 31u)
+                write_empty_records<C>(p, p.skipped[i]);
+            return;
+        }
         if (lane == 0) {
             int slot = 0;
             uint32_t round = 0, k = 0;  // k: walks of this CTA so far

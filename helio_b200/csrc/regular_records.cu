@@ -100,8 +100,8 @@ __global__ void __launch_bounds__(128) uniform_records_kernel(const RegularParam
     cc.visited_cells = static_cast<uint32_t>(__popcll(p.descs[chunk].dirty_microbricks)) * microbrick_cells;
     p.classify[chunk] = cc;
     hvx_range rg{};
-    rg.first_vertex = chunk * p.max_vertices;
-    rg.first_index = chunk * p.max_indices;
+    rg.first_vertex = (p.chunk_base + chunk) * p.max_vertices;
+    rg.first_index = (p.chunk_base + chunk) * p.max_indices;
     p.ranges[chunk] = rg;
 }
 
