@@ -235,7 +235,7 @@ def edit_latency_case(H, torch, device, local_rank, frames=220, warm_frames=20, 
     full = H.make_descs(n)
     ctx.extract_regular(None, full, n)
     state = 1
-    dev_ms, wall_ms, dirty_chunks, dirty_bricks = [], [], [], []
+    dev_ms, wall_ms, edit_ms, dirty_chunks, dirty_bricks = [], [], [], [], []
     for f in range(frames):
         state = next_random(state)
         cx = (state % 1000) / 1000.0 * 100.0 - 50.0
@@ -244,15 +244,17 @@ def edit_latency_case(H, torch, device, local_rank, frames=220, warm_frames=20, 
         state = next_random(state)
         cy = -4.5 + (state % 1000) / 1000.0 * 4.0          # the terrain surface lies in [-6, 2] m
         t0 = time.perf_counter()
-        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record(stream)
         dirty, touched = ctx.apply_edit(2, (cx, cy, cz), 1.5, pages)
+        m.record(stream)
         ctx.extract_regular(None, H.make_descs(n, 10 + f, dirty), n)
         e.record(stream)
         e.synchronize()
         if f >= warm_frames:
             wall_ms.append((time.perf_counter() - t0) * 1e3)
             dev_ms.append(a.elapsed_time(e))
+            edit_ms.append(a.elapsed_time(m))
             dirty_chunks.append(int(np.count_nonzero(dirty)))
             dirty_bricks.append(int(sum(bin(int(d)).count("1") for d in dirty)))
     r_full = timed(torch, stream, lambda: ctx.extract_regular(None, full, n), 3, 30)
@@ -270,6 +272,8 @@ def edit_latency_case(H, torch, device, local_rank, frames=220, warm_frames=20, 
         "workload": "256x64^3 resident terrain chunks, one SubtractSphere(r = 1.5 m) per frame", "frames": len(d),
         "device_ms_p50": float(np.percentile(d, 50)), "device_ms_p95": float(np.percentile(d, 95)), "device_ms_p99": float(np.percentile(d, 99)),
         "wall_ms_p50": float(np.percentile(w, 50)), "wall_ms_p95": float(np.percentile(w, 95)), "wall_ms_p99": float(np.percentile(w, 99)),
+        "device_ms_p50_edit_only": float(np.percentile(np.array(edit_ms), 50)),
+        "device_ms_p50_extract_only": float(np.percentile(d - np.array(edit_ms), 50)),
         "dirty_chunks_per_frame_mean": float(np.mean(dirty_chunks)), "dirty_microbricks_per_frame_mean": float(np.mean(dirty_bricks)),
         "full_reextract_256_chunks_ms": r_full["ms_median"], "all_256_chunks_2x2x2_dirty_ms": r_all["ms_median"],
     }
