@@ -107,18 +107,26 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
 
     uint32_t n_samples = 0, n_probes = 0, n_misses = 0;
     if (regular) {
+        // One warp per sample row (fixed y, z): the 34 samples are the last texel of the page at -x, a whole 32-texel row
+        // of the page at 0 (contiguous and 128-byte aligned in the atlas: one coalesced load) and the first texel of the
+        // page at +x.  Page, tile row and miss / probe accounting are resolved once per row, not once per sample.
         uint32_t* out = p.samples + static_cast<size_t>(jobi) * REGULAR_COUNT;
-        for (int linear = threadIdx.x; linear < REGULAR_COUNT; linear += blockDim.x) {
-            const int x = linear % REGULAR_EDGE, y = (linear / REGULAR_EDGE) % REGULAR_EDGE, z = linear / (REGULAR_EDGE * REGULAR_EDGE);
-            const int cx = x - 1, cy = y - 1, cz = z - 1;  // cell coordinates relative to the page minimum
-            const int e = (page_of(cx) + 1) + 4 * (page_of(cy) + 1) + 16 * (page_of(cz) + 1);
-            const uint32_t origin = pg_origin[e];
-            uint32_t w = AIR;
-            if (origin != 0xffffffffu) w = __ldg(p.atlas + origin + local_of(cx) + local_of(cy) * row_words + local_of(cz) * slice_words);
-            else ++n_misses;
-            out[linear] = w;
-            n_probes += pg_probes[e];
-            ++n_samples;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int row = warp; row < REGULAR_EDGE * REGULAR_EDGE; row += 8) {
+            const int y = row % REGULAR_EDGE, z = row / REGULAR_EDGE;
+            const int cy = y - 1, cz = z - 1;
+            const int e_yz = 4 * (page_of(cy) + 1) + 16 * (page_of(cz) + 1);
+            const uint32_t row_off = local_of(cy) * row_words + local_of(cz) * slice_words;
+            const uint32_t o_m = pg_origin[e_yz + 0], o_0 = pg_origin[e_yz + 1], o_p = pg_origin[e_yz + 2];
+            uint32_t* dst = out + static_cast<size_t>(row) * REGULAR_EDGE;
+            dst[1 + lane] = o_0 != 0xffffffffu ? __ldg(p.atlas + o_0 + row_off + lane) : AIR;
+            if (lane == 0) dst[0] = o_m != 0xffffffffu ? __ldg(p.atlas + o_m + row_off + 31) : AIR;
+            if (lane == 1) dst[REGULAR_EDGE - 1] = o_p != 0xffffffffu ? __ldg(p.atlas + o_p + row_off) : AIR;
+            if (lane == 0) {  // the row's share of the per-sample counters
+                n_samples += REGULAR_EDGE;
+                n_probes += pg_probes[e_yz] + 32u * pg_probes[e_yz + 1] + pg_probes[e_yz + 2];
+                n_misses += (o_m == 0xffffffffu ? 1u : 0u) + (o_0 == 0xffffffffu ? 32u : 0u) + (o_p == 0xffffffffu ? 1u : 0u);
+            }
         }
     } else {
         uint32_t* out = p.slabs + static_cast<size_t>(jobi) * (6 * FACE_STRIDE) + static_cast<size_t>(face) * FACE_STRIDE;
