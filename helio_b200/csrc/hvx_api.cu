@@ -83,7 +83,7 @@ struct hvx_ctx {
 namespace {
 
 constexpr uint32_t MAX_SPLIT_ITEMS = 4096;  // a dispatch is only split while it has fewer chunks than resident CTAs (<= 444)
-constexpr uint32_t MAX_PARTS = 8;
+constexpr uint32_t MAX_PARTS = 16;  // SplitItem::part travels in four bits of a queue word
 
 thread_local std::string g_create_error;
 

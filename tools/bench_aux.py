@@ -55,9 +55,27 @@ def main():
     ex.context.fill_density(1, [[0, 0, 0]])
     descs = H.make_descs(1, 7)
     r = timed(stream, lambda: ex.context.extract_regular(None, descs, 1), 10, 50)
+    ex.context.debug_set_mode(0x100)
+    r_one = timed(stream, lambda: ex.context.extract_regular(None, descs, 1), 10, 50)
+    ex.context.debug_set_mode(0)
     c = ex.counters_buffer()
-    out.append({"case": "single_page_32_sphere", **r, "vertices": int(c["emitted_vertices"]), "triangles": int(c["emitted_indices"]) // 3,
+    out.append({"case": "single_page_32_sphere", **r, "ms_median_one_cta": r_one["ms_median"], "vertices": int(c["emitted_vertices"]), "triangles": int(c["emitted_indices"]) // 3,
                 "note": "reference wgpu/RTX 3060: 0.048 ms median (docs/planetary_voxel_extraction_benchmark.md:61)"})
+    ex.close()
+
+    # ---- one dense-adversarial 64^3 chunk (~6 vertices per cell): the worst case for "one CTA per chunk" ----------
+    cells = 64 ** 3
+    ex = H.TransvoxelGpuExtractor(0, H.TransvoxelGpuExtractorConfig(cells * 12, cells * 15), edge=64, debug_records=False)
+    ex.context.set_stream(stream.cuda_stream)
+    ex.context.fill_density(17, [[1, 2, 3]])
+    descs = H.make_descs(1, 7, transition_mask=0x3F)
+    r = timed(stream, lambda: ex.context.extract_regular(None, descs, 1), 3, 10)
+    ex.context.debug_set_mode(0x100)
+    r_whole = timed(stream, lambda: ex.context.extract_regular(None, descs, 1), 3, 10)
+    ex.context.debug_set_mode(0)
+    c = ex.counters_buffer()
+    out.append({"case": "single_chunk_64_dense_random", **r, "ms_median_one_cta": r_whole["ms_median"], "vertices": int(c["emitted_vertices"]),
+                "triangles": int(c["emitted_indices"]) // 3, "note": "split over 16 CTAs by z-range vs walked by one CTA"})
     ex.close()
 
     # ---- batch of the reference's page size ---------------------------------------------------------
