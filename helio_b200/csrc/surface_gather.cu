@@ -107,40 +107,18 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
 
     uint32_t n_samples = 0, n_probes = 0, n_misses = 0;
     if (regular) {
-        // One warp per sample row (fixed y, z): the 34 samples are the last texel of the page at -x, a whole 32-texel row
-        // of the page at 0 (contiguous and 128-byte aligned in the atlas: one coalesced load) and the first texel of the
-        // page at +x.  Page, tile row and miss / probe accounting are resolved once per row, not once per sample.
         uint32_t* out = p.samples + static_cast<size_t>(jobi) * REGULAR_COUNT;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        constexpr int ROWS = REGULAR_EDGE * REGULAR_EDGE, U = 4;  // four rows per step: four independent loads in flight per lane
-        for (int row0 = warp * U; row0 < ROWS; row0 += 8 * U) {
-            uint32_t mid[U], edge[U];
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                const int row = min(row0 + k, ROWS - 1);
-                const int cy = row % REGULAR_EDGE - 1, cz = row / REGULAR_EDGE - 1;
-                const int e_yz = 4 * (page_of(cy) + 1) + 16 * (page_of(cz) + 1);
-                const uint32_t row_off = local_of(cy) * row_words + local_of(cz) * slice_words;
-                const uint32_t o_m = pg_origin[e_yz + 0], o_0 = pg_origin[e_yz + 1], o_p = pg_origin[e_yz + 2];
-                mid[k] = o_0 != 0xffffffffu ? __ldg(p.atlas + o_0 + row_off + lane) : AIR;
-                // lane 0 fetches the -x halo texel, lane 1 the +x one
-                const uint32_t o_e = lane == 0 ? o_m : o_p;
-                edge[k] = AIR;
-                if (lane < 2 && o_e != 0xffffffffu) edge[k] = __ldg(p.atlas + o_e + row_off + (lane == 0 ? 31 : 0));
-                if (lane == 0 && row0 + k < ROWS) {  // the row's share of the per-sample counters
-                    n_samples += REGULAR_EDGE;
-                    n_probes += pg_probes[e_yz] + 32u * pg_probes[e_yz + 1] + pg_probes[e_yz + 2];
-                    n_misses += (o_m == 0xffffffffu ? 1u : 0u) + (o_0 == 0xffffffffu ? 32u : 0u) + (o_p == 0xffffffffu ? 1u : 0u);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < U; ++k) {
-                if (row0 + k >= ROWS) break;
-                uint32_t* dst = out + static_cast<size_t>(row0 + k) * REGULAR_EDGE;
-                dst[1 + lane] = mid[k];
-                if (lane == 0) dst[0] = edge[k];
-                if (lane == 1) dst[REGULAR_EDGE - 1] = edge[k];
-            }
+        for (int linear = threadIdx.x; linear < REGULAR_COUNT; linear += blockDim.x) {
+            const int x = linear % REGULAR_EDGE, y = (linear / REGULAR_EDGE) % REGULAR_EDGE, z = linear / (REGULAR_EDGE * REGULAR_EDGE);
+            const int cx = x - 1, cy = y - 1, cz = z - 1;  // cell coordinates relative to the page minimum
+            const int e = (page_of(cx) + 1) + 4 * (page_of(cy) + 1) + 16 * (page_of(cz) + 1);
+            const uint32_t origin = pg_origin[e];
+            uint32_t w = AIR;
+            if (origin != 0xffffffffu) w = __ldg(p.atlas + origin + local_of(cx) + local_of(cy) * row_words + local_of(cz) * slice_words);
+            else ++n_misses;
+            out[linear] = w;
+            n_probes += pg_probes[e];
+            ++n_samples;
         }
     } else {
         uint32_t* out = p.slabs + static_cast<size_t>(jobi) * (6 * FACE_STRIDE) + static_cast<size_t>(face) * FACE_STRIDE;
