@@ -90,7 +90,7 @@ class Ctx {
    private:
     hvx_ctx* ctx_ = nullptr;
 };
-inline hvx_chunk_desc desc(uint64_t generation, uint64_t dirty, uint32_t mask) { return {generation, dirty, mask, 0}; }
+inline hvx_chunk_desc desc(uint64_t generation, uint64_t dirty, uint32_t mask) { return {generation, dirty, mask, 0u, 0u, 0u}; }
 }  // namespace detail
 
 /// One page per dispatch, like the reference (PV/src/transvoxel_emit.rs:92-396).
@@ -172,6 +172,73 @@ class TransvoxelGpuTransitionExtractor {
     TransvoxelGpuTransitionExtractorConfig config_;
     detail::Ctx ctx_;
     uint64_t cells_;
+};
+
+/// The batch form the page queue feeds once it stops submitting one page per frame: N chunks per dispatch into
+/// fixed-stride per-chunk slots (chunk k at k * max_vertices / k * max_indices).  `prepare` validates and builds the
+/// descriptors (no device work), `encode` queues the extraction, `extract_to_host` adds the pipelined packed read-back
+/// -- the prepare / encode split of PV/src/transvoxel_emit.rs:256-330.
+class ChunkBatchExtractor {
+   public:
+    struct Request {
+        uint64_t generation = 1;
+        uint64_t dirty_microbricks = ~0ull;
+        uint8_t transition_mask = 0;
+        uint32_t cost_hint = 0;   // e.g. the chunk's vertex count last time: heaviest chunks start first
+        bool uniform = false;     // the producer knows the chunk holds no surface: not uploaded, not read
+    };
+    struct Meshes {
+        std::vector<hvx_vertex> vertices;  // back to back in chunk order
+        std::vector<uint32_t> indices;     // chunk-local values
+        std::vector<hvx_range> ranges;     // packed placement per chunk
+        std::vector<hvx_emission_counters> counters;
+    };
+
+    ChunkBatchExtractor(int device, uint32_t edge, uint32_t max_chunks, TransvoxelGpuExtractorConfig regular = {49152, 73728})
+        : edge_(edge), ctx_(device, hvx_config{edge, max_chunks, regular.max_vertices, regular.max_indices, 0, 0, 0u, 0}) {}
+
+    std::vector<hvx_chunk_desc> prepare(const std::vector<Request>& requests) const {
+        std::vector<hvx_chunk_desc> descs(requests.size());
+        for (size_t i = 0; i < requests.size(); ++i) {
+            if (requests[i].transition_mask & ~0x3fu) throw Error(HVX_E_TRANSITION_MASK, "transition mask uses bits outside the six page faces");
+            descs[i] = hvx_chunk_desc{requests[i].generation, requests[i].dirty_microbricks, requests[i].transition_mask,
+                                      requests[i].cost_hint, requests[i].uniform ? HVX_CHUNK_UNIFORM : 0u, 0u};
+        }
+        return descs;
+    }
+    uint64_t sample_words() const { return uint64_t(edge_ + 2) * (edge_ + 2) * (edge_ + 2); }
+    /// ExtractionFixture::new on the device for `n` pages (xyz triples); the samples stay in the ctx arena.
+    void fill(uint32_t kind, const int64_t* page_xyz, const uint8_t* lod, uint32_t n) { ctx_.check(hvx_fill_density(ctx_.get(), kind, page_xyz, lod, n, nullptr)); }
+    /// samples: host or device CellWords, or nullptr for the ctx arena.
+    void encode(const std::vector<hvx_chunk_desc>& descs, const uint32_t* samples = nullptr) {
+        const uint32_t n = static_cast<uint32_t>(descs.size());
+        ctx_.check(hvx_extract_regular(ctx_.get(), samples, n * sample_words(), descs.data(), n));
+    }
+    Meshes extract_to_host(const std::vector<hvx_chunk_desc>& descs, const uint32_t* samples, uint64_t vertex_capacity, uint64_t index_capacity) {
+        const uint32_t n = static_cast<uint32_t>(descs.size());
+        Meshes m{std::vector<hvx_vertex>(vertex_capacity), std::vector<uint32_t>(index_capacity), std::vector<hvx_range>(n),
+                 std::vector<hvx_emission_counters>(n)};
+        uint64_t tv = 0, ti = 0;
+        ctx_.check(hvx_extract_regular_to_host(ctx_.get(), samples, n * sample_words(), descs.data(), n, m.vertices.data(), vertex_capacity,
+                                               m.indices.data(), index_capacity, m.ranges.data(), m.counters.data(), &tv, &ti));
+        m.vertices.resize(tv);
+        m.indices.resize(ti);
+        return m;
+    }
+    /// One sphere edit (GpuVoxelEdit) on the resident samples of the `n` pages; returns the dirty microbricks per chunk.
+    std::vector<uint64_t> apply_edit(const hvx_voxel_edit& edit, const int64_t* page_xyz, const uint8_t* lod, uint32_t n, uint32_t* touched = nullptr) {
+        std::vector<uint64_t> dirty(n);
+        ctx_.check(hvx_apply_edit(ctx_.get(), &edit, page_xyz, lod, n, nullptr, dirty.data(), touched));
+        return dirty;
+    }
+    std::vector<hvx_emission_counters> counters_buffer(uint32_t n) const { return ctx_.read<hvx_emission_counters>(HVX_BUF_REGULAR_COUNTERS, 0, n); }
+    std::vector<hvx_range> ranges_buffer(uint32_t n) const { return ctx_.read<hvx_range>(HVX_BUF_REGULAR_RANGES, 0, n); }
+    void synchronize() { ctx_.check(hvx_synchronize(ctx_.get())); }
+    ResourceStats resource_stats() const { return ctx_.stats(); }
+
+   private:
+    uint32_t edge_;
+    detail::Ctx ctx_;
 };
 
 /// Batched GpuSurfaceSampler (PV/src/surface_sampling.rs:184-350): halo blocks + transition slabs of n jobs

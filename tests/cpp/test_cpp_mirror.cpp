@@ -49,6 +49,38 @@ int main() {
     tiny.dispatch(samples.data(), samples.size(), 2000, ~0ull, 0);
     const hvx_emission_counters t = tiny.counters_buffer();
     if (!(t.completed == 1 && t.vertex_overflow && t.index_overflow && t.emitted_vertices == 0 && t.required_vertices == 1323)) return 1;
+    // the batch form: fill three terrain chunks on the device, pipelined extraction + packed read-back, one sphere
+    // edit on the resident samples and the dirty re-extraction it asks for
+    {
+        ChunkBatchExtractor batch(0, 64, 3);
+        const int64_t pages[9] = {0, -1, 0, 1, -1, 0, 0, 4, 0};
+        batch.fill(16, pages, nullptr, 3);
+        std::vector<ChunkBatchExtractor::Request> requests(3);
+        requests[2].uniform = true;  // far above the terrain: the producer knows it is empty
+        const auto descs = batch.prepare(requests);
+        const ChunkBatchExtractor::Meshes m = batch.extract_to_host(descs, nullptr, 3 * 49152, 3 * 73728);
+        if (m.counters[0].emitted_vertices == 0 || m.counters[2].emitted_vertices != 0 || m.counters[2].completed != 1 ||
+            m.vertices.size() != size_t(m.counters[0].emitted_vertices) + m.counters[1].emitted_vertices ||
+            m.ranges[1].first_vertex != m.counters[0].emitted_vertices) {
+            std::printf("FAIL batch read-back\n");
+            return 1;
+        }
+        hvx_voxel_edit edit{0, 2, 0, {3.0f, -4.3f, 3.0f}, 0.8f, 0};  // SubtractSphere around the terrain surface
+        uint32_t touched = 0;
+        const std::vector<uint64_t> dirty = batch.apply_edit(edit, pages, nullptr, 3, &touched);
+        if (touched != 1 || dirty[0] == 0 || dirty[1] != 0 || dirty[2] != 0) {
+            std::printf("FAIL edit dirty set\n");
+            return 1;
+        }
+        for (size_t k = 0; k < 3; ++k) requests[k].dirty_microbricks = dirty[k];
+        requests[2].uniform = false;
+        batch.encode(batch.prepare(requests));
+        const auto after = batch.counters_buffer(3);
+        if (after[0].completed != 1 || after[0].vertex_overflow || after[1].emitted_vertices != 0 || after[2].emitted_vertices != 0 || after[2].completed != 1) {
+            std::printf("FAIL dirty re-extraction\n");
+            return 1;
+        }
+    }
     std::printf("OK cpp mirror: 1323 vertices / 661 triangles, errors and overflow contract as the reference\n");
     return 0;
 }
