@@ -82,8 +82,8 @@ struct hvx_ctx {
 
 namespace {
 
-constexpr uint32_t MAX_SPLIT_ITEMS = 4096;  // a dispatch is only split while it has fewer chunks than resident CTAs (<= 444)
-constexpr uint32_t MAX_PARTS = 8;   // measured: one 32^3 page 27 us on one CTA, 23 us on 8, 30 us on 16 (the look-back chain grows)
+constexpr uint32_t MAX_SPLIT_ITEMS = 8192;  // a dispatch is only split while it has fewer than 16 waves of chunks (16 x 444 resident CTAs)
+constexpr uint32_t MAX_PARTS = 16;  // the look-back reads all earlier parts at once (one lane each), so its cost does not grow with the parts
 
 thread_local std::string g_create_error;
 
@@ -367,10 +367,22 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
     // a counting launch leaves every part's totals, the extraction launch looks back over them (regular_extract.cu).
     std::vector<SplitItem> items;
     const uint32_t resident = static_cast<uint32_t>(ctx->dev.sm_count) * (ctx->cfg.edge == 32 ? 3u : 1u);
-    if (n_sub == 1 && n_work[0] != 0 && n_work[0] < resident && mode == MODE_EXTRACT && ctx->debug_mode == 0 &&
+    if (n_sub == 1 && n_work[0] != 0 && n_work[0] < 16u * resident && mode == MODE_EXTRACT && ctx->debug_mode == 0 &&
         !(ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) && !ctx->no_split) {
         const uint32_t steps_per_chunk = (ctx->cfg.edge + 2) / 2 - 1, steps_per_brick = ctx->cfg.edge / 8;
-        const uint32_t parts_wanted = std::min(MAX_PARTS, std::max(1u, 2u * resident / n_work[0]));
+        // Fewer chunks than resident CTAs: every chunk is split.  A few waves of chunks whose last wave is less than
+        // half full (3140 pages on 444 CTAs = 7.07 waves run as long as 8): the chunks of that last wave -- the
+        // lightest, the list is heaviest first -- are split over the idle CTAs, the others stay whole (one walk).
+        uint32_t parts_wanted = 1, first_split = 0;
+        if (n_work[0] < resident) {
+            parts_wanted = std::min(MAX_PARTS, std::max(1u, 2u * resident / n_work[0]));
+        } else {
+            const uint32_t rem = n_work[0] % resident;
+            if (rem != 0 && 2u * rem <= resident) {
+                parts_wanted = std::min(MAX_PARTS, resident / rem);
+                first_split = n_work[0] - rem;
+            }
+        }
         if (parts_wanted >= 2) {
             for (uint32_t w = 0; w < n_work[0]; ++w) {
                 const uint32_t chunk = order.empty() ? w : order[w];
@@ -381,7 +393,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
                         lo = std::min(lo, mz * steps_per_brick + 1);
                         hi = std::max(hi, (mz + 1) * steps_per_brick);
                     }
-                const uint32_t span = hi - lo + 1, parts = std::min(parts_wanted, span);
+                const uint32_t span = hi - lo + 1, parts = w < first_split ? 1u : std::min(parts_wanted, span);
                 for (uint32_t q = 0; q < parts; ++q)
                     items.push_back({chunk, static_cast<uint8_t>(lo + span * q / parts), static_cast<uint8_t>(lo + span * (q + 1) / parts - 1),
                                      static_cast<uint8_t>(q), static_cast<uint8_t>(parts)});

@@ -972,6 +972,9 @@ __device__ __forceinline__ WorkItem work_item(const RegularParams& p, uint32_t i
             id | (static_cast<uint32_t>(it.part) << 24) | ((it.part + 1u == it.parts ? 1u : 0u) << 28)};
 }
 
+// part 0 and the last part at once: the item is a whole chunk (a batch whose last wave is split keeps its other chunks whole)
+__device__ __forceinline__ bool split_whole(uint32_t tag) { return ((tag >> 24) & 31u) == 16u; }
+
 // Look-back state of the split walk: item_totals[i] = (vertices, indices, active cells, generation).  A part's counting
 // walk stores the three totals, fences, then stores the dispatch's generation; readers spin on the generation (parts
 // are claimed in ascending order, so a part's predecessors are always running or done: no dead-lock) and fence before
@@ -1066,7 +1069,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 const uint64_t need = PARTIAL ? slabs_of_steps(dirty_steps<C>(p.descs[it.chunk].dirty_microbricks)) : ~0ull;
                 // SPLIT: a part is walked twice -- the counting walk publishes its totals, the emitting walk looks back over
                 // the parts before it (the second stream of its few slabs comes out of L2)
-                for (uint32_t pass = SPLIT ? 0u : 1u; pass < 2u; ++pass, ++k) {
+                // (an item that is a whole chunk -- part 0 and last part -- needs no look-back: one walk)
+                for (uint32_t pass = SPLIT && !split_whole(it.tag) ? 0u : 1u; pass < 2u; ++pass, ++k) {
                 sm.chunk_ids[k & 7] = id | (SPLIT ? pass << 30 : 0u);
                 for (int j = it.j0; j <= it.j1; ++j) {
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
@@ -1291,15 +1295,18 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         const uint32_t chunk = e0.y, kcpar = (e0.x >> 18) & 15u;
         if (kind == QK_CHUNK_END) {
             // ---- chunk epilogue: one warp waits for the chain's final totals and writes the records ----
-            if (static_cast<int>(k % NW) == ew && lane == 0) {
+            if (static_cast<int>(k % NW) == ew) {
                 uint32_t v_tot = 0, i_tot = 0, cells = e0.z;
                 if (e1.w != 0u) {
-                    const volatile uint64_t* tot = &sm.chunk_total[kcpar];
-                    const uint64_t want = static_cast<uint64_t>(e0.w & 0xfffffu);
-                    uint64_t got;
-                    do {
-                        got = *tot;
-                    } while ((got >> 44) != want);
+                    uint64_t got = 0;
+                    if (lane == 0) {
+                        const volatile uint64_t* tot = &sm.chunk_total[kcpar];
+                        const uint64_t want = static_cast<uint64_t>(e0.w & 0xfffffu);
+                        do {
+                            got = *tot;
+                        } while ((got >> 44) != want);
+                    }
+                    got = __shfl_sync(0xffffffffu, got, 0);
                     v_tot = static_cast<uint32_t>(got & FIELD);
                     i_tot = static_cast<uint32_t>((got >> 22) & FIELD);
                 }
@@ -1308,20 +1315,32 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     const uint32_t item = e1.z & 0xffffffu, part = (e1.z >> 24) & 15u;
                     if (!((e1.z >> 29) & 1u)) {
                         // counting walk: what this part adds to the chunk (every part counts from zero)
-                        publish_part(&p.item_totals[item], v_tot, i_tot, cells, p.split_generation);
+                        if (lane == 0) publish_part(&p.item_totals[item], v_tot, i_tot, cells, p.split_generation);
                         records = false;
                     } else if (!((e1.z >> 28) & 1u)) {
                         records = false;  // the chunk's last part reports for the chunk
-                    } else {
-                        v_tot = i_tot = cells = 0u;
-                        for (uint32_t q = 0; q <= part; ++q) {
-                            const uint4 t = wait_part(&p.item_totals[item - part + q], p.split_generation);
-                            v_tot += t.x;
-                            i_tot += t.y;
-                            cells += t.z;
+                    } else if (part != 0u) {
+                        // one lane per part (this one included: its counting walk published them), then a warp sum
+                        uint32_t a = 0, b = 0, c = 0;
+                        if (static_cast<uint32_t>(lane) <= part) {
+                            const uint4 t = wait_part(&p.item_totals[item - part + static_cast<uint32_t>(lane)], p.split_generation);
+                            a = t.x;
+                            b = t.y;
+                            c = t.z;
                         }
-                    }
+                        __syncwarp();
+#pragma unroll
+                        for (int d = 16; d != 0; d >>= 1) {
+                            a += __shfl_xor_sync(0xffffffffu, a, d);
+                            b += __shfl_xor_sync(0xffffffffu, b, d);
+                            c += __shfl_xor_sync(0xffffffffu, c, d);
+                        }
+                        v_tot = a;
+                        i_tot = b;
+                        cells = c;
+                    }  // else: a whole chunk walked once, its own totals
                 }
+                records = records && lane == 0;
                 if (records) {
                 const uint64_t dirty = static_cast<uint64_t>(e1.x) | (static_cast<uint64_t>(e1.y) << 32);
                 const uint32_t vo = v_tot > p.max_vertices ? 1u : 0u, io = i_tot > p.max_indices ? 1u : 0u;
@@ -1474,15 +1493,21 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     }
                     if (SPLIT && first && emit) {
                         // look-back across the parts of the chunk: this part starts where parts 0 .. q-1 end (their counting
-                        // walks publish the totals; every lane polls the same words)
+                        // walks publish the totals)
                         const uint32_t item = e1.w & 0xffffffu, part = (e1.w >> 24) & 15u;
-                        uint64_t bv = 0, bi = 0;
-                        for (uint32_t q = 0; q < part; ++q) {
-                            const uint4 t = wait_part(&p.item_totals[item - part + q], p.split_generation);
-                            bv += t.x;
-                            bi += t.y;
+                        uint32_t bv = 0, bi = 0;  // one lane per earlier part: the look-back costs one round trip, not `part`
+                        if (static_cast<uint32_t>(lane) < part) {
+                            const uint4 t = wait_part(&p.item_totals[item - part + static_cast<uint32_t>(lane)], p.split_generation);
+                            bv = t.x;
+                            bi = t.y;
                         }
-                        base = bv | (bi << 22);
+                        __syncwarp();
+#pragma unroll
+                        for (int d = 16; d != 0; d >>= 1) {
+                            bv += __shfl_xor_sync(0xffffffffu, bv, d);
+                            bi += __shfl_xor_sync(0xffffffffu, bi, d);
+                        }
+                        base = static_cast<uint64_t>(bv) | (static_cast<uint64_t>(bi) << 22);
                     }
                     HVX_CHECK((base & FIELD) + tot_v <= FIELD && ((base >> 22) & FIELD) + tot_i <= FIELD, 5u, chunk, st | (slot << 8), seq,
                               static_cast<uint32_t>(base), static_cast<uint32_t>(base >> 32));

@@ -430,10 +430,11 @@ def test_uniform_flag_on_a_surface_chunk_empties_it():
     batch.close()
 
 
-@pytest.mark.parametrize("edge,n", [(32, 1), (32, 7), (32, 60), (64, 1), (64, 5), (64, 40), (64, 147)])
+@pytest.mark.parametrize("edge,n", [(32, 1), (32, 7), (32, 60), (64, 1), (64, 5), (64, 40), (64, 147), (64, 175), (32, 500)])
 def test_split_walk_equals_the_whole_chunk_walk(edge, n):
-    """A dispatch with fewer chunks than resident CTAs walks z-ranges of chunks (counting launch + look-back over
-    per-part totals).  Counters, classify counters, ranges and every mesh byte must equal the unsplit walk
+    """A dispatch with fewer chunks than resident CTAs walks z-ranges of chunks (counting walk + look-back over
+    per-part totals); one with a few waves of chunks and a thin last wave (175 and 500 here: 159 on 148 CTAs, 454 on
+    444) splits only the chunks of that wave and walks the others whole, in the same launch.  Counters, classify counters, ranges and every mesh byte must equal the unsplit walk
     (hvx_debug_set_mode 0x100) -- with transition masks, partially dirty and empty-dirty chunks, cost hints, uniform
     flags -- and the oracle."""
     rng = np.random.default_rng(100 * edge + n)

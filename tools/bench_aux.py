@@ -75,8 +75,12 @@ def main():
     ex.context.debug_set_mode(0)
     c = ex.counters_buffer()
     out.append({"case": "single_chunk_64_dense_random", **r, "ms_median_one_cta": r_whole["ms_median"], "vertices": int(c["emitted_vertices"]),
-                "triangles": int(c["emitted_indices"]) // 3, "note": "split over 8 CTAs by z-range vs walked by one CTA"})
+                "triangles": int(c["emitted_indices"]) // 3, "note": "split over 16 CTAs by z-range vs walked by one CTA"})
     ex.close()
+    if "--latency-only" in sys.argv:
+        for rec in out:
+            print(json.dumps(rec), flush=True)
+        return
 
     # ---- batch of the reference's page size ---------------------------------------------------------
     pages = grid(16, range(-8, 8))

@@ -170,6 +170,50 @@ def planet_case(H, torch, dist, device, local_rank, rank, world, steps=20, warmu
     }
 
 
+def planet_shard_probe(H, torch, device, local_rank, world=8, steps=20, foci=256):
+    """One GPU runs the shard rank 0 would own in a `world`-rank strong-scaling run of the planet set (same partition rule),
+    so the per-rank step -- and the A/B of the split last wave -- can be measured without `world` GPUs."""
+    EDGE = PLANET_EDGE
+    stream = torch.cuda.Stream(device=device)
+    pages_all, lods_all, masks_all = planet_page_set(H, foci)
+    plane = int(H.ExtractionFixtureKind.Plane)
+    byte_cost = np.array([H.chunk_cost(EDGE, int(m)) for m in masks_all], dtype=np.uint64)
+
+    def make(mine):
+        pages, lods, masks = np.ascontiguousarray(pages_all[mine]), np.ascontiguousarray(lods_all[mine]), masks_all[mine]
+        seam = np.flatnonzero(masks != 0)
+        batch = H.ChunkBatchExtractor(local_rank, edge=EDGE, max_chunks=len(mine), max_vertices=4608, max_indices=6912,
+                                      max_transition_vertices=2048, max_transition_indices=6144)
+        batch.ctx.set_stream(stream.cuda_stream)
+        batch.ctx.fill_density(plane, pages, lods)
+        if len(seam):
+            batch.ctx.fill_slabs(plane, np.ascontiguousarray(pages[seam]), np.ascontiguousarray(lods[seam]))
+        return batch, masks, seam
+
+    everything = np.arange(len(pages_all))
+    batch, masks, _ = make(everything)
+    batch.ctx.extract_regular(None, H.make_descs(len(everything), transition_mask=[int(m) for m in masks]), len(everything))
+    vertices_all = batch.counters(len(everything))["required_vertices"].astype(np.uint64)
+    batch.close()
+    owner = H.partition_chunks(byte_cost + np.uint64(EMISSION_BYTES_PER_VERTEX) * vertices_all, world)
+    mine = np.flatnonzero(owner == 0)
+    batch, masks, seam = make(mine)
+    ctx, n, nt = batch.ctx, len(mine), len(seam)
+    d_reg = H.make_descs(n, transition_mask=[int(m) for m in masks], cost_hint=[int(v) + 1 for v in vertices_all[mine]])
+    d_tr = H.make_descs(max(nt, 1), transition_mask=[int(m) for m in masks[seam]] if nt else 0)
+    out = {"case": "planet_rank0_shard_of_%d" % world, "pages": int(n), "pages_with_transition_faces": int(nt)}
+    for label, mode in (("split_last_wave", 0), ("whole_chunks_only", 0x100)):
+        ctx.debug_set_mode(mode)
+        out[label + "_regular_ms"] = timed(torch, stream, lambda: ctx.extract_regular(None, d_reg, n), iters=steps)
+        if nt:
+            out[label + "_step_ms"] = timed(torch, stream, lambda: (ctx.extract_regular(None, d_reg, n), ctx.extract_transition(None, d_tr, nt)), iters=steps)
+    ctx.debug_set_mode(0)
+    if nt:
+        out["transition_ms"] = timed(torch, stream, lambda: ctx.extract_transition(None, d_tr, nt), iters=steps)
+    batch.close()
+    return out
+
+
 def lod_seam_case(H, torch, device, local_rank, stream=None):
     """BASELINE configs[2]: a horizon plan spanning three LOD levels around one focus (13 pages at the reference's
     page edge: 4 x LOD0, 7 x LOD1, 2 x LOD2; five coarse-owned faces), terrain field; every page runs regular
