@@ -56,6 +56,7 @@ struct hvx_ctx {
     ChunkDesc* d_tdescs = nullptr;    // [max_chunks] descriptors of the last TRANSITION dispatch
     uint32_t n_regular = 0, n_transition = 0;  // sizes of those dispatches (hvx_build_meshlets reads the generations)
     uint32_t debug_mode = 0;          // hvx_debug_set_mode
+    bool split_last_wave = false;     // hvx_debug_set_mode bit 9: split the chunks of a thin last wave (measured slower; A/B and tests)
     bool no_split = false;            // hvx_debug_set_mode bit 8: never split chunks across CTAs (A/B measurements, tests)
     uint32_t* d_order = nullptr;      // [max_chunks] start order of a batch with cost hints
     int64_t* d_pages = nullptr;
@@ -371,12 +372,16 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         !(ctx->cfg.flags & HVX_CFG_FIRST_GENERATION) && !ctx->no_split) {
         const uint32_t steps_per_chunk = (ctx->cfg.edge + 2) / 2 - 1, steps_per_brick = ctx->cfg.edge / 8;
         // Fewer chunks than resident CTAs: every chunk is split.  A few waves of chunks whose last wave is less than
-        // half full (3140 pages on 444 CTAs = 7.07 waves run as long as 8): the chunks of that last wave -- the
-        // lightest, the list is heaviest first -- are split over the idle CTAs, the others stay whole (one walk).
+        // half full (3140 pages on 444 CTAs = 7.07 waves run as long as 8) can split the chunks of that last wave -- the
+        // lightest, the list is heaviest first -- over the idle CTAs while the others stay whole (one walk).  Measured
+        // on the planet set's per-rank shards (tools/probe_planet_shard.py) that LOSES: 0.364 instead of 0.323 ms for
+        // 3141 pages, 0.695 instead of 0.615 ms for 6281 -- every walk of the item-list kernel starts with a dependent
+        // global read of its item in three warp roles, which costs the whole chunks more than the last wave gains.
+        // It stays reachable for A/B runs and tests (hvx_debug_set_mode bit 9) and is off otherwise.
         uint32_t parts_wanted = 1, first_split = 0;
         if (n_work[0] < resident) {
             parts_wanted = std::min(MAX_PARTS, std::max(1u, 2u * resident / n_work[0]));
-        } else {
+        } else if (ctx->split_last_wave) {
             const uint32_t rem = n_work[0] % resident;
             if (rem != 0 && 2u * rem <= resident) {
                 parts_wanted = std::min(MAX_PARTS, resident / rem);
@@ -870,10 +875,11 @@ int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
 
 int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
-    if ((mode & 0xffu) > 2 || (mode & ~0x1ffu))
-        return fail(ctx, HVX_E_INVALID_ARGUMENT, "debug mode must be 0 (off), 1 (stream only) or 2 (stream + sign bits), optionally | 0x100 (no split walk)");
+    if ((mode & 0xffu) > 2 || (mode & ~0x3ffu))
+        return fail(ctx, HVX_E_INVALID_ARGUMENT, "debug mode must be 0 (off), 1 (stream only) or 2 (stream + sign bits), optionally | 0x100 (no split walk) | 0x200 (split a thin last wave)");
     ctx->debug_mode = mode & 0xffu;
     ctx->no_split = (mode & 0x100u) != 0;
+    ctx->split_last_wave = (mode & 0x200u) != 0;
     return HVX_OK;
 }
 

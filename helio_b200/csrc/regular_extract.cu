@@ -912,7 +912,8 @@ struct SmemD {
                                            // (the queue is 16 deep, so an item 16 later cannot be published before every
                                            // warp has left this item's CHUNK_END entry)
     uint32_t bits[3][C::BW];               // solid bits of the last three slabs (front warps only)
-    uint32_t q_ctr[NQ];                    // next tile of the entry
+    uint32_t q_ctr[NQ];                    // state of the entry in one word: next tile (low 16 bits) | tiles << 16 for a step,
+                                           // kind << 30 for the others -- a warp that finds no work reads nothing else
     uint32_t q_done[NQ];                   // finished tiles of the entry
     uint32_t wtot[C::RS][C::PWS];          // active cells per classifying warp
     uint32_t wlayer[C::NW][8];             // per emission warp: ring word offset of sample layer z0 + d
@@ -1208,7 +1209,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             if (q_tail >= NQ) mbar_wait(&sm.q_free[qi], ((q_tail / NQ) - 1u) & 1u);  // every emission warp has left its last use
             *reinterpret_cast<uint4*>(&sm.queue[qi][0]) = make_uint4(w0, w1, w2, w3);
             *reinterpret_cast<uint4*>(&sm.queue[qi][4]) = make_uint4(w4, w5, w6, w7);
-            sm.q_ctr[qi] = 0u;
+            sm.q_ctr[qi] = (w0 >> 30) == QK_STEP ? ((w2 + D::TC - 1u) / D::TC) << 16 : (w0 >> 30) << 30;
             sm.q_done[qi] = 0u;
             HVX_JIT(11);
             mbar_arrive(&sm.q_bar[qi]);  // release: the entry is visible to whoever sees the phase flip
@@ -1288,6 +1289,22 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         const uint32_t qi = k & (NQ - 1);
         mbar_wait_parked(&sm.q_bar[qi], (k / NQ) & 1u);
         HVX_JIT(1);
+        uint32_t state = 0;
+#if !defined(HVX_LEGACY_PROTOCOL) && !defined(HVX_LEGACY_LANE_READ)
+        {
+            // Every emission warp walks every entry, and most visits find nothing to do (a step of a terrain chunk has
+            // ~6 tiles for 20 warps): the entry's state word alone decides that.  ONE decision per warp (lane 0 reads,
+            // the shuffle makes the warp agree): the counter moves while the lanes look at it.
+            if (lane == 0) state = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]);
+            state = __shfl_sync(0xffffffffu, state, 0);
+            const bool idle = (state >> 30) == QK_STEP ? (state & 0xffffu) >= (state >> 16)
+                                                       : (state >> 30) == QK_CHUNK_END && static_cast<int>(k % NW) != ew;
+            if (idle) {
+                if (lane == 0) mbar_arrive(&sm.q_free[qi]);
+                continue;
+            }
+        }
+#endif
         const uint4 e0 = *reinterpret_cast<const uint4*>(&sm.queue[qi][0]);
         const uint4 e1 = *reinterpret_cast<const uint4*>(&sm.queue[qi][4]);
         const uint32_t kind = e0.x >> 30;
@@ -1381,11 +1398,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             // a warp whose lanes disagreed would meet itself in the collectives below from two different entries
             // (lane 0 reads, the shuffle makes the warp converge and agree)
 #if defined(HVX_LEGACY_PROTOCOL) || defined(HVX_LEGACY_LANE_READ)  // stress builds: the round-1 form (every lane reads for itself)
-            const uint32_t pulled = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]);
+            const uint32_t pulled = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]) & 0xffffu;
 #else
-            uint32_t pulled = 0;
-            if (lane == 0) pulled = *const_cast<volatile uint32_t*>(&sm.q_ctr[qi]);
-            pulled = __shfl_sync(0xffffffffu, pulled, 0);
+            const uint32_t pulled = state & 0xffffu;  // the warp's one look at the counter (above): tiles were left
 #endif
             if (pulled < ntiles) {
                 const int slot_m = slot == 0 ? RS - 1 : slot - 1, slot_p = slot + 1 == RS ? 0 : slot + 1;
@@ -1403,7 +1418,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 const int z0 = 2 * st - 2;
                 for (;;) {
                     uint32_t t = 0;
-                    if (lane == 0) t = atomicAdd(&sm.q_ctr[qi], 1u);
+                    if (lane == 0) t = atomicAdd(&sm.q_ctr[qi], 1u) & 0xffffu;  // at most tiles + NW increments: the low half never carries
                     t = __shfl_sync(0xffffffffu, t, 0);
                     if (t >= ntiles) break;
                     HVX_JIT(3);

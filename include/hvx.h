@@ -210,7 +210,8 @@ const char* hvx_regular_kernel_name(const hvx_ctx* ctx, int partial);
 uint64_t hvx_launch_count(const hvx_ctx* ctx);
 /* Roofline probes for the regular kernel (bench tools only): 0 = normal, 1 = stream the samples and do nothing else,
  * 2 = stream + sign bits.  Modes 1 and 2 produce no meshes.  | 0x100: never split chunks across CTAs (a dispatch with
- * fewer chunks than the machine has resident CTAs normally walks z-ranges of chunks; output is identical either way). */
+ * fewer chunks than the machine has resident CTAs normally walks z-ranges of chunks; output is identical either way).
+ * | 0x200: also split the chunks of a thin last wave of a batch of a few waves (measured slower, off by default). */
 int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode);
 
 /* Device-side proof of an arithmetic shortcut (diagnostics; tests/test_gpu_regular.py): the regular kernel divides

@@ -434,7 +434,7 @@ def test_uniform_flag_on_a_surface_chunk_empties_it():
 def test_split_walk_equals_the_whole_chunk_walk(edge, n):
     """A dispatch with fewer chunks than resident CTAs walks z-ranges of chunks (counting walk + look-back over
     per-part totals); one with a few waves of chunks and a thin last wave (175 and 500 here: 159 on 148 CTAs, 454 on
-    444) splits only the chunks of that wave and walks the others whole, in the same launch.  Counters, classify counters, ranges and every mesh byte must equal the unsplit walk
+    444) can split only the chunks of that wave and walk the others whole, in the same launch (debug bit 0x200).  Counters, classify counters, ranges and every mesh byte must equal the unsplit walk
     (hvx_debug_set_mode 0x100) -- with transition masks, partially dirty and empty-dirty chunks, cost hints, uniform
     flags -- and the oracle."""
     rng = np.random.default_rng(100 * edge + n)
@@ -460,6 +460,8 @@ def test_split_walk_equals_the_whole_chunk_walk(edge, n):
         v, i, packed = batch.ctx.read_meshes(0, 0, n)
         return c, r, k, v.copy(), i.copy(), packed.copy()
 
+    if n > 150:
+        batch.ctx.debug_set_mode(0x200)   # more chunks than resident CTAs: ask for the split last wave
     launches0 = batch.ctx.launch_count
     split = run()
     split_launches = batch.ctx.launch_count - launches0
@@ -467,11 +469,12 @@ def test_split_walk_equals_the_whole_chunk_walk(edge, n):
     launches0 = batch.ctx.launch_count
     whole = run()
     whole_launches = batch.ctx.launch_count - launches0
-    batch.ctx.debug_set_mode(0)
+    batch.ctx.debug_set_mode(0x200 if n > 150 else 0)
     assert split_launches == whole_launches, "the split walk is still one launch"
     for a, b in zip(split, whole):
         assert a.tobytes() == b.tobytes()
     again = run()
+    batch.ctx.debug_set_mode(0)
     for a, b in zip(split, again):
         assert a.tobytes() == b.tobytes()
     assert int(split[0]["emitted_vertices"].astype(np.int64).sum()) > 1000

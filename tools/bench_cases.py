@@ -202,7 +202,7 @@ def planet_shard_probe(H, torch, device, local_rank, world=8, steps=20, foci=256
     d_reg = H.make_descs(n, transition_mask=[int(m) for m in masks], cost_hint=[int(v) + 1 for v in vertices_all[mine]])
     d_tr = H.make_descs(max(nt, 1), transition_mask=[int(m) for m in masks[seam]] if nt else 0)
     out = {"case": "planet_rank0_shard_of_%d" % world, "pages": int(n), "pages_with_transition_faces": int(nt)}
-    for label, mode in (("split_last_wave", 0), ("whole_chunks_only", 0x100)):
+    for label, mode in (("split_last_wave", 0x200), ("whole_chunks_only", 0)):
         ctx.debug_set_mode(mode)
         out[label + "_regular_ms"] = timed(torch, stream, lambda: ctx.extract_regular(None, d_reg, n), iters=steps)
         if nt:

@@ -14,5 +14,5 @@ import helio_b200 as H  # noqa: E402
 
 device = torch.device("cuda:0")
 torch.cuda.set_device(device)
-for world in (8, 4, 2):
+for world in ([int(a) for a in sys.argv[1:]] or [8, 4, 2]):
     print(json.dumps(bench_cases.planet_shard_probe(H, torch, device, 0, world=world)), flush=True)
