@@ -94,6 +94,11 @@ __device__ __noinline__ void selfcheck_fail(uint32_t code, uint32_t a, uint32_t 
 #define HVX_TABLE static __device__ const
 #include "transvoxel_tables.inc"
 
+// nanoseconds an idle role (scheduler lane, emission warp without work) sleeps between two looks at its barrier
+#ifndef HVX_IDLE_NS
+#define HVX_IDLE_NS 100
+#endif
+
 template <int E_, int EBS_, int RS_, int NW_>
 struct Cfg {
     static constexpr int E = E_;          // cells per chunk edge
@@ -161,16 +166,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int NT>
 __device__ __forceinline__ void consumer_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-}
-
-// The chunk queue rearms itself: every CTA draws exactly one ticket past the end of the work list, and the last CTA to
-// do so (counted in work_counter[2]) zeroes both words, so a dispatch needs no memset in front of the launch (one
-// stream operation less on the single-page latency path).  The words are zeroed once when the ctx is created.
-__device__ __forceinline__ void rearm_work_counter(uint32_t* work_counter) {
-    if (atomicAdd(work_counter + 2, 1u) + 1u == gridDim.x) {
-        atomicExch(work_counter + 2, 0u);
-        atomicExch(work_counter, 0u);
-    }
 }
 
 // Solid bits of the 8 corners of every cell of one cell row: bit x of a** is the corner at
@@ -1216,7 +1211,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             ++q_tail;
         };
         for (uint32_t kc = 0;; ++kc) {
-            mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+            mbar_wait_idle<HVX_IDLE_NS>(&sm.full_bar[slot], round & 1u);
             const uint32_t idw = sm.chunk_ids[kc & 7];
             if (idw == 0xffffffffu) {
                 publish(QK_EXIT << 30, 0, 0, 0, 0, 0, 0, 0);
@@ -1232,7 +1227,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             uint32_t chunk_cells = 0;
             bool prev_empty = false;
             for (int j = it.j0; j <= it.j1; ++j) {
-                mbar_wait_parked(&sm.rec_bar[slot], round & 1u);
+                mbar_wait_idle<HVX_IDLE_NS>(&sm.rec_bar[slot], round & 1u);
                 HVX_JIT(10);
                 const int prev_slot = slot == 0 ? RS - 1 : slot - 1;
                 if (j == it.j0) {
@@ -1287,7 +1282,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
 
     for (uint32_t k = 0;; ++k) {
         const uint32_t qi = k & (NQ - 1);
-        mbar_wait_parked(&sm.q_bar[qi], (k / NQ) & 1u);
+        mbar_wait_idle<HVX_IDLE_NS>(&sm.q_bar[qi], (k / NQ) & 1u);
         HVX_JIT(1);
         uint32_t state = 0;
 #if !defined(HVX_LEGACY_PROTOCOL) && !defined(HVX_LEGACY_LANE_READ)

@@ -23,7 +23,7 @@ namespace hvx {
 
 namespace {
 
-#define HVX_TABLE static __device__ const
+#define HVX_TABLE alignas(16) static __device__ const
 #include "transvoxel_tables.inc"
 
 // PV/src/transvoxel_transition.rs:463-502 integer face bases: origin, u, v, outward.
@@ -131,9 +131,14 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
     TSmem<C>& sm = *reinterpret_cast<TSmem<C>*>(smem_raw);
     constexpr int E = C::E, W = C::W, NT = C::NT, CPT = C::CPT, NS = 2 * CPT + 1;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 512; i += NT) sm.case_info[i] = HVX_TRANSITION_CASE_INFO[i];
-    for (int i = tid; i < 512 * 12; i += NT) sm.vertex_edge[i] = HVX_TRANSITION_VERTEX_EDGE[i / 12][i % 12];
-    for (int i = tid; i < 56 * 36; i += NT) sm.class_index[i] = HVX_TRANSITION_CLASS_INDEX[i / 36][i % 36];
+    // Lengyel's transition tables, 9 KB, 16 bytes per load (every CTA of a small batch pays this before its first face)
+    static_assert(sizeof(sm.case_info) % 16 == 0 && sizeof(sm.vertex_edge) % 16 == 0 && sizeof(sm.class_index) % 16 == 0, "table copy granularity");
+    for (int i = tid; i < static_cast<int>(sizeof(sm.case_info) / 16); i += NT)
+        reinterpret_cast<uint4*>(sm.case_info)[i] = reinterpret_cast<const uint4*>(HVX_TRANSITION_CASE_INFO)[i];
+    for (int i = tid; i < static_cast<int>(sizeof(sm.vertex_edge) / 16); i += NT)
+        reinterpret_cast<uint4*>(sm.vertex_edge)[i] = reinterpret_cast<const uint4*>(&HVX_TRANSITION_VERTEX_EDGE[0][0])[i];
+    for (int i = tid; i < static_cast<int>(sizeof(sm.class_index) / 16); i += NT)
+        reinterpret_cast<uint4*>(sm.class_index)[i] = reinterpret_cast<const uint4*>(&HVX_TRANSITION_CLASS_INDEX[0][0])[i];
     // this thread's CPT cells of a face: one row segment, u fastest (face-local linear order)
     const int cell0 = tid * CPT;
 
@@ -142,7 +147,10 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
         if (tid == 0) sm.chunk_id = atomicAdd(p.work_counter, 1u);
         __syncthreads();
         const uint32_t chunk = sm.chunk_id;
-        if (chunk >= p.n_chunks) break;
+        if (chunk >= p.n_chunks) {
+            if (tid == 0) rearm_work_counter(p.work_counter);  // every CTA draws exactly one ticket past the end
+            break;
+        }
         const ChunkDesc desc = p.descs[chunk];
         const uint32_t mask = desc.transition_mask & 0x3fu;
         const uint32_t glo = static_cast<uint32_t>(desc.generation), ghi = static_cast<uint32_t>(desc.generation >> 32);
@@ -338,13 +346,18 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
 template <class C>
 cudaError_t launch_tcfg(const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream) {
     const size_t smem = sizeof(TSmem<C>);
-    cudaError_t err = cudaFuncSetAttribute(transition_extract_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
-    if (err != cudaSuccess) return err;
-    int per_sm = 1;
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transition_extract_kernel<C>, C::NT, smem);
-    if (err != cudaSuccess) return err;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    // the shared-memory opt-in and the occupancy are per device and do not change: asked once (as launch_persistent does)
+    static int cache[64];
+    int per_sm = dev.ordinal >= 0 && dev.ordinal < 64 ? __atomic_load_n(&cache[dev.ordinal], __ATOMIC_ACQUIRE) : 0;
+    if (per_sm == 0) {
+        cudaError_t err = cudaFuncSetAttribute(transition_extract_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               static_cast<int>(smem));
+        if (err != cudaSuccess) return err;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, transition_extract_kernel<C>, C::NT, smem);
+        if (err != cudaSuccess) return err;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        if (dev.ordinal >= 0 && dev.ordinal < 64) __atomic_store_n(&cache[dev.ordinal], per_sm, __ATOMIC_RELEASE);
+    }
     const uint32_t grid = static_cast<uint32_t>(
         min(static_cast<long long>(p.n_chunks), static_cast<long long>(dev.sm_count) * per_sm));
     transition_extract_kernel<C><<<grid, C::NT, smem, stream>>>(p);
@@ -355,8 +368,7 @@ cudaError_t launch_tcfg(const TransitionParams& p, const DeviceInfo& dev, cudaSt
 
 cudaError_t launch_transition(int edge, const TransitionParams& p, const DeviceInfo& dev, cudaStream_t stream) {
     if (p.n_chunks == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
-    if (e != cudaSuccess) return e;
+    // no memset: the work counter rearms itself (work_counter[0] tickets, work_counter[2] CTAs that have left)
     if (edge == 64) return launch_tcfg<TCfg<64, 512>>(p, dev, stream);
     if (edge == 32) return launch_tcfg<TCfg<32, 256>>(p, dev, stream);
     return cudaErrorInvalidValue;
