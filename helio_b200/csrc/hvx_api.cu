@@ -47,6 +47,9 @@ struct hvx_ctx {
     unsigned char* h_batch[2] = {nullptr, nullptr};
     cudaEvent_t batch_done[2] = {nullptr, nullptr};
     uint32_t batch_flip = 0;
+    unsigned char* h_tbatch[2] = {nullptr, nullptr};  // the same for the transition dispatch's descriptors
+    cudaEvent_t tbatch_done[2] = {nullptr, nullptr};
+    uint32_t tbatch_flip = 0;
     uint32_t* d_touched = nullptr;    // [max_chunks] hvx_apply_edit: chunks whose samples the edit changes
     uint32_t* h_touched = nullptr;    // pinned twin (the list goes up with a truly asynchronous copy)
     cudaEvent_t touched_done = nullptr;
@@ -226,8 +229,13 @@ int resolve_input(hvx_ctx* ctx, const uint32_t* ptr, uint64_t words, int arena_i
 
 int upload_descs(hvx_ctx* ctx, ChunkDesc* dst, const hvx_chunk_desc* descs, uint32_t n) {
     static_assert(sizeof(hvx_chunk_desc) == sizeof(ChunkDesc), "desc layout");
-    HVX_CUDA(ctx, cudaMemcpyAsync(dst, descs, static_cast<size_t>(n) * sizeof(ChunkDesc),
-                                  cudaMemcpyHostToDevice, ctx->stream));
+    // through pinned staging (two buffers, reused once the copy that read them is done): a copy from the caller's
+    // pageable array is staged by the driver anyway, synchronously, and costs the stream a second operation
+    const uint32_t flip = ctx->tbatch_flip ^= 1u;
+    HVX_CUDA(ctx, cudaEventSynchronize(ctx->tbatch_done[flip]));
+    memcpy(ctx->h_tbatch[flip], descs, static_cast<size_t>(n) * sizeof(ChunkDesc));
+    HVX_CUDA(ctx, cudaMemcpyAsync(dst, ctx->h_tbatch[flip], static_cast<size_t>(n) * sizeof(ChunkDesc), cudaMemcpyHostToDevice, ctx->stream));
+    HVX_CUDA(ctx, cudaEventRecord(ctx->tbatch_done[flip], ctx->stream));
     return HVX_OK;
 }
 
@@ -787,7 +795,15 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_touched), static_cast<size_t>(c.max_chunks) * sizeof(uint32_t), cudaHostAllocDefault)) != cudaSuccess)
         return bail(cuda_fail(ctx, e, "cudaHostAlloc"));
     if ((e = cudaEventCreateWithFlags(&ctx->touched_done, cudaEventDisableTiming)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaEventCreate"));
-    if (c.max_transition_vertices != 0 && (rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
+    if (c.max_transition_vertices != 0) {
+        if ((rc = small_alloc(ctx, &ctx->d_tdescs, c.max_chunks))) return bail(rc);
+        for (int i = 0; i < 2; ++i) {
+            if ((e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_tbatch[i]), static_cast<size_t>(c.max_chunks) * sizeof(ChunkDesc), cudaHostAllocDefault)) != cudaSuccess)
+                return bail(cuda_fail(ctx, e, "cudaHostAlloc"));
+            if ((e = cudaEventCreateWithFlags(&ctx->tbatch_done[i], cudaEventDisableTiming)) != cudaSuccess)
+                return bail(cuda_fail(ctx, e, "cudaEventCreate"));
+        }
+    }
 
     if ((rc = small_alloc(ctx, &ctx->d_item_totals, MAX_SPLIT_ITEMS))) return bail(rc);
     if ((e = cudaMemsetAsync(ctx->d_item_totals, 0, MAX_SPLIT_ITEMS * sizeof(uint4), ctx->stream)) != cudaSuccess)
@@ -820,6 +836,8 @@ void hvx_destroy(hvx_ctx* ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_batch[i]) cudaFreeHost(ctx->h_batch[i]);
         if (ctx->batch_done[i]) cudaEventDestroy(ctx->batch_done[i]);
+        if (ctx->h_tbatch[i]) cudaFreeHost(ctx->h_tbatch[i]);
+        if (ctx->tbatch_done[i]) cudaEventDestroy(ctx->tbatch_done[i]);
     }
     cudaFree(ctx->d_tdescs);
     cudaFree(ctx->d_pages);

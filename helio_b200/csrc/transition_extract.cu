@@ -61,9 +61,9 @@ struct TSmem {
     uint32_t rowbits[C::NT / 32][9][C::RW32 + 1];  // per warp: solid bits of its 9 layer-1 sample rows
     uint16_t cases[C::FACE_CELLS];   // 9-bit case of every cell of the face being processed
     uint32_t chunk_id;
-    uint16_t case_info[512];
-    uint8_t vertex_edge[512 * 12];
-    uint8_t class_index[56 * 36];
+    alignas(16) uint16_t case_info[512];     // the three tables are copied 16 bytes at a time
+    alignas(16) uint8_t vertex_edge[512 * 12];
+    alignas(16) uint8_t class_index[56 * 36];
 };
 
 template <class C>
