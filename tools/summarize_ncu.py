@@ -81,6 +81,41 @@ def main():
     lines.append("hottest CUDA source lines (line | executed warp instructions | stall samples):")
     for r in cand[:25]:
         lines.append(f"  {r[0].strip():>5s} | {int(f(r[iex])):>11d} | {int(f(r[ismp])):>6d} | {r[1].strip()[:100]}")
+    lines.append("")
+    lines.append("CUDA source lines by executed warp instructions (line | executed | share):")
+    total = sum(f(r[iex]) for r in cand) or 1.0
+    for r in sorted(cand, key=lambda r: -f(r[iex]))[:40]:
+        lines.append(f"  {r[0].strip():>5s} | {int(f(r[iex])):>11d} | {100.0 * f(r[iex]) / total:5.1f} % | {r[1].strip()[:90]}")
+    # pipe utilisation (which issue port is the busy one) and the SASS opcode mix behind it
+    lines.append("")
+    lines.append("pipe utilisation:")
+    for i, h in enumerate(hdr):
+        if "pipe" in h and ("pct_of_peak_sustained_active" in h) and f(vals[i]) >= 1.0:
+            lines.append(f"  {h:78s} {f(vals[i]):6.1f} {units[i]}")
+    sass = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"],
+                          capture_output=True, text=True).stdout
+    rows = list(csv.reader(sass.splitlines()))
+    try:
+        hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
+        hdr3, data3 = rows[hi], rows[hi + 1:]
+        iex3 = hdr3.index("Instructions Executed")
+        isrc = hdr3.index("Source") if "Source" in hdr3 else 1
+        ops = {}
+        for r in data3:
+            if len(r) <= iex3:
+                continue
+            toks = r[isrc].split()
+            if not toks:
+                continue
+            op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
+            ops[op.rstrip(";")] = ops.get(op.rstrip(";"), 0.0) + f(r[iex3])
+        tot = sum(ops.values()) or 1.0
+        lines.append("")
+        lines.append(f"SASS opcode mix by executed warp instructions (total {int(tot)}):")
+        for op, n in sorted(ops.items(), key=lambda kv: -kv[1])[:45]:
+            lines.append(f"  {op:28s} {int(n):>12d} {100.0 * n / tot:5.1f} %")
+    except StopIteration:
+        lines.append("(no SASS page)")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[:30]))
 
