@@ -172,7 +172,7 @@ EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
     "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_regular_kernel_name", "hvx_selftest_edge_parameter", "hvx_selftest_inv_sqrt",
     "hvx_fill_density", "hvx_fill_slabs", "hvx_apply_edit", "hvx_extract_regular", "hvx_extract_regular_to_host", "hvx_classify_regular", "hvx_extract_transition",
-    "hvx_build_meshlets", "hvx_gather_surface", "hvx_gather_bind_table", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
+    "hvx_build_meshlets", "hvx_weld_meshes", "hvx_gather_surface", "hvx_gather_bind_table", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
     "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
     "hvx_buffer", "hvx_buffer_bytes", "hvx_read", "hvx_write", "hvx_read_meshes", "hvx_lod_topology",
     "hvx_horizon_plan", "hvx_partition_chunks", "hvx_chunk_cost", "hvx_copy_segments",
@@ -233,6 +233,7 @@ def load() -> C.CDLL:
                                               C.c_uint64, C.POINTER(Range), vp, u64p, u64p]
     L.hvx_extract_transition.argtypes = [vp, vp, C.c_uint64, C.POINTER(ChunkDesc), C.c_uint32]
     L.hvx_build_meshlets.argtypes = [vp, C.c_int, C.c_uint32]
+    L.hvx_weld_meshes.argtypes = [vp, C.c_int, C.c_uint32]
     L.hvx_gather_surface.argtypes = [vp, vp, vp, vp, C.c_uint64, vp, C.c_uint32]
     L.hvx_gather_bind_table.argtypes = [vp, vp, C.c_uint32]
     L.hvx_publisher_create.argtypes = [vp, C.c_uint32, C.POINTER(vp)]

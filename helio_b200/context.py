@@ -280,6 +280,11 @@ class Context:
         """63-index meshlets + bounds for chunks [0, n) of the last extraction (PV/src/terrain_meshlet.rs)."""
         self._check(self._lib.hvx_build_meshlets(self._handle, kind, n), kind="transition" if kind else "regular")
 
+    def weld_meshes(self, n, kind=0):
+        """Optional vertex-reuse output: merge the bit-identical vertex records (the copies of one cell edge) of chunks
+        [0, n) of the last extraction in place; indices follow, ranges / emitted_vertices shrink (hvx_weld_meshes)."""
+        self._check(self._lib.hvx_weld_meshes(self._handle, kind, n), kind="transition" if kind else "regular")
+
     def gather_surface(self, residency, table, atlas, jobs):
         """hvx_gather_surface: halo blocks + transition slabs of ``jobs`` from the page atlas into the ctx arenas.
 

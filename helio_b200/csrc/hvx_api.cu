@@ -74,7 +74,9 @@ struct hvx_ctx {
     uint64_t stage_bytes[3] = {0, 0, 0};
     void* bound_table = nullptr;      // hvx_gather_bind_table: the page table, resident until the next bind
     uint64_t bound_table_bytes = 0;
-    uint32_t* d_work = nullptr;       // [2] work counters (regular, transition)
+    uint32_t* d_work = nullptr;       // [8] self-rearming work counters: regular [0],[2], transition [1],[3], weld [4],[6]
+    uint32_t* d_weld = nullptr;       // hvx_weld_meshes scratch (grow-only)
+    uint64_t weld_bytes = 0;
     hvx_range* d_packed = nullptr;    // [max_chunks] packed placement for hvx_read_meshes
     void* pack_v = nullptr;           // staging for hvx_read_meshes
     void* pack_i = nullptr;
@@ -813,8 +815,8 @@ int hvx_create(hvx_ctx** out, int device, const hvx_config* config) {
     if ((rc = small_alloc(ctx, &ctx->d_col_index, c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_xz, 2ull * c.max_chunks))) return bail(rc);
     if ((rc = small_alloc(ctx, &ctx->d_col_lod, c.max_chunks))) return bail(rc);
-    if ((rc = small_alloc(ctx, &ctx->d_work, 4))) return bail(rc);
-    if ((e = cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(uint32_t), ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
+    if ((rc = small_alloc(ctx, &ctx->d_work, 8))) return bail(rc);
+    if ((e = cudaMemsetAsync(ctx->d_work, 0, 8 * sizeof(uint32_t), ctx->stream)) != cudaSuccess) return bail(cuda_fail(ctx, e, "cudaMemsetAsync"));
     if ((rc = small_alloc(ctx, &ctx->d_packed, c.max_chunks))) return bail(rc);
     for (int id = HVX_BUF_REGULAR_VERTICES; id <= HVX_BUF_TRANSITION_BLOCKS; ++id)  // meshlet arenas stay lazy
         if (arena_bytes(c, id) != 0 && (rc = ensure_buffer(ctx, id))) return bail(rc);
@@ -849,6 +851,7 @@ void hvx_destroy(hvx_ctx* ctx) {
     for (void* b : ctx->stage) cudaFree(b);
     cudaFree(ctx->bound_table);
     cudaFree(ctx->d_work);
+    cudaFree(ctx->d_weld);
     cudaFree(ctx->d_packed);
     cudaFree(ctx->pack_v);
     cudaFree(ctx->pack_i);
@@ -1650,6 +1653,54 @@ int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n) {
     p.meshlet_counts = static_cast<uint32_t*>(ctx->buf[mid + 2]);
     cudaError_t e = launch_meshlets(p, ctx->dev, ctx->stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_meshlets");
+    ctx->launches += 1;
+    return HVX_OK;
+}
+
+int hvx_weld_meshes(hvx_ctx* ctx, int kind, uint32_t n) {
+    if (!ctx) return HVX_E_INVALID_ARGUMENT;
+    if (kind != 0 && kind != 1) return fail(ctx, HVX_E_INVALID_ARGUMENT, "kind must be 0 (regular) or 1 (transition)");
+    if (n > ctx->cfg.max_chunks) return fail(ctx, HVX_E_BATCH_CAPACITY, "batch of %u chunks exceeds max_chunks %u", n, ctx->cfg.max_chunks);
+    if (kind == 1 && ctx->cfg.max_transition_vertices == 0)
+        return fail(ctx, HVX_E_INVALID_CAPACITY, "Transvoxel transition capacities must be nonzero (vertices=0, indices=0)");
+    if (n == 0) return HVX_OK;
+    const uint32_t last = kind ? ctx->n_transition : ctx->n_regular;
+    if (n > last)
+        return fail(ctx, HVX_E_BATCH_CAPACITY, "weld requested for %u chunks, the last %s extraction held %u", n,
+                    kind ? "transition" : "regular", last);
+    DeviceGuard guard(ctx->device);
+    WeldParams p{};
+    p.n_chunks = n;
+    p.max_vertices = kind ? ctx->cfg.max_transition_vertices : ctx->cfg.max_vertices;
+    p.max_indices = kind ? ctx->cfg.max_transition_indices : ctx->cfg.max_indices;
+    p.table_words = 64;
+    while (p.table_words < 2ull * p.max_vertices) p.table_words <<= 1;
+    p.scratch_words_per_cta = p.table_words + 2u * p.max_vertices;
+    const uint32_t ctas = std::min<uint32_t>(n, static_cast<uint32_t>(ctx->dev.sm_count));
+    const uint64_t need = static_cast<uint64_t>(ctx->dev.sm_count) * p.scratch_words_per_cta * sizeof(uint32_t);
+    if (need > ctx->weld_bytes) {  // grow-only scratch, sized for a full machine of CTAs at this kind's capacity
+        if (ctx->d_weld) {
+            HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->d_weld);
+            ctx->allocated -= ctx->weld_bytes;
+            ctx->d_weld = nullptr;
+            ctx->weld_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ctx->d_weld), need);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+        ctx->weld_bytes = need;
+        ctx->allocated += need;
+    }
+    p.vertices = static_cast<hvx_vertex*>(ctx->buf[kind ? HVX_BUF_TRANSITION_VERTICES : HVX_BUF_REGULAR_VERTICES]);
+    p.indices = static_cast<uint32_t*>(ctx->buf[kind ? HVX_BUF_TRANSITION_INDICES : HVX_BUF_REGULAR_INDICES]);
+    p.ranges = static_cast<hvx_range*>(ctx->buf[kind ? HVX_BUF_TRANSITION_RANGES : HVX_BUF_REGULAR_RANGES]);
+    p.counters = ctx->buf[kind ? HVX_BUF_TRANSITION_COUNTERS : HVX_BUF_REGULAR_COUNTERS];
+    p.counter_stride = kind ? sizeof(hvx_transition_counters) : sizeof(hvx_emission_counters);
+    p.emitted_vertices_offset = kind ? offsetof(hvx_transition_counters, emitted_vertices) : offsetof(hvx_emission_counters, emitted_vertices);
+    p.scratch = ctx->d_weld;
+    p.work_counter = ctx->d_work + 4;
+    cudaError_t e = launch_weld(p, ctx->dev, ctas, ctx->stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "launch_weld");
     ctx->launches += 1;
     return HVX_OK;
 }

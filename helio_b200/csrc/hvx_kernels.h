@@ -191,6 +191,21 @@ struct MeshletParams {
     uint32_t* meshlet_counts;             // [n]
 };
 
+// hvx_weld_meshes: merge bit-identical vertex records of each chunk's mesh in place (mesh_weld.cu)
+struct WeldParams {
+    uint32_t n_chunks;
+    uint32_t max_vertices, max_indices;   // per-chunk slot capacity of the arenas
+    hvx_vertex* vertices;
+    uint32_t* indices;
+    hvx_range* ranges;                    // vertex_count is rewritten
+    void* counters;                       // hvx_emission_counters or hvx_transition_counters, [n]
+    uint32_t counter_stride, emitted_vertices_offset;
+    uint32_t* scratch;                    // [ctas][scratch_words_per_cta]: table | representative | destination
+    uint32_t table_words;                 // power of two >= 2 * max_vertices
+    uint32_t scratch_words_per_cta;       // table_words + 2 * max_vertices
+    uint32_t* work_counter;               // [0] tickets, [2] CTAs that have left (rearm_work_counter)
+};
+
 struct DeviceInfo {
     int ordinal;
     int sm_count;
@@ -211,6 +226,7 @@ cudaError_t launch_fill_slabs(int edge, const FillParams& p, const DeviceInfo& d
 cudaError_t launch_terrain_heights(int edge, const long long* col_xz, const uint8_t* col_lod, uint32_t n_cols, float* heights,
                                    cudaStream_t stream);
 cudaError_t launch_meshlets(const MeshletParams& p, const DeviceInfo& dev, cudaStream_t stream);
+cudaError_t launch_weld(const WeldParams& p, const DeviceInfo& dev, uint32_t ctas, cudaStream_t stream);
 cudaError_t launch_gather(const GatherParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_publish(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);
 cudaError_t launch_visibility(const PublishParams& p, const DeviceInfo& dev, cudaStream_t stream);

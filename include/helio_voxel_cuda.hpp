@@ -231,6 +231,9 @@ class ChunkBatchExtractor {
         ctx_.check(hvx_apply_edit(ctx_.get(), &edit, page_xyz, lod, n, nullptr, dirty.data(), touched));
         return dirty;
     }
+    /// Optional vertex-reuse output (off by default: the reference shares no vertices between cells): merges the
+    /// bit-identical vertex records of chunks [0, n) of the last extraction in place (hvx_weld_meshes).
+    void weld_meshes(uint32_t n, bool transition = false) { ctx_.check(hvx_weld_meshes(ctx_.get(), transition ? 1 : 0, n)); }
     std::vector<hvx_emission_counters> counters_buffer(uint32_t n) const { return ctx_.read<hvx_emission_counters>(HVX_BUF_REGULAR_COUNTERS, 0, n); }
     std::vector<hvx_range> ranges_buffer(uint32_t n) const { return ctx_.read<hvx_range>(HVX_BUF_REGULAR_RANGES, 0, n); }
     void synchronize() { ctx_.check(hvx_synchronize(ctx_.get())); }

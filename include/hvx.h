@@ -300,6 +300,18 @@ int hvx_extract_transition(hvx_ctx* ctx, const uint32_t* slabs, uint64_t slab_wo
  * overflowed publish none.  kind 0 = regular, 1 = transition. */
 int hvx_build_meshlets(hvx_ctx* ctx, int kind, uint32_t n);
 
+/* ---- optional vertex-reuse output (north_star kernel 4) -------------------------------------------- */
+/* The reference never shares vertices between cells: the reuse byte of the Transvoxel vertex code is not consumed
+ * (PV/src/transvoxel_emit.wgsl:322-358 uses `code & 0xff` only; PV/src/transvoxel.rs:99-101 reuse() has no caller), so
+ * the default output repeats every crossing edge once per cell that touches it, and parity demands exactly that.
+ * hvx_weld_meshes rewrites the meshes of chunks [0, n) of the last extraction of that kind IN PLACE into the indexed
+ * mesh edge-ownership reuse would give: bit-identical 32-byte vertex records (the copies of one edge) are merged, the
+ * first occurrence is kept and the original order preserved; every index is redirected to the kept copy (triangle
+ * order and winding unchanged); range.vertex_count and counters.emitted_vertices become the kept count
+ * (required_vertices still reports what the unshared mesh needs).  Idempotent.  Off by default, no reference
+ * counterpart: the oracle is oracle/weld.py.  kind 0 = regular, 1 = transition. */
+int hvx_weld_meshes(hvx_ctx* ctx, int kind, uint32_t n);
+
 /* ---- surface gather (the step before extraction in the reference's pass) ---------- */
 /* GpuPageTableEntry (PV/src/table.rs:8-19): open-addressed page table of the residency atlas. */
 typedef struct {

@@ -344,6 +344,12 @@ impl ChunkBatchExtractor {
         let status = unsafe { ffi::hvx_build_meshlets(self.ctx.raw, transition as c_int, n) };
         self.ctx.check(status, n as usize, 0, 0)
     }
+    /// Optional vertex-reuse output (off by default; the reference shares no vertices): merges the bit-identical vertex
+    /// records of chunks `[0, n)` of the last extraction in place, indices follow, ranges / emitted_vertices shrink.
+    pub fn weld_meshes(&self, n: u32, transition: bool) -> Result<(), TransvoxelGpuError> {
+        let status = unsafe { ffi::hvx_weld_meshes(self.ctx.raw, transition as c_int, n) };
+        self.ctx.check(status, n as usize, 0, 0)
+    }
     pub fn counters(&self, n: usize) -> Result<Vec<GpuTransvoxelEmissionCounters>, TransvoxelGpuError> { self.ctx.read(ffi::HVX_BUF_REGULAR_COUNTERS, 0, n) }
     pub fn transition_counters(&self, n: usize) -> Result<Vec<GpuTransvoxelTransitionCounters>, TransvoxelGpuError> { self.ctx.read(ffi::HVX_BUF_TRANSITION_COUNTERS, 0, n) }
     pub fn ranges(&self, n: usize) -> Result<Vec<ffi::hvx_range>, TransvoxelGpuError> {

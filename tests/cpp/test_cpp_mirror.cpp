@@ -80,6 +80,20 @@ int main() {
             std::printf("FAIL dirty re-extraction\n");
             return 1;
         }
+        // optional vertex-reuse output: fewer vertices, the same index count, and a second weld is a no-op
+        for (size_t k = 0; k < 3; ++k) requests[k].dirty_microbricks = ~0ull;
+        batch.encode(batch.prepare(requests));
+        const auto unshared = batch.counters_buffer(3);
+        batch.weld_meshes(3);
+        const auto shared = batch.counters_buffer(3);
+        batch.weld_meshes(3);
+        const auto again = batch.counters_buffer(3);
+        if (unshared[0].emitted_vertices == 0 || shared[0].emitted_vertices * 2 >= unshared[0].emitted_vertices ||
+            shared[0].emitted_indices != unshared[0].emitted_indices || shared[0].required_vertices != unshared[0].required_vertices ||
+            again[0].emitted_vertices != shared[0].emitted_vertices || batch.ranges_buffer(3)[0].vertex_count != shared[0].emitted_vertices) {
+            std::printf("FAIL weld: %u -> %u -> %u vertices\n", unshared[0].emitted_vertices, shared[0].emitted_vertices, again[0].emitted_vertices);
+            return 1;
+        }
     }
     std::printf("OK cpp mirror: 1323 vertices / 661 triangles, errors and overflow contract as the reference\n");
     return 0;

@@ -95,6 +95,13 @@ def main():
     out.append({"case": "batch_4096x32^3_fbm", **r, "cells_per_s": len(pages) * 32 ** 3 / (r["ms_median"] * 1e-3),
                 "pages_per_s": len(pages) / (r["ms_median"] * 1e-3), "algorithmic_GBps": nbytes / (r["ms_median"] * 1e-3) / 1e9,
                 "vertices": v, "overflowed": int((cnt["vertex_overflow"] | cnt["index_overflow"]).sum())})
+    # optional vertex-reuse output on the same batch (the weld rewrites the meshes, so it is timed behind an extraction)
+    n_pages = len(pages)
+    r_both = timed(stream, lambda: (b.ctx.extract_regular(None, descs, n_pages), b.ctx.weld_meshes(n_pages)))
+    kept = int(b.counters(n_pages)["emitted_vertices"].astype(np.int64).sum())
+    out.append({"case": "weld_4096x32^3_fbm", "extract_ms": r["ms_median"], "extract_plus_weld_ms": r_both["ms_median"],
+                "weld_ms": r_both["ms_median"] - r["ms_median"], "vertices": v, "kept_vertices": kept, "kept_fraction": kept / max(v, 1),
+                "vertex_bytes_saved": 32 * (v - kept)})
     for kind, name in [(0, "plane"), (1, "sphere"), (16, "terrain_fbm"), (17, "dense_random")]:
         r = timed(stream, lambda: b.fill_density(kind, pages), 2, 10)
         out.append({"case": f"fill_32^3_{name}", **r, "GBps": len(pages) * 34 ** 3 * 4 / (r["ms_median"] * 1e-3) / 1e9})
