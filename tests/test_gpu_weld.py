@@ -96,3 +96,26 @@ def test_weld_errors():
     batch.ctx.weld_meshes(2)
     assert list(batch.counters(2)["emitted_vertices"]) == [1089, 1089]
     batch.close()
+
+
+def test_meshlets_of_a_welded_mesh_match_the_oracle():
+    """The weld composes with the next step of the reference's pass: build_terrain_meshlets on the shared-vertex mesh
+    (its unique-vertex counts now see the sharing) equals the oracle's builder run on the oracle-welded mesh."""
+    edge, specs = 32, [(O.FIELD_SPHERE, [0, 0, 0], 0), (O.FIELD_PLANE, [0, -1, 0], 0x3F), (O.FIELD_TERRAIN_FBM, [0, -1, 0], 0)]
+    n, maxv, maxi = len(specs), 16_384, 24_576
+    batch = H.ChunkBatchExtractor(0, edge=edge, max_chunks=n, max_vertices=maxv, max_indices=maxi)
+    samples = np.concatenate([O.fixture_fill(k, p, edge=edge) for k, p, _ in specs])
+    gens = [77 + i for i in range(n)]
+    batch.extract_regular(samples, n, generation=gens, transition_mask=[m for _, _, m in specs])
+    batch.ctx.weld_meshes(n)
+    batch.ctx.build_meshlets(n, 0)
+    stride = (maxi + 62) // 63
+    for i, (kind, page, mask) in enumerate(specs):
+        mesh = O.extract_regular(samples[i * 34 ** 3:(i + 1) * 34 ** 3], edge=edge, transition_mask=mask, debug=False)
+        kept, idx, _ = weld.weld_mesh(mesh.vertices, mesh.indices)
+        want_m, want_b = O.build_meshlets(kept, idx, i * maxi, i * maxv, i * stride, gens[i], 0)
+        got_m, got_b = batch.ctx.read_meshlets(i, 0)
+        assert got_m.tobytes() == want_m.tobytes(), f"chunk {i}: descriptors"
+        for name in got_b.dtype.names:
+            assert np.array_equal(got_b[name], want_b[name]), f"chunk {i}: bounds.{name}"
+    batch.close()
