@@ -1676,8 +1676,12 @@ int hvx_weld_meshes(hvx_ctx* ctx, int kind, uint32_t n) {
     p.table_words = 64;
     while (p.table_words < 2ull * p.max_vertices) p.table_words <<= 1;
     p.scratch_words_per_cta = p.table_words + 2u * p.max_vertices;
-    const uint32_t ctas = std::min<uint32_t>(n, static_cast<uint32_t>(ctx->dev.sm_count));
-    const uint64_t need = static_cast<uint64_t>(ctx->dev.sm_count) * p.scratch_words_per_cta * sizeof(uint32_t);
+    // four 512-thread CTAs per SM hide the phase barriers of small meshes behind each other; fewer when their scratch
+    // (table + two maps per CTA) would pass 1 GiB
+    uint32_t per_sm = 4;
+    while (per_sm > 1 && static_cast<uint64_t>(ctx->dev.sm_count) * per_sm * p.scratch_words_per_cta * sizeof(uint32_t) > (1ull << 30)) per_sm /= 2;
+    const uint32_t ctas = std::min<uint32_t>(n, static_cast<uint32_t>(ctx->dev.sm_count) * per_sm);
+    const uint64_t need = static_cast<uint64_t>(ctx->dev.sm_count) * per_sm * p.scratch_words_per_cta * sizeof(uint32_t);
     if (need > ctx->weld_bytes) {  // grow-only scratch, sized for a full machine of CTAs at this kind's capacity
         if (ctx->d_weld) {
             HVX_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
