@@ -16,9 +16,12 @@ for edge in (32, 64):
         b.fill_density(kind, pages)
         b.extract_regular(None, n, transition_mask=[0, 0x3F, 1, 2, 0, 0x15], dirty_microbricks=[(1 << 64) - 1] * 5 + [0xFF00FF])
         b.ctx.build_meshlets(n, 0)
+    b.ctx.weld_meshes(n)          # optional vertex-reuse pass, then meshlets over the shared-vertex mesh
+    b.ctx.build_meshlets(n, 0)
     b.fill_slabs(16, pages, [1] * n)
     b.extract_transition(None, n, [0x3F, 0x15, 0, 1, 0x2A, 0x3F])
     b.ctx.build_meshlets(n, 1)
+    b.ctx.weld_meshes(n, kind=1)
     c = b.counters(n)
     t = b.transition_counters(n)
     print(edge, int(c["emitted_vertices"].sum()), int(t["emitted_vertices"].sum()))
