@@ -89,6 +89,26 @@ __device__ __noinline__ void selfcheck_fail(uint32_t code, uint32_t a, uint32_t 
 #define HVX_CHECK(cond, code, a, b, c, d, e) ((void)0)
 #endif
 
+// HVX_TIMELINE (tools/timeline.py; variant build only): a few time stamps per CTA of the decoupled kernel -- when the CTA
+// was up, when it drew each ticket, when a walk's first slab had landed, when a chunk's records were written -- to see
+// where a short launch spends its time (launch ramp, first-slab latency, tail).  Event = globaltimer ns (44 bits) |
+// kind << 44 | id << 48; row 0 of a CTA's record counts its events.
+#ifdef HVX_TIMELINE
+__device__ unsigned long long g_timeline[1024][64];
+__device__ __forceinline__ void timeline_event(uint32_t kind, uint32_t id) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    unsigned long long* row = g_timeline[blockIdx.x & 1023u];
+    const unsigned long long n = atomicAdd(&row[0], 1ull);
+    if (n < 63ull) row[1ull + n] = (t & ((1ull << 44) - 1ull)) | (static_cast<unsigned long long>(kind) << 44) |
+                                   (static_cast<unsigned long long>(id & 0xffffu) << 48);
+}
+#define HVX_TL(kind, id) timeline_event(kind, id)
+#else
+#define HVX_TL(kind, id) ((void)0)
+#endif
+enum : uint32_t { TL_CTA_UP = 0, TL_TICKET = 1, TL_FIRST_SLAB = 2, TL_CHUNK_END = 3, TL_PRODUCER_EXIT = 4 };
+
 // Lengyel's tables live in device global memory (statically initialised); every CTA copies the
 // 3.8 KB it needs into shared memory once (the kernel is persistent).
 #define HVX_TABLE static __device__ const
@@ -1037,6 +1057,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         mbar_fence_init();
     }
     __syncthreads();
+    if (tid == 0) HVX_TL(TL_CTA_UP, 0u);
 
     // ---- PRODUCER warp ------------------------------------------------------------------------
     if (warp == FW + NW) {
@@ -1056,6 +1077,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 // the work list: every chunk in index order, or the caller's list -- heaviest chunks first when the batch
                 // carries cost hints, chunks flagged uniform left out (a chunk's slot does not depend on when it runs)
                 const uint32_t id = ticket < p.n_work ? (p.order != nullptr ? p.order[ticket] : ticket) : 0xffffffffu;
+                HVX_TL(id == 0xffffffffu ? TL_PRODUCER_EXIT : TL_TICKET, ticket);
                 if (id == 0xffffffffu) {
                     rearm_work_counter(p.work_counter);
                     sm.chunk_ids[k & 7] = id;
@@ -1103,6 +1125,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             mbar_wait_parked(&sm.full_bar[slot], round & 1u);
             const uint32_t idw = sm.chunk_ids[kc & 7];
             if (idw == 0xffffffffu) return;
+            if (tid == 0) HVX_TL(TL_FIRST_SLAB, idw);
             const WorkItem it = work_item<C, SPLIT>(p, idw & 0x3fffffffu);
             dirty = p.descs[it.chunk].dirty_microbricks;
             if (PARTIAL) need = slabs_of_steps(dirty_steps<C>(dirty));
@@ -1356,6 +1379,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     }  // else: a whole chunk walked once, its own totals
                 }
                 records = records && lane == 0;
+                if (lane == 0) HVX_TL(TL_CHUNK_END, chunk);
                 if (records) {
                 const uint64_t dirty = static_cast<uint64_t>(e1.x) | (static_cast<uint64_t>(e1.y) << 32);
                 const uint32_t vo = v_tot > p.max_vertices ? 1u : 0u, io = i_tot > p.max_indices ? 1u : 0u;
@@ -1672,6 +1696,18 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     if (e != cudaSuccess) return e;
     return launch_regular_records(edge, p, stream);
 }
+
+#ifdef HVX_TIMELINE
+// variant build only (tools/timeline.py): the per-CTA time stamps of the decoupled kernel
+extern "C" int hvx_debug_timeline_read(unsigned long long* out /* [1024][64] */, int reset) {
+    if (cudaMemcpyFromSymbol(out, g_timeline, sizeof(unsigned long long) * 1024 * 64) != cudaSuccess) return -1;
+    if (reset) {
+        void* ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_timeline) != cudaSuccess || cudaMemset(ptr, 0, sizeof(unsigned long long) * 1024 * 64) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
 
 #ifdef HVX_SELFCHECK
 // stress builds only (tools/repro_race.py): the invariant log of the decoupled kernel

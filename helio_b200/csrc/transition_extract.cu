@@ -23,6 +23,11 @@ namespace hvx {
 
 namespace {
 
+// how many vertices of a face a thread has in flight (14 sample loads each, one L2 / HBM round trip per trip of the loop)
+#ifndef HVX_T_UNROLL
+#define HVX_T_UNROLL 1
+#endif
+constexpr int T_UNROLL = HVX_T_UNROLL;
 #define HVX_TABLE alignas(16) static __device__ const
 #include "transvoxel_tables.inc"
 
@@ -295,6 +300,7 @@ __global__ void __launch_bounds__(C::NT) transition_extract_kernel(const Transit
             }
             // ---- vertices: one thread per vertex; owner thread by binary search over the prefix,
             //      owner cell by walking that thread's 4-bit vertex counts ---------------------------
+#pragma unroll T_UNROLL
             for (uint32_t v = tid; v < face_v; v += NT) {
                 uint32_t lo = 0;
 #pragma unroll
