@@ -107,6 +107,22 @@ __device__ __forceinline__ void timeline_event(uint32_t kind, uint32_t id) {
 #else
 #define HVX_TL(kind, id) ((void)0)
 #endif
+// HVX_WAITTRACE (tools/wait_trace.py; variant build only): every warp role records the wait it is about to enter
+// (site | detail << 8) in a per-CTA table in global memory and clears it afterwards, so a launch that does not finish
+// can be asked, from the host and while it hangs, what each warp of each CTA is waiting for.
+#ifdef HVX_WAITTRACE
+__device__ uint32_t g_wait[1024][32];
+#define HVX_WAIT_BEGIN(site, detail) (*const_cast<volatile uint32_t*>(&g_wait[blockIdx.x & 1023u][threadIdx.x >> 5]) = (site) | (static_cast<uint32_t>(detail) << 8))
+#define HVX_WAIT_END() (*const_cast<volatile uint32_t*>(&g_wait[blockIdx.x & 1023u][threadIdx.x >> 5]) = 0u)
+#else
+#define HVX_WAIT_BEGIN(site, detail) ((void)0)
+#define HVX_WAIT_END() ((void)0)
+#endif
+enum : uint32_t {
+    WS_PRODUCER_EMPTY = 1, WS_FRONT_FIRST_FULL = 2, WS_FRONT_FULL = 3, WS_FRONT_BAR = 4, WS_SCHED_FULL = 5, WS_SCHED_REC = 6,
+    WS_SCHED_QFREE = 7, WS_EMIT_QBAR = 8, WS_EMIT_NEXT_SLAB = 9, WS_EMIT_CHAIN = 10, WS_EMIT_CHUNK_TOTAL = 11,
+    WS_EMIT_LOOKBACK = 12, WS_EMIT_RECORDS_LOOKBACK = 13, WS_DONE = 15
+};
 enum : uint32_t { TL_CTA_UP = 0, TL_TICKET = 1, TL_FIRST_SLAB = 2, TL_CHUNK_END = 3, TL_PRODUCER_EXIT = 4 };
 
 // Lengyel's tables live in device global memory (statically initialised); every CTA copies the
@@ -1081,7 +1097,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 if (id == 0xffffffffu) {
                     rearm_work_counter(p.work_counter);
                     sm.chunk_ids[k & 7] = id;
+                    HVX_WAIT_BEGIN(WS_PRODUCER_EMPTY, slot | 0x80);
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    HVX_WAIT_BEGIN(WS_DONE, 0);
                     mbar_arrive(&sm.full_bar[slot]);
                     break;
                 }
@@ -1094,7 +1112,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 for (uint32_t pass = SPLIT && !split_whole(it.tag) ? 0u : 1u; pass < 2u; ++pass, ++k) {
                 sm.chunk_ids[k & 7] = id | (SPLIT ? pass << 30 : 0u);
                 for (int j = it.j0; j <= it.j1; ++j) {
+                    HVX_WAIT_BEGIN(WS_PRODUCER_EMPTY, slot | (j << 8));
                     mbar_wait_parked(&sm.empty_bar[slot], (round & 1u) ^ 1u);
+                    HVX_WAIT_END();
                     HVX_JIT(30);
                     if ((need >> j) & 1ull) {
                         mbar_arrive_expect_tx(&sm.full_bar[slot], C::SLAB_BYTES);
@@ -1122,15 +1142,22 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         for (uint32_t kc = 0;; ++kc) {
             uint64_t dirty = 0, need = ~0ull;
             // the first wait of a walk is for its first slab (or the sentinel): only then is the work item known
+            HVX_WAIT_BEGIN(WS_FRONT_FIRST_FULL, slot | (kc << 8));
             mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+            HVX_WAIT_END();
             const uint32_t idw = sm.chunk_ids[kc & 7];
-            if (idw == 0xffffffffu) return;
+            if (idw == 0xffffffffu) {
+                HVX_WAIT_BEGIN(WS_DONE, 0);
+                return;
+            }
             if (tid == 0) HVX_TL(TL_FIRST_SLAB, idw);
             const WorkItem it = work_item<C, SPLIT>(p, idw & 0x3fffffffu);
             dirty = p.descs[it.chunk].dirty_microbricks;
             if (PARTIAL) need = slabs_of_steps(dirty_steps<C>(dirty));
             for (int j = it.j0; j <= it.j1; ++j) {
+                HVX_WAIT_BEGIN(WS_FRONT_FULL, slot | (j << 8));
                 if (j != it.j0) mbar_wait_parked(&sm.full_bar[slot], round & 1u);
+                HVX_WAIT_END();
                 HVX_JIT(20);
                 // a slab no dirty step reads was not fetched: no ballots, and its own step (not dirty) has no cells
                 const bool live = !PARTIAL || ((need >> j) & 1ull);
@@ -1170,7 +1197,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         if (lane == 0) sm.bits[bcur][C::FULL] = v;
                     }
                 }
+                HVX_WAIT_BEGIN(WS_FRONT_BAR, slot | (j << 8));
                 asm volatile("bar.sync 2, %0;" ::"n"(FW * 32) : "memory");  // the slab's bits are complete
+                HVX_WAIT_END();
                 HVX_JIT(21);
                 if (warp < CW) {
                     uint32_t incl = 0;
@@ -1227,7 +1256,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         auto publish = [&](uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6,
                            uint32_t w7) {
             const uint32_t qi = q_tail & (NQ - 1);
+            HVX_WAIT_BEGIN(WS_SCHED_QFREE, qi | (q_tail << 8));
             if (q_tail >= NQ) mbar_wait(&sm.q_free[qi], ((q_tail / NQ) - 1u) & 1u);  // every emission warp has left its last use
+            HVX_WAIT_END();
             *reinterpret_cast<uint4*>(&sm.queue[qi][0]) = make_uint4(w0, w1, w2, w3);
             *reinterpret_cast<uint4*>(&sm.queue[qi][4]) = make_uint4(w4, w5, w6, w7);
             sm.q_ctr[qi] = (w0 >> 30) == QK_STEP ? ((w2 + D::TC - 1u) / D::TC) << 16 : (w0 >> 30) << 30;
@@ -1237,10 +1268,13 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             ++q_tail;
         };
         for (uint32_t kc = 0;; ++kc) {
+            HVX_WAIT_BEGIN(WS_SCHED_FULL, slot | (kc << 8));
             mbar_wait_idle<HVX_IDLE_NS>(&sm.full_bar[slot], round & 1u);
+            HVX_WAIT_END();
             const uint32_t idw = sm.chunk_ids[kc & 7];
             if (idw == 0xffffffffu) {
                 publish(QK_EXIT << 30, 0, 0, 0, 0, 0, 0, 0);
+                HVX_WAIT_BEGIN(WS_DONE, 0);
                 return;
             }
             WorkItem it = work_item<C, SPLIT>(p, idw & 0x3fffffffu);
@@ -1253,7 +1287,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             uint32_t chunk_cells = 0;
             bool prev_empty = false;
             for (int j = it.j0; j <= it.j1; ++j) {
+                HVX_WAIT_BEGIN(WS_SCHED_REC, slot | (j << 8));
                 mbar_wait_idle<HVX_IDLE_NS>(&sm.rec_bar[slot], round & 1u);
+                HVX_WAIT_END();
                 HVX_JIT(10);
                 const int prev_slot = slot == 0 ? RS - 1 : slot - 1;
                 if (j == it.j0) {
@@ -1308,7 +1344,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
 
     for (uint32_t k = 0;; ++k) {
         const uint32_t qi = k & (NQ - 1);
+        HVX_WAIT_BEGIN(WS_EMIT_QBAR, qi | (k << 8));
         mbar_wait_idle<HVX_IDLE_NS>(&sm.q_bar[qi], (k / NQ) & 1u);
+        HVX_WAIT_END();
         HVX_JIT(1);
         uint32_t state = 0;
 #if !defined(HVX_LEGACY_PROTOCOL) && !defined(HVX_LEGACY_LANE_READ)
@@ -1329,7 +1367,10 @@ regular_extract_decoupled_kernel(const RegularParams p) {
         const uint4 e0 = *reinterpret_cast<const uint4*>(&sm.queue[qi][0]);
         const uint4 e1 = *reinterpret_cast<const uint4*>(&sm.queue[qi][4]);
         const uint32_t kind = e0.x >> 30;
-        if (kind == QK_EXIT) return;
+        if (kind == QK_EXIT) {
+            HVX_WAIT_BEGIN(WS_DONE, 0);
+            return;
+        }
         const uint32_t chunk = e0.y, kcpar = (e0.x >> 18) & 15u;
         if (kind == QK_CHUNK_END) {
             // ---- chunk epilogue: one warp waits for the chain's final totals and writes the records ----
@@ -1340,9 +1381,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     if (lane == 0) {
                         const volatile uint64_t* tot = &sm.chunk_total[kcpar];
                         const uint64_t want = static_cast<uint64_t>(e0.w & 0xfffffu);
+                        HVX_WAIT_BEGIN(WS_EMIT_CHUNK_TOTAL, kcpar | (e0.w << 8));
                         do {
                             got = *tot;
                         } while ((got >> 44) != want);
+                        HVX_WAIT_END();
                     }
                     got = __shfl_sync(0xffffffffu, got, 0);
                     v_tot = static_cast<uint32_t>(got & FIELD);
@@ -1360,6 +1403,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     } else if (part != 0u) {
                         // one lane per part (this one included: its counting walk published them), then a warp sum
                         uint32_t a = 0, b = 0, c = 0;
+                        HVX_WAIT_BEGIN(WS_EMIT_RECORDS_LOOKBACK, part | (item << 8));
                         if (static_cast<uint32_t>(lane) <= part) {
                             const uint4 t = wait_part(&p.item_totals[item - part + static_cast<uint32_t>(lane)], p.split_generation);
                             a = t.x;
@@ -1367,6 +1411,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             c = t.z;
                         }
                         __syncwarp();
+                        HVX_WAIT_END();
 #pragma unroll
                         for (int d = 16; d != 0; d >>= 1) {
                             a += __shfl_xor_sync(0xffffffffu, a, d);
@@ -1424,25 +1469,37 @@ regular_extract_decoupled_kernel(const RegularParams p) {
 #else
             const uint32_t pulled = state & 0xffffu;  // the warp's one look at the counter (above): tiles were left
 #endif
-            if (pulled < ntiles) {
+            if (pulled < ntiles) {   // a hint: whether THIS warp gets a tile is decided by the pull below
                 const int slot_m = slot == 0 ? RS - 1 : slot - 1, slot_p = slot + 1 == RS ? 0 : slot + 1;
-                // the z gradient of the step's upper layer reads the first layer of slab st+1
-                if (st + 1 < C::NSLAB) mbar_wait(&sm.full_bar[slot_p], next_parity);
-                // ring word offsets of sample layers z0 .. z0+4 (slabs st-1, st, st+1)
-                __syncwarp();
-                if (lane < 6) {
-                    const int s2 = lane < 2 ? slot_m : lane < 4 ? slot : slot_p;
-                    wl[lane] = static_cast<uint32_t>(s2 * C::SLAB_WORDS + (lane & 1) * LW);
-                }
-                __syncwarp();
                 hvx_vertex* const out_v = p.vertices + static_cast<size_t>(chunk) * p.max_vertices;
                 uint32_t* const out_i = p.indices + static_cast<size_t>(chunk) * p.max_indices;
                 const int z0 = 2 * st - 2;
+                bool window_ready = false;
                 for (;;) {
                     uint32_t t = 0;
                     if (lane == 0) t = atomicAdd(&sm.q_ctr[qi], 1u) & 0xffffu;  // at most tiles + NW increments: the low half never carries
                     t = __shfl_sync(0xffffffffu, t, 0);
                     if (t >= ntiles) break;
+                    if (!window_ready) {
+                        // Only a warp that HOLDS a tile may touch the step's slabs or their barriers: the step cannot
+                        // finish -- and its slabs cannot be handed back and refilled -- before this tile is done.  The
+                        // wait for slab st+1 (the z gradient of the step's upper layer reads its first layer) used to
+                        // sit in front of the pull; a warp delayed between its look at the counter and that wait could
+                        // then find the others had finished the step and the slot refilled twice, and wait for a phase
+                        // of the slot's barrier that never comes (found by the jittered stress build, which sleeps
+                        // exactly there; profiles/r02_wait_trace.txt).
+                        HVX_WAIT_BEGIN(WS_EMIT_NEXT_SLAB, slot_p | (st << 8));
+                        if (st + 1 < C::NSLAB) mbar_wait(&sm.full_bar[slot_p], next_parity);
+                        HVX_WAIT_END();
+                        // ring word offsets of sample layers z0 .. z0+4 (slabs st-1, st, st+1)
+                        __syncwarp();
+                        if (lane < 6) {
+                            const int s2 = lane < 2 ? slot_m : lane < 4 ? slot : slot_p;
+                            wl[lane] = static_cast<uint32_t>(s2 * C::SLAB_WORDS + (lane & 1) * LW);
+                        }
+                        __syncwarp();
+                        window_ready = true;
+                    }
                     HVX_JIT(3);
                     // ---- one tile: TC consecutive active cells of the step ---------------------------
                     const uint32_t seq = tile_base + t;
@@ -1519,9 +1576,11 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         const volatile uint64_t* prev = &sm.tile_prefix[(seq - 1u) & 31u];
                         const uint64_t want = static_cast<uint64_t>((seq - 1u) & 0xfffffu);
                         uint64_t got;
+                        HVX_WAIT_BEGIN(WS_EMIT_CHAIN, seq);
                         do {
                             got = *prev;
                         } while ((got >> 44) != want);
+                        HVX_WAIT_END();
                         // all lanes poll (a lane-0 spin leaves the warp split, and everything after it is issued twice),
                         // but the word can be overwritten 32 tiles later: the warp takes lane 0's copy, so a lane that
                         // looked late cannot carry a different prefix into the collectives below
@@ -1533,12 +1592,14 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         // walks publish the totals)
                         const uint32_t item = e1.w & 0xffffffu, part = (e1.w >> 24) & 15u;
                         uint32_t bv = 0, bi = 0;  // one lane per earlier part: the look-back costs one round trip, not `part`
+                        HVX_WAIT_BEGIN(WS_EMIT_LOOKBACK, part | (item << 8));
                         if (static_cast<uint32_t>(lane) < part) {
                             const uint4 t = wait_part(&p.item_totals[item - part + static_cast<uint32_t>(lane)], p.split_generation);
                             bv = t.x;
                             bi = t.y;
                         }
                         __syncwarp();
+                        HVX_WAIT_END();
 #pragma unroll
                         for (int d = 16; d != 0; d >>= 1) {
                             bv += __shfl_xor_sync(0xffffffffu, bv, d);
@@ -1696,6 +1757,17 @@ cudaError_t launch_regular(int edge, const RegularParams& p, const DeviceInfo& d
     if (e != cudaSuccess) return e;
     return launch_regular_records(edge, p, stream);
 }
+
+#ifdef HVX_WAITTRACE
+// variant build only (tools/wait_trace.py): what every warp of every CTA is waiting for, readable while a launch hangs
+// (the copy runs on its own non-blocking stream)
+extern "C" int hvx_debug_wait_read(uint32_t* out /* [1024][32] */) {
+    static cudaStream_t side = nullptr;
+    if (!side && cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbolAsync(out, g_wait, sizeof(uint32_t) * 1024 * 32, 0, cudaMemcpyDeviceToHost, side) != cudaSuccess) return -2;
+    return cudaStreamSynchronize(side) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 #ifdef HVX_TIMELINE
 // variant build only (tools/timeline.py): the per-CTA time stamps of the decoupled kernel
