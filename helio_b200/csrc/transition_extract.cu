@@ -23,7 +23,9 @@ namespace hvx {
 
 namespace {
 
-// how many vertices of a face a thread has in flight (14 sample loads each, one L2 / HBM round trip per trip of the loop)
+// How many vertices of a face a thread has in flight (14 sample loads each, one L2 / HBM round trip per trip of the
+// loop).  Measured 1 / 2 / 4: 1024 coarse 64^3 pages 0.190 / 0.191 / 0.190 ms, the planet set's faces 0.184 / 0.188 /
+// 0.192 ms -- the occupancy already hides the round trips; kept at 1.
 #ifndef HVX_T_UNROLL
 #define HVX_T_UNROLL 1
 #endif
