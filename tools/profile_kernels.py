@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """One launch (or a few) of every kernel OTHER than the regular extractor, at its benchmark size, for
-`ncu --set full` (tools/gpu_call4.sh); profiles/r02_*_ncu.txt are cut from that capture."""
+`ncu --set full` (tools/gpu_calls/gpu_call4.sh); profiles/r02_*_ncu.txt are cut from that capture."""
 import sys
 from pathlib import Path
 
