@@ -57,6 +57,13 @@ r = H.ChunkBatchExtractor(0, edge=32, max_chunks=512, max_vertices=12288, max_in
 r.fill_density(16, grid(16, [-2, -1]))
 r.ctx.extract_regular(None, H.make_descs(512), 512)
 r.ctx.synchronize()
+# optional vertex-reuse pass over 4096 terrain pages
+w = H.ChunkBatchExtractor(0, edge=32, max_chunks=4096, max_vertices=12288, max_indices=18432)
+w.fill_density(16, grid(16, range(-8, 8)))
+w.ctx.extract_regular(None, H.make_descs(4096), 4096)
+w.ctx.weld_meshes(4096)
+w.ctx.synchronize()
+w.close()
 r.close()
 
 # gather -> extract -> meshlets -> publish from a resident atlas (one pass)
