@@ -235,6 +235,8 @@ def run_ours(args):
     batch = H.ChunkBatchExtractor(local_rank, edge=EDGE, max_chunks=n, max_vertices=MAX_VERTICES,
                                   max_indices=MAX_INDICES)
     ctx = batch.ctx
+    if args.spread:
+        ctx.debug_set_mode(args.spread << 12)
     stream = torch.cuda.Stream(device=device)
     ctx.set_stream(stream.cuda_stream)
     descs = H.make_descs(n)
@@ -438,7 +440,7 @@ def run_ours(args):
                        "l2_policy": "inputs larger than L2 (4.71 GB samples per GPU vs 126 MB L2)",
                        "slot_capacity": [MAX_VERTICES, MAX_INDICES], "overflowed_chunks": overflow,
                        "partition": "LPT static, no data-path collective",
-                       "chunk_order": "identity" if args.no_hints or not args.warmup else "heaviest first by the previous pass's vertex counts (hvx_chunk_desc.cost_hint)"},
+                       "chunk_order": "identity" if args.no_hints or not args.warmup else "by the previous pass's vertex counts (hvx_chunk_desc.cost_hint): heavy chunks heaviest first, spread over the first 75 % of the start order" + (f" (--spread {args.spread})" if args.spread else "")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -480,6 +482,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     ap.add_argument("--no-hints", action="store_true", help="do not feed the previous pass's vertex counts back as cost hints")
+    ap.add_argument("--spread", type=int, default=0, help="diagnostic: share (per cent) of the start order the heavy chunks are spread over; 255 = plain descending order; 0 = library default")
     ap.add_argument("--no-numa", action="store_true", help="do not bind ranks to their GPU's NUMA node (N > 1)")
     ap.add_argument("--cpu-stride", type=int, default=1, help="CPU baseline runs every k-th chunk of the workload (default: all of them)")
     ap.add_argument("--cpu-offset", type=int, default=0)

@@ -59,6 +59,7 @@ struct hvx_ctx {
     ChunkDesc* d_tdescs = nullptr;    // [max_chunks] descriptors of the last TRANSITION dispatch
     uint32_t n_regular = 0, n_transition = 0;  // sizes of those dispatches (hvx_build_meshlets reads the generations)
     uint32_t debug_mode = 0;          // hvx_debug_set_mode
+    uint32_t spread_pct = 75;         // heavy chunks of a hinted batch are spread over this share of the start order (0: plain descending order; hvx_debug_set_mode bits 12..19)
     bool split_last_wave = false;     // hvx_debug_set_mode bit 9: split the chunks of a thin last wave (measured slower; A/B and tests)
     bool no_split = false;            // hvx_debug_set_mode bit 8: never split chunks across CTAs (A/B measurements, tests)
     uint32_t* d_order = nullptr;      // [max_chunks] start order of a batch with cost hints
@@ -369,9 +370,31 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         n_work[k] = m;
         skipped_begin[k + 1] = static_cast<uint32_t>(uniform.size());
         // descending hint, ties in chunk order (the scheduler's LPT rule)
-        if (hinted)
+        if (hinted) {
             std::stable_sort(order.begin() + first, order.begin() + first + m,
                              [&](uint32_t a, uint32_t b) { return descs[first + a].cost_hint > descs[first + b].cost_hint; });
+            // A batch of a few heavy chunks among many light ones (the headline: 298 of 4096 cross the surface, the
+            // others only stream) is bound by HBM as a whole, and a heavy chunk leaves its SM's share of the bandwidth
+            // unused while its emission runs.  Started all at once, the heavy chunks leave most of the machine's
+            // bandwidth idle for their duration; spread over the start order, the SMs that stream take up what the
+            // emitting ones leave.  So: heavy = more than four times the median hint (no chunk of an all-surface
+            // batch is), placed evenly over the first `spread_pct` per cent of the start order, still heaviest
+            // first; the rest of the order is light chunks, so the launch does not end on a heavy one.
+            const uint32_t pct = ctx->spread_pct;
+            const uint32_t median = descs[first + order[first + m / 2]].cost_hint;
+            uint32_t heavy = 0;
+            while (heavy < m && static_cast<uint64_t>(descs[first + order[first + heavy]].cost_hint) > 4ull * median) ++heavy;
+            if (pct != 0 && heavy != 0 && heavy <= m / 4) {
+                const uint32_t span = std::max<uint32_t>(heavy, static_cast<uint32_t>(static_cast<uint64_t>(m) * pct / 100));
+                std::vector<uint32_t> mixed(m);
+                uint32_t h = 0, l = heavy;
+                for (uint32_t pos = 0; pos < m; ++pos) {
+                    const bool slot_of_heavy = h < heavy && pos == static_cast<uint32_t>(static_cast<uint64_t>(h) * span / heavy);
+                    mixed[pos] = slot_of_heavy ? order[first + h++] : (l < m ? order[first + l++] : order[first + h++]);
+                }
+                std::copy(mixed.begin(), mixed.end(), order.begin() + first);
+            }
+        }
     }
     // ---- too few chunks to fill the machine (one page, an edit frame): walk z-ranges of chunks instead -----------
     // Each chunk of the work list becomes up to MAX_PARTS consecutive items over the steps that can hold a dirty cell;
@@ -896,11 +919,15 @@ int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
 
 int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode) {
     if (!ctx) return HVX_E_INVALID_ARGUMENT;
-    if ((mode & 0xffu) > 2 || (mode & ~0x3ffu))
+    if ((mode & 0xffu) > 2 || (mode & ~0xff3ffu))
         return fail(ctx, HVX_E_INVALID_ARGUMENT, "debug mode must be 0 (off), 1 (stream only) or 2 (stream + sign bits), optionally | 0x100 (no split walk) | 0x200 (split a thin last wave)");
     ctx->debug_mode = mode & 0xffu;
     ctx->no_split = (mode & 0x100u) != 0;
     ctx->split_last_wave = (mode & 0x200u) != 0;
+    // bits 12..19: where the heavy chunks of a hinted batch go: 0 = default (75 per cent), 1..100 = that share of the
+    // start order, 255 = plain descending order
+    const uint32_t spread = (mode >> 12) & 0xffu;
+    ctx->spread_pct = spread == 0 ? 75u : spread == 255u ? 0u : std::min(spread, 100u);
     return HVX_OK;
 }
 

@@ -153,8 +153,11 @@ typedef struct {
     uint32_t transition_mask;   /* TransitionFace bits 0..5 (-X,+X,-Y,+Y,-Z,+Z) */
     uint32_t cost_hint;         /* scheduler input, 0 = unknown: a relative cost estimate, e.g. the chunk's vertex
                                    count at its last extraction.  When any chunk of a batch carries a hint, the
-                                   batch is STARTED in descending hint order (longest first, so the kernel does not
-                                   end on a lone heavy chunk); slots, ranges and meshes do not depend on it. */
+                                   start order follows the hints: descending (longest first, so the kernel does not
+                                   end on a lone heavy chunk); a few heavy chunks among many light ones are spread
+                                   over the first three quarters of the order instead of starting all at once (the
+                                   SMs that only stream then use the bandwidth the emitting ones leave).  Slots,
+                                   ranges and meshes do not depend on the order. */
     uint32_t flags;             /* HVX_CHUNK_* */
     uint32_t _reserved;
 } hvx_chunk_desc;
@@ -211,7 +214,9 @@ uint64_t hvx_launch_count(const hvx_ctx* ctx);
 /* Roofline probes for the regular kernel (bench tools only): 0 = normal, 1 = stream the samples and do nothing else,
  * 2 = stream + sign bits.  Modes 1 and 2 produce no meshes.  | 0x100: never split chunks across CTAs (a dispatch with
  * fewer chunks than the machine has resident CTAs normally walks z-ranges of chunks; output is identical either way).
- * | 0x200: also split the chunks of a thin last wave of a batch of a few waves (measured slower, off by default). */
+ * | 0x200: also split the chunks of a thin last wave of a batch of a few waves (measured slower, off by default).
+ * | pct << 12 (bits 12..19): share of the start order the heavy chunks of a hinted batch are spread over
+ *   (0 = default 75, 255 = plain descending order). */
 int hvx_debug_set_mode(hvx_ctx* ctx, uint32_t mode);
 
 /* Device-side proof of an arithmetic shortcut (diagnostics; tests/test_gpu_regular.py): the regular kernel divides
