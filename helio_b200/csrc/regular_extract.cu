@@ -50,6 +50,14 @@
 #ifndef HVX_E32_CTAS
 #define HVX_E32_CTAS 3
 #endif
+// Edge 32: a step whose active rows are all FULL rows (a planar surface: every horizon-plan page of the planet set) is
+// cut into tiles of 32 cells = one row = exactly four full vertex passes for the usual four vertices per cell; every
+// other step keeps 30 cells per tile (a 32-cell tile of terrain spills a few vertices into a fifth pass).  Measured with
+// fixed tile sizes 30 / 31 / 32: planet set 2.36 / 2.35 / 2.10 ms, 4096 terrain pages 0.173 / 0.172 / 0.179 ms.
+// Edge 64 has no shared memory left for the larger owner map.
+#ifndef HVX_E32_WIDE_TILES
+#define HVX_E32_WIDE_TILES 1
+#endif
 
 namespace hvx {
 
@@ -957,7 +965,7 @@ struct SmemD {
     alignas(16) uint8_t class_index[16 * 16];
     uint16_t vertex_base[256];             // first entry of a case's run in vertex_packed
     uint8_t vertex_packed[1536];           // edge codes (corner pair) of every case's vertices, back to back
-    uint8_t owner[C::NW][360];             // per emission warp: tile vertex -> lane (cell) that owns it (TC * 12)
+    uint8_t owner[C::NW][C::E == 32 ? 384 : 360];  // per emission warp: tile vertex -> lane (cell) that owns it (tile cells * 12)
 };
 
 template <class C>
@@ -970,6 +978,7 @@ struct DecoupledCfg {
     // cells per tile: a typical surface cell has 4 vertices, so 30 cells fill four 32-lane vertex
     // passes (~120 vertices); 32 cells would spill a handful of vertices into a fifth
     static constexpr int TC = 30;
+    static constexpr bool WIDE = C::E == 32 && HVX_E32_WIDE_TILES != 0;  // full-row steps use 32-cell tiles (see HVX_E32_WIDE_TILES)
     static_assert(TC * 12 <= 360, "owner map size");
     static_assert(C::STEP_ROWS == CW * 32, "one classifying lane per cell row");
     static_assert(C::FULL % GB == 0 && NG <= 18, "the slab's ballot blocks split into whole groups");
@@ -1231,6 +1240,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         }
                         sm.active[slot][r] = act;
                         sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
+                        // bit 31 of the warp's total: some active row of its 32 is not a full row
+                        if (D::WIDE && __any_sync(0xffffffffu, act != 0 && act != ROWMASK)) incl |= 0x80000000u;
                     }
                     if (lane == 31) sm.wtot[slot][warp] = incl;
                     HVX_JIT(22);
@@ -1261,7 +1272,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             HVX_WAIT_END();
             *reinterpret_cast<uint4*>(&sm.queue[qi][0]) = make_uint4(w0, w1, w2, w3);
             *reinterpret_cast<uint4*>(&sm.queue[qi][4]) = make_uint4(w4, w5, w6, w7);
-            sm.q_ctr[qi] = (w0 >> 30) == QK_STEP ? ((w2 + D::TC - 1u) / D::TC) << 16 : (w0 >> 30) << 30;
+            const uint32_t tile_cells = (w0 >> 24) & 1u ? 32u : static_cast<uint32_t>(D::TC);
+            sm.q_ctr[qi] = (w0 >> 30) == QK_STEP ? ((w2 + tile_cells - 1u) / tile_cells) << 16 : (w0 >> 30) << 30;
             sm.q_done[qi] = 0u;
             HVX_JIT(11);
             mbar_arrive(&sm.q_bar[qi]);  // release: the entry is visible to whoever sees the phase flip
@@ -1300,12 +1312,16 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 } else {
                     if (prev_empty) mbar_arrive(&sm.empty_bar[slot]);  // "step j-1 done" for slab j, now that it is current
                     uint32_t cum[4] = {0, 0, 0, 0};
-                    uint32_t n = 0;
+                    uint32_t n = 0, ragged = 0;
 #pragma unroll
                     for (int i = 0; i < CW; ++i) {
-                        n += sm.wtot[slot][i];
+                        const uint32_t w = sm.wtot[slot][i];
+                        ragged |= w >> 31;
+                        n += w & 0x7fffffffu;
                         cum[i] = n;
                     }
+                    const uint32_t wide = D::WIDE && ragged == 0u ? 1u : 0u;  // every active row is full: 32-cell tiles
+                    const uint32_t tc = wide ? 32u : static_cast<uint32_t>(D::TC);
                     if (n == 0) {
                         mbar_arrive(&sm.empty_bar[slot]);       // "step j done" for slab j
                         mbar_arrive(&sm.empty_bar[prev_slot]);  // "step j done" for slab j-1
@@ -1314,9 +1330,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         const uint32_t next_parity = (slot + 1 == RS ? round + 1u : round) & 1u;
                         const uint32_t w0 = static_cast<uint32_t>(slot) | (static_cast<uint32_t>(j) << 4) | (tmask << 12) |
                                             ((kc & 15u) << 18) | ((tile_total == chunk_first_tile ? 1u : 0u) << 22) |
-                                            (next_parity << 23) | (QK_STEP << 30);
+                                            (next_parity << 23) | (wide << 24) | (QK_STEP << 30);
                         publish(w0, chunk, n, tile_total, cum[0], cum[1], cum[2], it.tag);
-                        tile_total += (n + D::TC - 1u) / D::TC;
+                        tile_total += (n + tc - 1u) / tc;
                         chunk_cells += n;
                         prev_empty = false;
                     }
@@ -1459,7 +1475,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
             const uint32_t n_cells = e0.z, tile_base = e0.w;
             const uint32_t cum[3] = {e1.x, e1.y, e1.z};
             const bool emit = do_emit && (!SPLIT || ((e1.w >> 29) & 1u));  // SPLIT: the counting walk writes no mesh
-            const uint32_t ntiles = (n_cells + D::TC - 1u) / D::TC;
+            const uint32_t tc = D::WIDE && ((e0.x >> 24) & 1u) ? 32u : static_cast<uint32_t>(D::TC);  // cells per tile of this step
+            const uint32_t ntiles = tc == 32u ? (n_cells + 31u) >> 5 : (n_cells + D::TC - 1u) / D::TC;
             HVX_JIT(2);
             // "are there tiles left" must be ONE decision per warp: the counter moves while the lanes look at it, and
             // a warp whose lanes disagreed would meet itself in the collectives below from two different entries
@@ -1505,8 +1522,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                     const uint32_t seq = tile_base + t;
                     const bool first = first_of_chunk != 0u && t == 0u;
                     HVX_CHECK(slot < RS && st >= 1 && st < C::NSLAB && seq - tile_base < ntiles, 7u, chunk, st | (slot << 8), seq, t, ntiles);
-                    const uint32_t r = D::TC * t + static_cast<uint32_t>(lane);
-                    const bool valid = lane < D::TC && r < n_cells;
+                    const uint32_t r = tc * t + static_cast<uint32_t>(lane);
+                    const bool valid = static_cast<uint32_t>(lane) < tc && r < n_cells;
                     uint32_t rec = 0, packed = 0, info = 0, vbase = 0;
                     if (valid) {
                         // locate: classifying warp -> row (largest row whose first rank <= mine) -> k-th set bit
