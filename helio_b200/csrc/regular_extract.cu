@@ -50,9 +50,10 @@
 #ifndef HVX_E32_CTAS
 #define HVX_E32_CTAS 3
 #endif
-// Edge 32: a step whose active cells are whole layers of FULL rows (a planar surface: every horizon-plan page of the
-// planet set) is cut into tiles of 32 cells = one row = exactly four full vertex passes for its four vertices per cell;
-// every other step keeps 30 cells per tile (a 32-cell tile of terrain spills a few vertices into a fifth pass).  Measured with
+// Edge 32: a step whose active rows are all FULL rows (a planar surface: every horizon-plan page of the planet set
+// crosses it in two rows of 32 cells per step) is cut into tiles of 32 cells = one row = exactly four full vertex passes
+// for its four vertices per cell -- two tiles instead of 30 + 30 + 4; every other step keeps 30 cells per tile (a
+// 32-cell tile of terrain spills a few vertices into a fifth pass).  Measured with
 // fixed tile sizes 30 / 31 / 32: planet set 2.36 / 2.35 / 2.10 ms, 4096 terrain pages 0.173 / 0.172 / 0.179 ms.
 // Edge 64 has no shared memory left for the larger owner map.
 #ifndef HVX_E32_WIDE_TILES
@@ -1240,8 +1241,6 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         }
                         sm.active[slot][r] = act;
                         sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
-                        // bit 31 of the warp's total: some active row of its 32 is not a full row
-                        if (D::WIDE && __any_sync(0xffffffffu, act != 0 && act != ROWMASK)) incl |= 0x80000000u;
                     }
                     if (lane == 31) sm.wtot[slot][warp] = incl;
                     HVX_JIT(22);
@@ -1312,18 +1311,27 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 } else {
                     if (prev_empty) mbar_arrive(&sm.empty_bar[slot]);  // "step j-1 done" for slab j, now that it is current
                     uint32_t cum[4] = {0, 0, 0, 0};
-                    uint32_t n = 0, ragged = 0;
+                    uint32_t n = 0;
 #pragma unroll
                     for (int i = 0; i < CW; ++i) {
-                        const uint32_t w = sm.wtot[slot][i];
-                        ragged |= w >> 31;
-                        n += w & 0x7fffffffu;
+                        n += sm.wtot[slot][i];
                         cum[i] = n;
                     }
-                    // whole cell layers of full rows (a planar surface): 32-cell tiles.  Full rows alone are not enough --
-                    // gently sloping terrain has them too, with five or six vertices in some cells, and a 32-cell tile
-                    // then spills into a fifth vertex pass (4096 terrain pages: 0.178 instead of 0.173 ms)
-                    const uint32_t wide = D::WIDE && ragged == 0u && (n & (E * E - 1)) == 0u ? 1u : 0u;
+                    // Every active row of the step a FULL row (a planar surface: 64 cells in two rows for a horizon-plan
+                    // page): 32-cell tiles, one per row -- two tiles instead of 30 + 30 + 4.  Looked for here, by the one
+                    // scheduler lane and only when the count allows it (a multiple of 32), not by the classifying warps:
+                    // their per-slab chain is what bounds a page (a vote there cost the terrain batch 3 %).
+                    uint32_t wide = 0u;
+                    if (D::WIDE && n != 0u && (n & 31u) == 0u) {
+                        wide = 1u;
+                        for (int r = 0; r < C::STEP_ROWS; ++r) {
+                            const uint64_t act = sm.active[slot][r];
+                            if (act != 0ull && act != ROWMASK) {
+                                wide = 0u;
+                                break;
+                            }
+                        }
+                    }
                     const uint32_t tc = wide ? 32u : static_cast<uint32_t>(D::TC);
                     if (n == 0) {
                         mbar_arrive(&sm.empty_bar[slot]);       // "step j done" for slab j
