@@ -1232,7 +1232,9 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                 if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
                             act &= dirty_x;
                         }
-                        const uint32_t cnt = static_cast<uint32_t>(__popcll(act));
+                        // the scan carries a second count for free: rows that are active but not full (bits 16..)
+                        const uint32_t cnt = static_cast<uint32_t>(__popcll(act)) +
+                                             (D::WIDE && act != 0ull && act != ROWMASK ? 0x10000u : 0u);
                         incl = cnt;
 #pragma unroll
                         for (int d = 1; d < 32; d <<= 1) {
@@ -1240,7 +1242,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             if (lane >= d) incl += up;
                         }
                         sm.active[slot][r] = act;
-                        sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
+                        sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);  // the low half: cells before this row
                     }
                     if (lane == 31) sm.wtot[slot][warp] = incl;
                     HVX_JIT(22);
@@ -1311,27 +1313,17 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 } else {
                     if (prev_empty) mbar_arrive(&sm.empty_bar[slot]);  // "step j-1 done" for slab j, now that it is current
                     uint32_t cum[4] = {0, 0, 0, 0};
-                    uint32_t n = 0;
+                    uint32_t n = 0, ragged = 0;
 #pragma unroll
                     for (int i = 0; i < CW; ++i) {
-                        n += sm.wtot[slot][i];
+                        const uint32_t w = sm.wtot[slot][i];  // cells | rows that are active but not full << 16
+                        ragged += w >> 16;
+                        n += w & 0xffffu;
                         cum[i] = n;
                     }
                     // Every active row of the step a FULL row (a planar surface: 64 cells in two rows for a horizon-plan
-                    // page): 32-cell tiles, one per row -- two tiles instead of 30 + 30 + 4.  Looked for here, by the one
-                    // scheduler lane and only when the count allows it (a multiple of 32), not by the classifying warps:
-                    // their per-slab chain is what bounds a page (a vote there cost the terrain batch 3 %).
-                    uint32_t wide = 0u;
-                    if (D::WIDE && n != 0u && (n & 31u) == 0u) {
-                        wide = 1u;
-                        for (int r = 0; r < C::STEP_ROWS; ++r) {
-                            const uint64_t act = sm.active[slot][r];
-                            if (act != 0ull && act != ROWMASK) {
-                                wide = 0u;
-                                break;
-                            }
-                        }
-                    }
+                    // page): 32-cell tiles, one per row -- two tiles instead of 30 + 30 + 4.
+                    const uint32_t wide = D::WIDE && ragged == 0u ? 1u : 0u;
                     const uint32_t tc = wide ? 32u : static_cast<uint32_t>(D::TC);
                     if (n == 0) {
                         mbar_arrive(&sm.empty_bar[slot]);       // "step j done" for slab j
