@@ -50,10 +50,11 @@
 #ifndef HVX_E32_CTAS
 #define HVX_E32_CTAS 3
 #endif
-// Edge 32: a step whose active rows are all FULL rows (a planar surface: every horizon-plan page of the planet set
-// crosses it in two rows of 32 cells per step) is cut into tiles of 32 cells = one row = exactly four full vertex passes
-// for its four vertices per cell -- two tiles instead of 30 + 30 + 4; every other step keeps 30 cells per tile (a
-// 32-cell tile of terrain spills a few vertices into a fifth pass).  Measured with
+// Edge 32: a step whose active rows are all FLAT rows -- full, and every cell of the row the same case (a planar
+// surface: every horizon-plan page of the planet set crosses it in two rows of 32 cells per step) -- is cut into tiles
+// of 32 cells = one row = exactly four full vertex passes for its four vertices per cell, two tiles instead of
+// 30 + 30 + 4; every other step keeps 30 cells per tile (a 32-cell tile of terrain, where some cells carry five or six
+// vertices, spills into a fifth pass: full rows alone as the criterion cost the terrain batch 2 %).  Measured with
 // fixed tile sizes 30 / 31 / 32: planet set 2.36 / 2.35 / 2.10 ms, 4096 terrain pages 0.173 / 0.172 / 0.179 ms.
 // Edge 64 has no shared memory left for the larger owner map.
 #ifndef HVX_E32_WIDE_TILES
@@ -1232,9 +1233,13 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                 if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
                             act &= dirty_x;
                         }
-                        // the scan carries a second count for free: rows that are active but not full (bits 16..)
+                        // The scan carries a second count for free (bits 16..): active rows that are not "flat" -- full,
+                        // and every cell of the row the same case (each corner row equals itself shifted by one cell:
+                        // a** ^ b** == 0).  A flat row's cells all have the same vertex count, four for a planar crossing;
+                        // full rows of gently sloping terrain are not flat and keep the 30-cell tiles.
+                        const uint64_t bumps = ((rc.a00 ^ rc.b00) | (rc.a10 ^ rc.b10) | (rc.a01 ^ rc.b01) | (rc.a11 ^ rc.b11)) & ROWMASK;
                         const uint32_t cnt = static_cast<uint32_t>(__popcll(act)) +
-                                             (D::WIDE && act != 0ull && act != ROWMASK ? 0x10000u : 0u);
+                                             (D::WIDE && act != 0ull && (act != ROWMASK || bumps != 0ull) ? 0x10000u : 0u);
                         incl = cnt;
 #pragma unroll
                         for (int d = 1; d < 32; d <<= 1) {
@@ -1321,8 +1326,8 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                         n += w & 0xffffu;
                         cum[i] = n;
                     }
-                    // Every active row of the step a FULL row (a planar surface: 64 cells in two rows for a horizon-plan
-                    // page): 32-cell tiles, one per row -- two tiles instead of 30 + 30 + 4.
+                    // Every active row of the step a flat row (a planar surface: 64 cells in two rows for a horizon-plan
+                    // page): 32-cell tiles, one per row -- two tiles instead of 30 + 30 + 4, four full vertex passes each.
                     const uint32_t wide = D::WIDE && ragged == 0u ? 1u : 0u;
                     const uint32_t tc = wide ? 32u : static_cast<uint32_t>(D::TC);
                     if (n == 0) {
