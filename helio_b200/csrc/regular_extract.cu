@@ -50,12 +50,14 @@
 #ifndef HVX_E32_CTAS
 #define HVX_E32_CTAS 3
 #endif
-// Edge 32: a step whose active rows are all FLAT rows -- full, and every cell of the row the same case (a planar
-// surface: every horizon-plan page of the planet set crosses it in two rows of 32 cells per step) -- is cut into tiles
-// of 32 cells = one row = exactly four full vertex passes for its four vertices per cell, two tiles instead of
-// 30 + 30 + 4; every other step keeps 30 cells per tile (a 32-cell tile of terrain, where some cells carry five or six
-// vertices, spills into a fifth pass: full rows alone as the criterion cost the terrain batch 2 %).  Measured with
-// fixed tile sizes 30 / 31 / 32: planet set 2.36 / 2.35 / 2.10 ms, 4096 terrain pages 0.173 / 0.172 / 0.179 ms.
+// Edge 32: a step whose number of active cells is a multiple of 32 is cut into tiles of 32 cells instead of 30.  That
+// is every step of a planar surface (a horizon-plan page of the planet set crosses a step in two full rows: 64 cells =
+// two tiles of four full vertex passes each instead of 30 + 30 + 4) and one step in 32 of anything else, where a 32-cell
+// tile costs a fifth, nearly empty vertex pass (terrain cells carry five or six vertices here and there).  The rule
+// needs nothing from the front end, whose per-slab chain bounds a page: telling planar rows from terrain there was
+// tried three ways (a vote, a second count carried by the scan, a same-case-along-the-row test) and cost the terrain
+// batch 2-5 %.  Fixed tile sizes 30 / 31 / 32: planet set 2.36 / 2.35 / 2.10 ms, 4096 terrain pages 0.173 / 0.172 /
+// 0.179 ms.
 // Edge 64 has no shared memory left for the larger owner map.
 #ifndef HVX_E32_WIDE_TILES
 #define HVX_E32_WIDE_TILES 1
@@ -1233,13 +1235,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                                 if ((nib >> mx) & 1u) dirty_x |= ((1ull << C::QW) - 1ull) << (mx * C::QW);
                             act &= dirty_x;
                         }
-                        // The scan carries a second count for free (bits 16..): active rows that are not "flat" -- full,
-                        // and every cell of the row the same case (each corner row equals itself shifted by one cell:
-                        // a** ^ b** == 0).  A flat row's cells all have the same vertex count, four for a planar crossing;
-                        // full rows of gently sloping terrain are not flat and keep the 30-cell tiles.
-                        const uint64_t bumps = ((rc.a00 ^ rc.b00) | (rc.a10 ^ rc.b10) | (rc.a01 ^ rc.b01) | (rc.a11 ^ rc.b11)) & ROWMASK;
-                        const uint32_t cnt = static_cast<uint32_t>(__popcll(act)) +
-                                             (D::WIDE && act != 0ull && (act != ROWMASK || bumps != 0ull) ? 0x10000u : 0u);
+                        const uint32_t cnt = static_cast<uint32_t>(__popcll(act));
                         incl = cnt;
 #pragma unroll
                         for (int d = 1; d < 32; d <<= 1) {
@@ -1247,7 +1243,7 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                             if (lane >= d) incl += up;
                         }
                         sm.active[slot][r] = act;
-                        sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);  // the low half: cells before this row
+                        sm.rowrank[slot][r] = static_cast<uint16_t>(incl - cnt);
                     }
                     if (lane == 31) sm.wtot[slot][warp] = incl;
                     HVX_JIT(22);
@@ -1318,17 +1314,14 @@ regular_extract_decoupled_kernel(const RegularParams p) {
                 } else {
                     if (prev_empty) mbar_arrive(&sm.empty_bar[slot]);  // "step j-1 done" for slab j, now that it is current
                     uint32_t cum[4] = {0, 0, 0, 0};
-                    uint32_t n = 0, ragged = 0;
+                    uint32_t n = 0;
 #pragma unroll
                     for (int i = 0; i < CW; ++i) {
-                        const uint32_t w = sm.wtot[slot][i];  // cells | rows that are active but not full << 16
-                        ragged += w >> 16;
-                        n += w & 0xffffu;
+                        n += sm.wtot[slot][i];
                         cum[i] = n;
                     }
-                    // Every active row of the step a flat row (a planar surface: 64 cells in two rows for a horizon-plan
-                    // page): 32-cell tiles, one per row -- two tiles instead of 30 + 30 + 4, four full vertex passes each.
-                    const uint32_t wide = D::WIDE && ragged == 0u ? 1u : 0u;
+                    // A step whose cell count is a multiple of 32 is cut into 32-cell tiles (see HVX_E32_WIDE_TILES)
+                    const uint32_t wide = D::WIDE && (n & 31u) == 0u ? 1u : 0u;
                     const uint32_t tc = wide ? 32u : static_cast<uint32_t>(D::TC);
                     if (n == 0) {
                         mbar_arrive(&sm.empty_bar[slot]);       // "step j done" for slab j
