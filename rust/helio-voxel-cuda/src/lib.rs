@@ -344,6 +344,17 @@ impl ChunkBatchExtractor {
         let status = unsafe { ffi::hvx_build_meshlets(self.ctx.raw, transition as c_int, n) };
         self.ctx.check(status, n as usize, 0, 0)
     }
+    /// One edit of the legacy edit ring (`GpuVoxelEdit`, crates/helio-voxel-core/src/gpu_types.rs:47-54) applied to the
+    /// resident samples of `pages`; returns each chunk's dirty microbricks (the mask `prepare` takes) and how many chunks
+    /// the edit touched (sphere-vs-box rule of `OctreeNode::mark_sphere_dirty`, octree.rs:139-173).
+    pub fn apply_edit(&self, edit: &ffi::hvx_voxel_edit, pages: &[[i64; 3]], lods: Option<&[u8]>) -> Result<(Vec<u64>, u32), TransvoxelGpuError> {
+        let mut dirty = vec![0u64; pages.len()];
+        let mut touched = 0u32;
+        let lod_ptr = lods.map_or(core::ptr::null(), |l| l.as_ptr());
+        let status = unsafe { ffi::hvx_apply_edit(self.ctx.raw, edit, pages.as_ptr() as *const i64, lod_ptr, pages.len() as u32,
+                                                   core::ptr::null_mut(), dirty.as_mut_ptr(), &mut touched) };
+        self.ctx.check(status, pages.len(), 0, 0).map(|_| (dirty, touched))
+    }
     /// Optional vertex-reuse output (off by default; the reference shares no vertices): merges the bit-identical vertex
     /// records of chunks `[0, n)` of the last extraction in place, indices follow, ranges / emitted_vertices shrink.
     pub fn weld_meshes(&self, n: u32, transition: bool) -> Result<(), TransvoxelGpuError> {
@@ -370,8 +381,16 @@ impl<'a> GpuSurfaceSampler<'a> {
     /// `table` / `atlas`: host slices or device memory (detected by the library); `jobs`: host.
     pub fn dispatch(&self, residency: &ffi::hvx_residency, table: &[ffi::hvx_page_table_entry], atlas: *const u32, atlas_words: u64,
                     jobs: &[ffi::hvx_gather_job]) -> Result<(), TransvoxelGpuError> {
-        let status = unsafe { ffi::hvx_gather_surface(self.batch.ctx.raw, residency, table.as_ptr(), atlas, atlas_words, jobs.as_ptr(), jobs.len() as u32) };
+        let table_ptr = if table.is_empty() { core::ptr::null() } else { table.as_ptr() };  // empty: the table bound with bind_page_table
+        let status = unsafe { ffi::hvx_gather_surface(self.batch.ctx.raw, residency, table_ptr, atlas, atlas_words, jobs.as_ptr(), jobs.len() as u32) };
         self.batch.ctx.check(status, jobs.len(), 0, 0)
+    }
+    /// Upload the residency layer's page table once per publication (PV/src/table.rs:62-72); `dispatch` then takes an
+    /// empty `table` slice and reads the bound one.  An empty slice here unbinds.
+    pub fn bind_page_table(&self, table: &[ffi::hvx_page_table_entry]) -> Result<(), TransvoxelGpuError> {
+        let ptr = if table.is_empty() { core::ptr::null() } else { table.as_ptr() };
+        let status = unsafe { ffi::hvx_gather_bind_table(self.batch.ctx.raw, ptr, table.len() as u32) };
+        self.batch.ctx.check(status, table.len(), 0, 0)
     }
     pub fn counters(&self, n: usize) -> Result<Vec<ffi::hvx_gather_counters>, TransvoxelGpuError> {
         let mut out = vec![ffi::hvx_gather_counters::default(); n];
