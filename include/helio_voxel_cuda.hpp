@@ -252,7 +252,11 @@ class GpuSurfaceSampler {
                       TransvoxelGpuTransitionExtractorConfig transition = {})
         : ctx_(device, hvx_config{PAGE_EDGE, max_jobs, regular.max_vertices, regular.max_indices, transition.max_vertices,
                                   transition.max_indices, 0u, 0}) {}
-    /// prepare + encode for n jobs.  table: table_mask + 1 entries; atlas: linear R32Uint texels (host or device).
+    /// Upload the residency layer's page table once per publication (PV/src/table.rs:62-72); dispatch(table = nullptr)
+    /// then reads the bound table.  entries = 0 unbinds.
+    void bind_page_table(const hvx_page_table_entry* table, uint32_t entries) { ctx_.check(hvx_gather_bind_table(ctx_.get(), table, entries)); }
+    /// prepare + encode for n jobs.  table: table_mask + 1 entries, or nullptr for the bound table; atlas: linear R32Uint
+    /// texels (host or device).
     void dispatch(const hvx_residency& residency, const hvx_page_table_entry* table, const uint32_t* atlas,
                   uint64_t atlas_words, const hvx_gather_job* jobs, uint32_t n) {
         ctx_.check(hvx_gather_surface(ctx_.get(), &residency, table, atlas, atlas_words, jobs, n));
