@@ -26,7 +26,7 @@ from .extractor import (EXTRACTION_SAMPLE_COUNT, TRANSITION_ALL_FACE_SLAB_SAMPLE
                         TransvoxelGpuTransitionExtractorConfig)
 from .gather import (GATHER_JOB_DTYPE, PAGE_TABLE_ENTRY_DTYPE, RESIDENCY_UNIFORM_DTYPE, GpuLookupKey, GpuSurfaceSampler,
                      PageTable, PageTableError, gather_job, residency_uniform)
-from .lod import HorizonLodFixturePlan, TerrainLodTopology, TerrainLodTopologyStats, chunk_cost, partition_chunks
+from .lod import HorizonLodFixturePlan, TerrainLodTopology, TerrainLodTopologyStats, chunk_cost, partition_chunks, start_order
 from .publish import (DRAW_INDEXED_INDIRECT_DTYPE, DRAW_PAGE_DTYPE, PAGE_META_DTYPE, SURFACE_FEEDBACK_DTYPE, SURFACE_JOB_DTYPE,
                       SURFACE_STATE_DTYPE, SurfacePublisher, max_meshlets_for_indices)
 from .types import (MAX_ADDRESSABLE_LOD, PAGE_EDGE, TRANSITION_FACE_MASK, CellWord, ExtractionFixtureKind,

@@ -170,7 +170,7 @@ class ExtractionPublisherCounters(C.Structure):
 # every symbol include/hvx.h declares; tests assert the library exports all of them
 EXPORTS = [
     "hvx_create", "hvx_destroy", "hvx_last_error", "hvx_status_name", "hvx_abi_version", "hvx_get_config",
-    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_regular_kernel_name", "hvx_selftest_edge_parameter", "hvx_selftest_inv_sqrt",
+    "hvx_allocated_bytes", "hvx_set_stream", "hvx_get_stream", "hvx_synchronize", "hvx_launch_count", "hvx_debug_set_mode", "hvx_start_order", "hvx_regular_kernel_name", "hvx_selftest_edge_parameter", "hvx_selftest_inv_sqrt",
     "hvx_fill_density", "hvx_fill_slabs", "hvx_apply_edit", "hvx_extract_regular", "hvx_extract_regular_to_host", "hvx_classify_regular", "hvx_extract_transition",
     "hvx_build_meshlets", "hvx_weld_meshes", "hvx_gather_surface", "hvx_gather_bind_table", "hvx_publisher_create", "hvx_publisher_destroy", "hvx_publish_surfaces",
     "hvx_refresh_visibility", "hvx_publisher_buffer", "hvx_publisher_buffer_bytes", "hvx_publisher_read", "hvx_publisher_write",
@@ -220,6 +220,7 @@ def load() -> C.CDLL:
     L.hvx_launch_count.argtypes = [vp]
     L.hvx_launch_count.restype = C.c_uint64
     L.hvx_debug_set_mode.argtypes = [vp, C.c_uint32]
+    L.hvx_start_order.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     L.hvx_regular_kernel_name.argtypes = [vp, C.c_int]
     L.hvx_regular_kernel_name.restype = C.c_char_p
     L.hvx_selftest_edge_parameter.argtypes = [C.c_int, u64p, u32p]

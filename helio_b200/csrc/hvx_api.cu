@@ -303,6 +303,32 @@ int grow_device(hvx_ctx* ctx, void** ptr, uint64_t* have, uint64_t need, cudaStr
     return HVX_OK;
 }
 
+// The order in which the chunks of a hinted batch are started (hvx_start_order exposes it for tests).
+// Descending hint, ties in chunk order: the scheduler's LPT rule, so the launch does not end on a lone heavy chunk.
+// A batch of a few heavy chunks among many light ones (the headline: 298 of 4096 cross the surface, the others only
+// stream) is bound by HBM as a whole, and a heavy chunk leaves its SM's share of the bandwidth unused while its
+// emission runs.  Started all at once, the heavy chunks leave most of the machine's bandwidth idle for their duration;
+// spread over the start order, the SMs that stream take up what the emitting ones leave.  So: heavy = more than four
+// times the median hint (no chunk of an all-surface batch is), placed evenly over the first `pct` per cent of the
+// start order, still heaviest first; the rest of the order is light chunks.  pct = 0: plain descending order.
+template <class HintOf>
+void start_order(uint32_t* order, uint32_t m, HintOf hint_of, uint32_t pct) {
+    std::stable_sort(order, order + m, [&](uint32_t a, uint32_t b) { return hint_of(a) > hint_of(b); });
+    if (m == 0 || pct == 0) return;
+    const uint32_t median = hint_of(order[m / 2]);
+    uint32_t heavy = 0;
+    while (heavy < m && static_cast<uint64_t>(hint_of(order[heavy])) > 4ull * median) ++heavy;
+    if (heavy == 0 || heavy > m / 4) return;
+    const uint32_t span = std::max<uint32_t>(heavy, static_cast<uint32_t>(static_cast<uint64_t>(m) * std::min(pct, 100u) / 100));
+    std::vector<uint32_t> mixed(m);
+    uint32_t h = 0, l = heavy;
+    for (uint32_t pos = 0; pos < m; ++pos) {
+        const bool slot_of_heavy = h < heavy && pos == static_cast<uint32_t>(static_cast<uint64_t>(h) * span / heavy);
+        mixed[pos] = slot_of_heavy ? order[h++] : (l < m ? order[l++] : order[h++]);
+    }
+    std::copy(mixed.begin(), mixed.end(), order);
+}
+
 // One regular dispatch over n chunks.
 //   * device-resident samples (or the ctx arena): one launch.
 //   * HOST samples: the batch is cut into sub-batches of ~256 MiB.  Sub-batch k is copied on the copy stream
@@ -370,31 +396,7 @@ int run_regular(hvx_ctx* ctx, const uint32_t* samples, uint64_t words, const hvx
         n_work[k] = m;
         skipped_begin[k + 1] = static_cast<uint32_t>(uniform.size());
         // descending hint, ties in chunk order (the scheduler's LPT rule)
-        if (hinted) {
-            std::stable_sort(order.begin() + first, order.begin() + first + m,
-                             [&](uint32_t a, uint32_t b) { return descs[first + a].cost_hint > descs[first + b].cost_hint; });
-            // A batch of a few heavy chunks among many light ones (the headline: 298 of 4096 cross the surface, the
-            // others only stream) is bound by HBM as a whole, and a heavy chunk leaves its SM's share of the bandwidth
-            // unused while its emission runs.  Started all at once, the heavy chunks leave most of the machine's
-            // bandwidth idle for their duration; spread over the start order, the SMs that stream take up what the
-            // emitting ones leave.  So: heavy = more than four times the median hint (no chunk of an all-surface
-            // batch is), placed evenly over the first `spread_pct` per cent of the start order, still heaviest
-            // first; the rest of the order is light chunks, so the launch does not end on a heavy one.
-            const uint32_t pct = ctx->spread_pct;
-            const uint32_t median = descs[first + order[first + m / 2]].cost_hint;
-            uint32_t heavy = 0;
-            while (heavy < m && static_cast<uint64_t>(descs[first + order[first + heavy]].cost_hint) > 4ull * median) ++heavy;
-            if (pct != 0 && heavy != 0 && heavy <= m / 4) {
-                const uint32_t span = std::max<uint32_t>(heavy, static_cast<uint32_t>(static_cast<uint64_t>(m) * pct / 100));
-                std::vector<uint32_t> mixed(m);
-                uint32_t h = 0, l = heavy;
-                for (uint32_t pos = 0; pos < m; ++pos) {
-                    const bool slot_of_heavy = h < heavy && pos == static_cast<uint32_t>(static_cast<uint64_t>(h) * span / heavy);
-                    mixed[pos] = slot_of_heavy ? order[first + h++] : (l < m ? order[first + l++] : order[first + h++]);
-                }
-                std::copy(mixed.begin(), mixed.end(), order.begin() + first);
-            }
-        }
+        if (hinted) start_order(order.data() + first, m, [&](uint32_t i) { return descs[first + i].cost_hint; }, ctx->spread_pct);
     }
     // ---- too few chunks to fill the machine (one page, an edit frame): walk z-ranges of chunks instead -----------
     // Each chunk of the work list becomes up to MAX_PARTS consecutive items over the steps that can hold a dirty cell;
@@ -914,6 +916,14 @@ int hvx_set_stream(hvx_ctx* ctx, void* cuda_stream) {
     HVX_CUDA(ctx, cudaEventRecord(ctx->handover, ctx->stream));
     HVX_CUDA(ctx, cudaStreamWaitEvent(next, ctx->handover, 0));
     ctx->stream = next;
+    return HVX_OK;
+}
+
+int hvx_start_order(const uint32_t* cost_hints, uint32_t n, uint32_t spread_pct, uint32_t* order_out) {
+    if (n != 0 && (!cost_hints || !order_out)) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "hvx_start_order: NULL argument");
+    if (spread_pct > 100u) return fail(nullptr, HVX_E_INVALID_ARGUMENT, "spread_pct %u is not a percentage", spread_pct);
+    for (uint32_t i = 0; i < n; ++i) order_out[i] = i;
+    start_order(order_out, n, [&](uint32_t i) { return cost_hints[i]; }, spread_pct);
     return HVX_OK;
 }
 

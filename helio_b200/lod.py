@@ -122,3 +122,15 @@ def partition_chunks(costs, ranks):
     if status != _ffi.HVX_OK:
         raise_for_status(status, "invalid partition request")
     return owner
+
+
+def start_order(cost_hints, spread_pct=75):
+    """The order in which hvx_extract_regular starts the chunks of a hinted batch (hvx_start_order): descending hint,
+    a few heavy chunks among many light ones spread over the first ``spread_pct`` per cent of the order."""
+    import numpy as np
+    hints = np.ascontiguousarray(cost_hints, dtype=np.uint32)
+    order = np.zeros(hints.size, dtype=np.uint32)
+    status = _ffi.load().hvx_start_order(hints.ctypes.data, hints.size, int(spread_pct), order.ctypes.data)
+    if status != _ffi.HVX_OK:
+        raise_for_status(status, "invalid start-order request")
+    return order

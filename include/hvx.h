@@ -211,6 +211,13 @@ int hvx_synchronize(hvx_ctx* ctx);
 const char* hvx_regular_kernel_name(const hvx_ctx* ctx, int partial);
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches). */
 uint64_t hvx_launch_count(const hvx_ctx* ctx);
+/* The order in which hvx_extract_regular starts the chunks of a batch that carries cost hints (host-only; for tests and
+ * for callers that want to see the schedule): order_out[k] = index of the k-th chunk started.  Descending hint, ties in
+ * index order; when a few chunks are heavy (more than four times the median hint, at most a quarter of the batch) they
+ * are placed evenly over the first spread_pct per cent of the order instead of all first -- the library uses 75;
+ * 0 = plain descending order. */
+int hvx_start_order(const uint32_t* cost_hints, uint32_t n, uint32_t spread_pct, uint32_t* order_out);
+
 /* Roofline probes for the regular kernel (bench tools only): 0 = normal, 1 = stream the samples and do nothing else,
  * 2 = stream + sign bits.  Modes 1 and 2 produce no meshes.  | 0x100: never split chunks across CTAs (a dispatch with
  * fewer chunks than the machine has resident CTAs normally walks z-ranges of chunks; output is identical either way).

@@ -240,3 +240,35 @@ def test_planet_scale_page_set_is_reproducible_and_partitions_evenly():
         load = np.array([costs[owner == r].sum() for r in range(ranks)], dtype=np.float64)
         assert set(owner) == set(range(ranks))
         assert load.max() - load.min() <= float(costs.max()), (ranks, load)
+
+
+def test_start_order_of_a_hinted_batch():
+    """hvx_start_order (the schedule hvx_extract_regular derives from hvx_chunk_desc.cost_hint): a permutation; descending
+    hints when the batch is uniform or the spread is off; a few heavy chunks among many light ones are spread evenly
+    over the first spread_pct per cent, heaviest first, and the order ends on light chunks."""
+    rng = np.random.default_rng(3)
+    # the headline's shape: 298 heavy of 4096
+    hints = np.zeros(4096, dtype=np.uint32)
+    heavy_ids = rng.choice(4096, 298, replace=False)
+    hints[heavy_ids] = rng.integers(15_000, 30_000, 298)
+    plain = H.start_order(hints, 0)
+    assert sorted(plain.tolist()) == list(range(4096))
+    assert np.all(np.diff(hints[plain].astype(np.int64)) <= 0), "descending"
+    assert np.array_equal(plain[:298], sorted(heavy_ids, key=lambda i: (-int(hints[i]), i)))   # ties in index order
+    spread = H.start_order(hints, 75)
+    assert sorted(spread.tolist()) == list(range(4096))
+    pos = np.flatnonzero(hints[spread] > 0)
+    assert len(pos) == 298 and pos[0] == 0 and pos[-1] < 0.75 * 4096
+    assert np.all(np.diff(hints[spread][pos].astype(np.int64)) <= 0), "heavy chunks still heaviest first"
+    gaps = np.diff(pos)
+    assert gaps.min() >= 10 and gaps.max() <= 11, "evenly spread (3072 / 298 = 10.3)"
+    assert np.all(hints[spread][int(0.75 * 4096):] == 0), "the order ends on light chunks"
+    # an all-surface batch has no heavy chunk (nothing above four times the median): plain descending order
+    uniform = rng.integers(20_000, 26_000, 500).astype(np.uint32)
+    assert np.array_equal(H.start_order(uniform, 75), H.start_order(uniform, 0))
+    # more than a quarter heavy: not "a few"
+    many = np.where(np.arange(100) % 3 == 0, 5000, 1).astype(np.uint32)
+    assert np.array_equal(H.start_order(many, 75), H.start_order(many, 0))
+    assert len(H.start_order(np.zeros(0, dtype=np.uint32))) == 0
+    with pytest.raises(H.HvxError):
+        H.start_order(hints, 101)
