@@ -918,6 +918,12 @@ __device__ __forceinline__ int select_bit32(uint32_t w, uint32_t k) {
 //   * chunk totals travel with the chain: whoever handles the last tile of a step stores the
 //     inclusive totals in chunk_total[] before publishing; a CHUNK_END queue entry tells one
 //     emission warp to wait for the final value and write the chunk's counter records.
+//   * THE RULE every wait obeys: a warp touches shared state that can be recycled -- a queue entry, a step's
+//     slabs and their barriers, a prefix word -- only while something it holds keeps that state from being
+//     recycled: its missing q_free arrival (the entry), a pulled tile that is not done (the step's slabs), the
+//     strictly ordered publication of the chain (prefix words), the queue depth (chunk_total).  An emission warp
+//     decides "nothing to do here" from the entry's one state word (kind | tiles << 16 | next tile) and waits for
+//     slab s+1 only after its first successful pull of a tile of step s.
 // =============================================================================================
 // Partially dirty chunks (the incremental-edit path): which steps can hold a dirty cell, and which slabs those
 // steps' classification (slabs s-1, s) and emission window (slabs s-1, s, s+1) read.  Dirty bit = mx + 4 my + 16 mz,
